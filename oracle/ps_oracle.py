@@ -1,0 +1,288 @@
+"""CPU oracle for the tools21cm power-spectrum path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a numpy/scipy *restatement* of the algorithm in the reference
+``src/tools21cm/power_spectrum.py`` (tools21cm v2.4.0).  It is the checker the
+CUDA path is compared against; it is never imported by the product package
+``tools21cm_b200``.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.
+
+Parity pin: the reference holds no golden vectors for this path (its tests are
+unseeded slope checks, ``tests/test_PowerSpectrum.py:10-48``).  This oracle is
+therefore pinned against outputs of the reference itself, generated in the
+build container by ``tests/golden/make_golden.py`` and committed under
+``tests/golden/*.npz`` (``tests/test_oracle_golden.py`` checks them bit-for-bit
+for mode counts and to 1e-13 for powers).
+
+The third-party arithmetic the reference leans on is kept identical on purpose:
+``scipy.fftpack.fftn/fftshift`` (reference ``power_spectrum.py:45,85-86``),
+``numpy.histogram`` (``:128,131``) and ``numpy.mean`` (``:430``).  Neither numpy
+nor scipy is pinned by the reference (``requirements.txt:2-3``); the versions in
+this image are numpy 2.3 / scipy 1.18.
+
+Every function cites the reference lines it follows.  Arithmetic order matters
+for bit-exact mode counts (see ``k_axis`` and ``k_magnitude``).
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy import fftpack
+
+# reference conv.py:10-11 with const.py:37 (h = 0.7): default comoving box in Mpc
+DEFAULT_BOX_MPC = 244.0 / 0.7
+
+
+# --------------------------------------------------------------------------
+# geometry helpers
+# --------------------------------------------------------------------------
+def box_lengths(box_dims, shape):
+    """Per-axis box lengths.  Reference ``_get_dims`` power_spectrum.py:522-534:
+    None -> default box on every axis, scalar -> repeated, iterable -> as is."""
+    if box_dims is None:
+        return [DEFAULT_BOX_MPC] * len(shape)
+    if not hasattr(box_dims, "__iter__"):
+        return [box_dims] * len(shape)
+    return box_dims
+
+
+def axis_centre(n, ndim):
+    """Index of the k=0 sample on the fftshifted grid as the reference defines it.
+
+    3-D (power_spectrum.py:471-472): n/2 for even n, (n-1)/2 for odd n.
+    1-D / 2-D (power_spectrum.py:458,463): (n-1)/2 for every n (a reference quirk
+    that mis-centres even-length 1-D/2-D maps; reproduced deliberately)."""
+    if ndim == 3:
+        return n / 2 if n % 2 == 0 else (n - 1) / 2
+    return (n - 1) / 2.0
+
+
+def k_axis(n, length, ndim):
+    """k component along one axis, float64, in fftshift index order.
+    Operation order of power_spectrum.py:473-475: ``2.*np.pi * (x-c) / L``
+    i.e. (2*pi*(x-c))/L with x int32 and c float64."""
+    x = np.arange(n, dtype="int32")
+    return 2.0 * np.pi * (x - axis_centre(n, ndim)) / length
+
+
+def k_components(shape, box_dims):
+    """Per-axis 1-D k tables (the reference builds full grids with np.indices,
+    power_spectrum.py:462,470; broadcasting these tables gives the same values)."""
+    nd = len(shape)
+    return [k_axis(shape[d], box_dims[d], nd) for d in range(nd)]
+
+
+def k_magnitude(shape, box_dims):
+    """|k| on the full fftshifted grid.  power_spectrum.py:477 sums squares left
+    to right: sqrt((kx**2 + ky**2) + kz**2).  1-D returns the signed kx itself
+    (power_spectrum.py:459-460)."""
+    kc = k_components(shape, box_dims)
+    nd = len(shape)
+    if nd == 1:
+        return kc, kc[0]
+    if nd == 2:
+        kx, ky = kc[0][:, None], kc[1][None, :]
+        return kc, np.sqrt(kx ** 2 + ky ** 2)
+    kx, ky, kz = kc[0][:, None, None], kc[1][None, :, None], kc[2][None, None, :]
+    return kc, np.sqrt(kx ** 2 + ky ** 2 + kz ** 2)
+
+
+def k_edges(kbins, box_dims, kmax, binning="log", breakpoint=0.1):
+    """Bin edges.  Reference ``_get_kbins`` power_spectrum.py:505-519.  Only a
+    Python ``int`` asks for automatic edges; anything else is returned as given.
+    kmin = 2*pi/min(L); kmax = max |k| on the grid."""
+    if isinstance(kbins, int):
+        kmin = 2.0 * np.pi / min(box_dims)
+        if binning == "linear":
+            return np.linspace(kmin, kmax, kbins + 1)
+        if binning == "log":
+            return 10 ** np.linspace(np.log10(kmin), np.log10(kmax), kbins + 1)
+        lin = np.linspace(kmin, kmax, kbins + 1)
+        log = 10 ** np.linspace(np.log10(kmin), np.log10(kmax), kbins + 1)
+        return np.hstack((lin[lin < breakpoint], log[log > breakpoint]))
+    return kbins
+
+
+def volume_scale(shape, box_dims):
+    """(V/prod N)^2 / V.  power_spectrum.py:50-52."""
+    boxvol = np.prod(box_dims)
+    pixelsize = boxvol / np.prod(shape)
+    return pixelsize ** 2 / boxvol
+
+
+# --------------------------------------------------------------------------
+# n-D spectra
+# --------------------------------------------------------------------------
+def power_spectrum_nd(input_array, box_dims=None, verbose=False, **kwargs):
+    """|FFT|^2 on the fftshifted grid, float64.  power_spectrum.py:24-54."""
+    if kwargs.get("boxsize") is not None:
+        box_dims = kwargs.get("boxsize")
+    box_dims = box_lengths(box_dims, input_array.shape)
+    ft = fftpack.fftshift(fftpack.fftn(input_array.astype("float64")))
+    ps = np.abs(ft) ** 2
+    ps *= volume_scale(input_array.shape, box_dims)
+    return ps
+
+
+def cross_power_spectrum_nd(input_array1, input_array2, box_dims, **kwargs):
+    """Re(F1 conj F2) on the fftshifted grid.  power_spectrum.py:57-95."""
+    assert input_array1.shape == input_array2.shape
+    if kwargs.get("boxsize") is not None:
+        box_dims = kwargs.get("boxsize")
+    box_dims = box_lengths(box_dims, input_array1.shape)
+    f1 = fftpack.fftshift(fftpack.fftn(input_array1.astype("float64")))
+    f2 = fftpack.fftshift(fftpack.fftn(input_array2.astype("float64")))
+    ps = np.real(f1) * np.real(f2) + np.imag(f1) * np.imag(f2)
+    ps *= volume_scale(input_array1.shape, box_dims)
+    return ps
+
+
+# --------------------------------------------------------------------------
+# binning
+# --------------------------------------------------------------------------
+def radial_average(input_array, box_dims, kbins=10, binning="log", breakpoint=0.1, **kwargs):
+    """Shell average by two histograms.  power_spectrum.py:98-134.  Bins are
+    half-open except the last, which is closed (np.histogram semantics); the
+    returned centres are arithmetic mid-points; counts come back as float64."""
+    if kwargs.get("boxsize") is not None:
+        box_dims = kwargs.get("boxsize")
+    _, k = k_magnitude(input_array.shape, box_dims)
+    edges = k_edges(kbins, box_dims, k.max(), binning=binning, breakpoint=breakpoint)
+    half = (edges[1:] - edges[:-1]) / 2.0
+    total = np.histogram(k.flatten(), bins=edges, weights=input_array.flatten())[0]
+    n_modes = np.histogram(k.flatten(), bins=edges)[0].astype("float")
+    with np.errstate(all="ignore"):  # reference __init__.py:94-95 silences FP warnings
+        total = total / n_modes
+    return total, edges[:-1] + half, n_modes
+
+
+def mu_of(kc, k, los_axis, absolute_mus):
+    """cos(theta) to the line of sight; NaN where k < 0.001.  power_spectrum.py:481-502."""
+    if los_axis not in (0, 1, 2):
+        raise Exception("Your space is not %d-dimensional!" % los_axis)
+    shape = [1, 1, 1]
+    shape[los_axis] = -1
+    klos = kc[los_axis].reshape(shape) * np.ones_like(k)
+    with np.errstate(all="ignore"):
+        mu = np.abs(klos / k) if absolute_mus else klos / np.abs(k)
+    mu[np.where(k < 0.001)] = np.nan
+    return mu
+
+
+def kperp_nonzero(shape, los_axis):
+    """Mask of modes off the k_perp = 0 line.  power_spectrum.py:563-575.  The
+    comparison is against N/2 as a float, so it never matches for odd N."""
+    idx = np.indices(shape)
+    perp = [a for a in (0, 1, 2) if a != los_axis] if los_axis in (0, 1) else [0, 1]
+    on_line = (idx[perp[0]] == shape[perp[0]] / 2) * (idx[perp[1]] == shape[perp[1]] / 2)
+    return np.invert(on_line)
+
+
+def mu_binning(powerspectrum, los_axis=0, mubins=20, kbins=10, box_dims=None, weights=None,
+               exclude_zero_modes=True, binning="log", absolute_mus=True):
+    """(k, mu) averages; every bin half-open in both k and mu.  power_spectrum.py:380-435.
+    Like the reference this zeroes the centre sample of its input in place (:414)."""
+    if weights is not None:
+        raise ValueError("weights are not usable in the reference either (power_spectrum.py:386,433)")
+    assert len(powerspectrum.shape) == 3
+    kc, k = k_magnitude(powerspectrum.shape, box_dims)
+    mu = mu_of(kc, k, los_axis, absolute_mus)
+    edges = k_edges(kbins, box_dims, k.max(), binning=binning)
+    half_k = (edges[1:] - edges[:-1]) / 2.0
+    nk = len(edges) - 1
+    good = kperp_nonzero(powerspectrum.shape, los_axis) if exclude_zero_modes \
+        else np.ones(powerspectrum.shape, dtype=bool)
+    if isinstance(mubins, int):
+        mubins = np.linspace(0.0 if absolute_mus else -1.0, 1.0, mubins + 1)
+    half_mu = (mubins[1:] - mubins[:-1]) / 2.0
+    nmu = len(mubins) - 1
+    powerspectrum[tuple((np.array(powerspectrum.shape) / 2).astype(int))] = 0.0
+    out = np.zeros((nmu, nk))
+    n_modes = np.zeros((nmu, nk))
+    with np.errstate(all="ignore"):
+        for ik in range(nk):
+            in_k = (k >= edges[ik]) & (k < edges[ik + 1]) & good
+            for im in range(nmu):
+                sel = (mu >= mubins[im]) & (mu < mubins[im + 1]) & in_k
+                vals = powerspectrum[sel]
+                out[im, ik] = np.mean(vals) if vals.size else np.nan
+                n_modes[im, ik] = vals.size
+    return out, mubins[:-1] + half_mu, edges[:-1] + half_k, n_modes
+
+
+# --------------------------------------------------------------------------
+# user-facing estimators
+# --------------------------------------------------------------------------
+def apply_window(input_array, window):
+    """Taper along the last axis, in place.  power_spectrum.py:12-21."""
+    if window is None:
+        return input_array
+    from scipy.signal import windows
+    name = window.lower()
+    if name == "blackmanharris":
+        input_array *= windows.blackmanharris(input_array.shape[-1])[None, None, :]
+    elif name == "tukey":
+        input_array *= windows.tukey(input_array.shape[-1])[None, None, :]
+    else:
+        input_array *= window
+    return input_array
+
+
+def power_spectrum_1d(input_array_nd, kbins=100, box_dims=None, return_n_modes=False,
+                      binning="log", breakpoint=0.1, window=None, **kwargs):
+    """power_spectrum.py:137-174."""
+    input_array_nd = apply_window(input_array_nd, window)
+    if kwargs.get("boxsize") is not None:
+        box_dims = kwargs.get("boxsize")
+    box_dims = box_lengths(box_dims, input_array_nd.shape)
+    p = power_spectrum_nd(input_array_nd, box_dims=box_dims)
+    ps, centres, n_modes = radial_average(p, kbins=kbins, box_dims=box_dims,
+                                          binning=binning, breakpoint=breakpoint)
+    return (ps, centres, n_modes) if return_n_modes else (ps, centres)
+
+
+def cross_power_spectrum_1d(input_array1_nd, input_array2_nd, kbins=100, box_dims=None,
+                            return_n_modes=False, binning="log", breakpoint=0.1, **kwargs):
+    """power_spectrum.py:257-289."""
+    if kwargs.get("boxsize") is not None:
+        box_dims = kwargs.get("boxsize")
+    box_dims = box_lengths(box_dims, input_array1_nd.shape)
+    p = cross_power_spectrum_nd(input_array1_nd, input_array2_nd, box_dims=box_dims)
+    ps, centres, n_modes = radial_average(p, kbins=kbins, box_dims=box_dims,
+                                          binning=binning, breakpoint=breakpoint)
+    return (ps, centres, n_modes) if return_n_modes else (ps, centres)
+
+
+def power_spectrum_mu(input_array, los_axis=0, mubins=20, kbins=10, box_dims=None, weights=None,
+                      exclude_zero_modes=True, return_n_modes=False, absolute_mus=True, **kwargs):
+    """power_spectrum.py:292-332 (``binning`` is not forwarded: always 'log')."""
+    if kwargs.get("boxsize") is not None:
+        box_dims = kwargs.get("boxsize")
+    box_dims = box_lengths(box_dims, input_array.shape)
+    p = power_spectrum_nd(input_array, box_dims=box_dims)
+    ps, mu_c, k_c, n_modes = mu_binning(p, los_axis, mubins, kbins, box_dims, weights,
+                                        exclude_zero_modes, absolute_mus=absolute_mus)
+    return (ps, mu_c, k_c, n_modes) if return_n_modes else (ps, mu_c, k_c)
+
+
+def cross_power_spectrum_mu(input_array1, input_array2, los_axis=0, mubins=20, kbins=10,
+                            box_dims=None, weights=None, exclude_zero_modes=True,
+                            return_n_modes=False, absolute_mus=True, **kwargs):
+    """power_spectrum.py:335-377."""
+    if kwargs.get("boxsize") is not None:
+        box_dims = kwargs.get("boxsize")
+    box_dims = box_lengths(box_dims, input_array1.shape)
+    p = cross_power_spectrum_nd(input_array1, input_array2, box_dims=box_dims)
+    ps, mu_c, k_c, n_modes = mu_binning(p, los_axis, mubins, kbins, box_dims, weights,
+                                        exclude_zero_modes, absolute_mus=absolute_mus)
+    return (ps, mu_c, k_c, n_modes) if return_n_modes else (ps, mu_c, k_c)
+
+
+def dimensionless_ps(data, kbins=100, box_dims=None, binning="log", factor=10):
+    """Delta^2(k) = P k^3 / 2 pi^2 interpolated from a finer binning.  power_spectrum.py:536-561."""
+    from scipy.interpolate import interp1d
+    pk, ks = power_spectrum_1d(data, kbins=kbins * factor, box_dims=box_dims, binning=binning)
+    f = interp1d(ks, pk * ks ** 3 / 2 / np.pi ** 2)
+    if binning == "log":
+        knew = 10 ** np.linspace(np.log10(ks[1]), np.log10(ks[-1]), kbins)
+    else:
+        knew = np.linspace(ks[1], ks[-1], kbins)
+    return f(knew), knew

@@ -1,0 +1,116 @@
+/* t21ps -- C ABI of the B200-native power-spectrum estimator.
+ *
+ * The reference (tools21cm v2.4.0) is pure Python: its "FFI" for this path is the
+ * set of module functions in src/tools21cm/power_spectrum.py.  Each entry point
+ * below is what a binding for one of those functions would call; the Python host
+ * side in tools21cm_b200/power_spectrum.py binds them with ctypes and keeps the
+ * reference signatures.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every `const void*` / `void*` data pointer is a DEVICE pointer owned by the
+ *     caller (the Python side allocates them as torch tensors); the library
+ *     allocates nothing on the device except the immutable twiddle tables of a plan;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous with
+ *     respect to the host and ordered on that stream;
+ *   - functions return 0 on success or a negative T21_E* code and never throw;
+ *     t21_last_error() returns a thread-local message for the last failure.
+ */
+#ifndef T21PS_H
+#define T21PS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define T21_F32 0
+#define T21_F64 1
+
+#define T21_OK 0
+#define T21_EINVAL -1   /* bad argument */
+#define T21_ECUDA -2    /* CUDA runtime error (message in t21_last_error) */
+#define T21_ENOMEM -3   /* workspace too small */
+
+#define T21_LUT_OUTSIDE 0xFFFFu /* lookup cell lies outside every bin */
+#define T21_LUT_EXACT 0xFFFEu   /* lookup cell touches an edge: use the float64 path */
+
+typedef struct t21_plan t21_plan;
+
+/* Everything the binning code needs, built on the host by tools21cm_b200/binspec.py
+ * with the reference's float64 expressions:
+ *   tab_s[d][i]  addend of s along axis d (k_d^2; reference power_spectrum.py:473-477)
+ *   thr[b]       bin b  <=>  thr[b] <= s < thr[b+1], s = (tab_s0 + tab_s1) + tab_s2
+ *                (edges of _get_kbins :505-519 mapped through sqrt; last one strict or
+ *                 not depending on np.histogram :128 vs mu_binning :424 semantics)
+ *   tab_los      signed k along the line of sight (_get_mu :481-502)
+ *   mu_edges     half-open mu bins (:406-409, :428)
+ *   *_lut        fp32 fast-path tables; T21_LUT_EXACT cells fall back to float64.
+ * Indices are FFT order for the fused kernels, fftshift order for t21_bin_only. */
+typedef struct t21_binspec {
+    int32_t n[3];
+    int32_t nk;
+    int32_t nmu;          /* 0: spherical shells only */
+    int32_t los_axis;     /* 0..2, or -1 when nmu == 0 */
+    int32_t absolute_mus;
+    int32_t exclude_zero; /* drop the k_perp = 0 line (_get_nonzero_idx :563-575) */
+    int32_t zero_idx[3];  /* index of k=0 along each axis */
+    int32_t nyq_idx[3];   /* index of the self-conjugate Nyquist sample, -1 if none */
+    const double* tab_s[3];
+    const float* tab_sf[3];
+    const double* tab_los;
+    const float* tab_losf;
+    const double* thr;
+    const double* mu_edges;
+    double s_nan;         /* modes with s < s_nan have mu = NaN (:501) */
+    const uint16_t* k_lut;
+    int32_t k_cells;
+    float k_lut_c0;       /* cell = floor(log2(s) * k_lut_inv + k_lut_c0) */
+    float k_lut_inv;
+    const uint16_t* mu_lut;
+    int32_t mu_cells;     /* cell = floor((mu + 1) * mu_cells / 2) */
+} t21_binspec;
+
+/* Plan for real cubes of shape (nx, ny, nz), C order.  dtype T21_F32 / T21_F64 is the
+ * arithmetic type of the transform.  Replaces the implicit scipy.fftpack plan behind
+ * power_spectrum.py:45,85-86. */
+int t21_plan_create(t21_plan** plan, int nx, int ny, int nz, int dtype, int device);
+int t21_plan_destroy(t21_plan* plan);
+
+/* Bytes of caller-provided workspace t21_ps_binned / t21_ps_nd need for n_fields
+ * (1 = auto, 2 = cross) input cubes. */
+size_t t21_workspace_bytes(const t21_plan* plan, int n_fields);
+
+/* power_spectrum_1d / cross_power_spectrum_1d / power_spectrum_mu / cross_power_spectrum_mu
+ * (power_spectrum.py:137-174, 257-289, 292-332, 335-377) without the final division:
+ * R2C 3-D FFT of x1 (and x2), |F|^2 or Re(F1 conj F2), binned on the fly.
+ *   sums_out[nbins]   float64 unscaled sum of power per bin (bin = imu*nk + ik)
+ *   counts_out[nbins] int64 number of modes per bin
+ * subtract_mean != 0: transform x - c with c ~ mean(x) estimated on the device and repair the
+ * DC sample analytically (only changes rounding; DC keeps its true value). */
+int t21_ps_binned(const t21_plan* plan, const void* x1, const void* x2_or_null, int subtract_mean,
+                  const t21_binspec* spec, double* sums_out, long long* counts_out,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* power_spectrum_nd / cross_power_spectrum_nd (power_spectrum.py:24-54, 57-95): the full
+ * fftshifted power array, multiplied by `scale`, written as out_dtype (T21_F32/T21_F64). */
+int t21_ps_nd(const t21_plan* plan, const void* x1, const void* x2_or_null, int subtract_mean,
+              double scale, void* out, int out_dtype, void* workspace, size_t workspace_bytes,
+              void* stream);
+
+/* radial_average / mu_binning (power_spectrum.py:98-134, 380-435) on a caller-supplied
+ * fftshifted array of spec->n elements (1-/2-D arrays are padded with leading 1s). */
+int t21_bin_only(const void* p_shifted, int dtype, const t21_binspec* spec, double* sums_out,
+                 long long* counts_out, void* workspace, size_t workspace_bytes, void* stream);
+size_t t21_bin_only_workspace_bytes(const t21_binspec* spec);
+
+const char* t21_last_error(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+unsigned long long t21_launch_count(void);
+int t21_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T21PS_H */

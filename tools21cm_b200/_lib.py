@@ -1,0 +1,130 @@
+"""ctypes binding of libt21ps.so (the C ABI declared in include/t21ps.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a) and lives at
+``tools21cm_b200/lib/libt21ps.so``.  There is no CPU fallback: if the library is
+missing, or no CUDA device is present when a compute entry point is called, the
+caller gets a RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+T21_F32, T21_F64 = 0, 1
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libt21ps.so")
+
+
+class BinSpecC(C.Structure):
+    """Mirror of ``t21_binspec`` in include/t21ps.h (field order matters)."""
+    _fields_ = [
+        ("n", C.c_int32 * 3),
+        ("nk", C.c_int32),
+        ("nmu", C.c_int32),
+        ("los_axis", C.c_int32),
+        ("absolute_mus", C.c_int32),
+        ("exclude_zero", C.c_int32),
+        ("zero_idx", C.c_int32 * 3),
+        ("nyq_idx", C.c_int32 * 3),
+        ("tab_s", C.c_void_p * 3),
+        ("tab_sf", C.c_void_p * 3),
+        ("tab_los", C.c_void_p),
+        ("tab_losf", C.c_void_p),
+        ("thr", C.c_void_p),
+        ("mu_edges", C.c_void_p),
+        ("s_nan", C.c_double),
+        ("k_lut", C.c_void_p),
+        ("k_cells", C.c_int32),
+        ("k_lut_c0", C.c_float),
+        ("k_lut_inv", C.c_float),
+        ("mu_lut", C.c_void_p),
+        ("mu_cells", C.c_int32),
+    ]
+
+
+def pack_binspec(spec, to_buffer):
+    """Flatten a ``binspec.BinSpec`` into (BinSpecC, keepalive).
+
+    ``to_buffer(np.ndarray) -> (address, owner)`` places one table where the consumer can
+    read it: identity for the CPU emulator, a host->device copy for the CUDA library."""
+    keep = []
+
+    def put(a, dtype):
+        addr, owner = to_buffer(np.ascontiguousarray(a, dtype=dtype))
+        keep.append(owner)
+        return addr
+
+    c = BinSpecC()
+    for d in range(3):
+        c.n[d] = int(spec.shape[d])
+        c.zero_idx[d] = int(spec.zero_idx[d])
+        c.nyq_idx[d] = int(spec.nyq_idx[d])
+        c.tab_s[d] = put(spec.tab_s[d], np.float64)
+        c.tab_sf[d] = put(spec.tab_s[d], np.float32)
+    c.nk, c.nmu, c.los_axis = int(spec.nk), int(spec.nmu), int(spec.los_axis)
+    c.absolute_mus, c.exclude_zero = int(spec.absolute_mus), int(spec.exclude_zero)
+    c.tab_los = put(spec.tab_los, np.float64)
+    c.tab_losf = put(spec.tab_los, np.float32)
+    c.thr = put(spec.thr, np.float64)
+    c.mu_edges = put(spec.mu_edges if spec.nmu else np.zeros(1), np.float64)
+    c.s_nan = float(spec.s_nan)
+    c.k_lut = put(spec.k_lut, np.uint16)
+    c.k_cells = int(spec.k_lut.size)
+    inv = np.float32(spec.k_lut_inv)
+    c.k_lut_inv = float(inv)
+    c.k_lut_c0 = float(np.float32(-spec.k_lut_u0 * spec.k_lut_inv))
+    c.mu_lut = put(spec.mu_lut if spec.nmu else np.zeros(1, np.uint16), np.uint16)
+    c.mu_cells = int(spec.mu_lut.size) if spec.nmu else 1
+    return c, keep
+
+
+def host_buffer(a):
+    return a.ctypes.data, a
+
+
+_lib = None
+
+
+def load():
+    """Load libt21ps.so and declare the prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "tools21cm_b200: %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback for this path." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, sz, dbl = C.c_void_p, C.c_int, C.c_size_t, C.c_double
+    lib.t21_plan_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i32]
+    lib.t21_plan_create.restype = i32
+    lib.t21_plan_destroy.argtypes = [vp]
+    lib.t21_plan_destroy.restype = i32
+    lib.t21_workspace_bytes.argtypes = [vp, i32, i32]
+    lib.t21_workspace_bytes.restype = sz
+    lib.t21_ps_binned.argtypes = [vp, vp, vp, i32, C.POINTER(BinSpecC), vp, vp, vp, sz, vp]
+    lib.t21_ps_binned.restype = i32
+    lib.t21_ps_nd.argtypes = [vp, vp, vp, i32, dbl, vp, i32, vp, sz, vp]
+    lib.t21_ps_nd.restype = i32
+    lib.t21_bin_only.argtypes = [vp, i32, C.POINTER(BinSpecC), vp, vp, vp, sz, vp]
+    lib.t21_bin_only.restype = i32
+    lib.t21_bin_only_workspace_bytes.argtypes = [C.POINTER(BinSpecC)]
+    lib.t21_bin_only_workspace_bytes.restype = sz
+    lib.t21_last_error.argtypes = []
+    lib.t21_last_error.restype = C.c_char_p
+    lib.t21_launch_count.argtypes = []
+    lib.t21_launch_count.restype = C.c_ulonglong
+    lib.t21_version.argtypes = []
+    lib.t21_version.restype = i32
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().t21_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError("%s: %s" % (what, msg))
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, msg))

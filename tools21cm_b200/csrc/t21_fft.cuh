@@ -1,0 +1,160 @@
+// In-register radix butterflies and the staged Stockham pencil FFT.
+//
+// A length-N pencil (N a power of two) is transformed by T = N/E threads, each
+// holding E complex values in registers.  Stage s applies E/R_s radix-R_s
+// butterflies per thread; between stages values are exchanged through shared
+// memory in Stockham (self-sorting) order, so the last stage produces natural
+// frequency order with no bit reversal:
+//
+//   butterfly jj in [0, N/R):  in[jj + k*N/R] * w^(k*(jj mod Ns))  -> DFT_R ->
+//                              out[(jj - jj mod Ns)*R + jj mod Ns + k*Ns]
+//
+// Twiddles between stages come from per-stage tables laid out [k-1][m]
+// (m = jj mod Ns fastest) so consecutive butterflies read consecutive entries.
+// Tables are built on the host in float64 and rounded once (t21_plan_create).
+#pragma once
+#include "t21_common.cuh"
+
+namespace t21 {
+
+// ---- compile-time constants: exp(-2*pi*i*idx/32) --------------------------------
+constexpr double kCos32[9] = {1.0,
+                              0.98078528040323044912618223613424,
+                              0.92387953251128675612818318939679,
+                              0.83146961230254523707878837761791,
+                              0.70710678118654752440084436210485,
+                              0.55557023301960222474283081394853,
+                              0.38268343236508977172845998403040,
+                              0.19509032201612826784828486847702,
+                              0.0};
+constexpr double cos32(int i) {
+    i &= 31;
+    if (i > 16) i = 32 - i;
+    return i > 8 ? -kCos32[16 - i] : kCos32[i];
+}
+constexpr double sin32(int i) { return cos32((i + 24) & 31); }
+
+// v *= exp(-2*pi*i*k/R), with the trivial cases folded after unrolling
+template <int R, typename T>
+T21_HD cx<T> rot(cx<T> v, int k) {
+    const int idx = k * (32 / R);  // in 32nds of a turn
+    if (idx == 0) return v;
+    if (idx == 8) return cmake<T>(v.y, -v.x);                       // * -i
+    if (idx == 16) return cmake<T>(-v.x, -v.y);
+    if (idx == 24) return cmake<T>(-v.y, v.x);                      // * +i
+    const T h = (T)kCos32[4];  // sqrt(1/2)
+    if (idx == 4) return cmake<T>((v.x + v.y) * h, (v.y - v.x) * h);    // * (1-i)/sqrt2
+    if (idx == 12) return cmake<T>((v.y - v.x) * h, -(v.x + v.y) * h);  // * (-1-i)/sqrt2
+    const T c = (T)cos32(idx), s = (T)sin32(idx);
+    // general: (x + iy)(c - is) = (xc + ys) + i(yc - xs)
+    return cmake<T>(v.x * c + v.y * s, v.y * c - v.x * s);
+}
+
+template <int R, typename T>
+struct DFT {
+    // in place, natural order in and out; forward sign exp(-i...)
+    static T21_HD void run(cx<T>* v) {
+        static_assert(R >= 4 && R <= 32 && is_pow2(R), "radix");
+        cx<T> e[R / 2], o[R / 2];
+#pragma unroll
+        for (int i = 0; i < R / 2; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+        DFT<R / 2, T>::run(e);
+        DFT<R / 2, T>::run(o);
+#pragma unroll
+        for (int k = 0; k < R / 2; ++k) {
+            cx<T> t = rot<R, T>(o[k], k);
+            v[k] = cadd(e[k], t);
+            v[k + R / 2] = csub(e[k], t);
+        }
+    }
+};
+template <typename T>
+struct DFT<2, T> {
+    static T21_HD void run(cx<T>* v) {
+        cx<T> a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    }
+};
+template <typename T>
+struct DFT<1, T> {
+    static T21_HD void run(cx<T>*) {}
+};
+
+// ---- compile-time plan ------------------------------------------------------------
+template <int N>
+struct Plan {
+    static_assert(is_pow2(N) && N >= 2, "pencil length must be a power of two");
+    static constexpr int E = N < 16 ? N : 16;  // values per thread
+    static constexpr int T = N / E;            // threads per pencil
+    static constexpr int radix(int s) {        // radix of stage s (0 past the end)
+        int rem = N;
+        for (int i = 0; i < s; ++i) rem /= (rem < E ? rem : E);
+        return rem <= 1 ? 0 : (rem < E ? rem : E);
+    }
+    static constexpr int ns(int s) {           // product of the radices before stage s
+        int p = 1;
+        for (int i = 0; i < s; ++i) p *= radix(i);
+        return p;
+    }
+    static constexpr int stages() {
+        int s = 0;
+        while (radix(s) != 0) ++s;
+        return s;
+    }
+    static constexpr int NS = stages();
+    static constexpr int tw_off(int s) {       // offset of stage s in the twiddle table
+        int o = 0;
+        for (int i = 1; i < s; ++i) o += (radix(i) - 1) * ns(i);
+        return o;
+    }
+    static constexpr int TW_TOTAL = tw_off(NS);
+};
+
+// number of twiddle entries for a run-time N (host side of t21_plan_create)
+inline int plan_tw_total(int n) {
+    int e = n < 16 ? n : 16, rem = n, nsv = 1, tot = 0, s = 0;
+    while (rem > 1) {
+        int r = rem < e ? rem : e;
+        if (s > 0) tot += (r - 1) * nsv;
+        nsv *= r; rem /= r; ++s;
+    }
+    return tot;
+}
+
+// ---- one stage, split into its load and its compute+store halves -------------------
+// ld(i) returns element i of this thread's pencil; st(i, v, slot) stores element i, which
+// lives in register slot `slot` (a compile-time constant after unrolling).
+template <int N, int S, typename T, class LoadFn>
+T21_HD void stage_load(cx<T>* v, int j, LoadFn&& ld) {
+    using P = Plan<N>;
+    constexpr int R = P::radix(S), NB = P::E / R, STRIDE = N / R;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int jj = j + b * P::T;
+#pragma unroll
+        for (int k = 0; k < R; ++k) v[b * R + k] = ld(jj + k * STRIDE);
+    }
+}
+
+template <int N, int S, typename T, class StoreFn>
+T21_HD void stage_compute(cx<T>* v, int j, const cx<T>* __restrict__ tw, StoreFn&& st) {
+    using P = Plan<N>;
+    constexpr int R = P::radix(S), NB = P::E / R, NSV = P::ns(S), OFF = P::tw_off(S);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int jj = j + b * P::T;
+        const int m = jj & (NSV - 1);
+        if (NSV > 1) {
+#pragma unroll
+            for (int k = 1; k < R; ++k)
+                v[b * R + k] = cmul(v[b * R + k], ldg(tw + OFF + (k - 1) * NSV + m));
+        }
+        DFT<R, T>::run(v + b * R);
+        const int base = (jj - m) * R + m;
+#pragma unroll
+        for (int k = 0; k < R; ++k) st(base + k * NSV, v[b * R + k], b * R + k);
+    }
+}
+
+}  // namespace t21

@@ -25,6 +25,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define T21_API __attribute__((visibility("default")))
+#else
+#define T21_API
+#endif
+
 #define T21_F32 0
 #define T21_F64 1
 
@@ -75,12 +81,12 @@ typedef struct t21_binspec {
 /* Plan for real cubes of shape (nx, ny, nz), C order.  dtype T21_F32 / T21_F64 is the
  * arithmetic type of the transform.  Replaces the implicit scipy.fftpack plan behind
  * power_spectrum.py:45,85-86. */
-int t21_plan_create(t21_plan** plan, int nx, int ny, int nz, int dtype, int device);
-int t21_plan_destroy(t21_plan* plan);
+T21_API int t21_plan_create(t21_plan** plan, int nx, int ny, int nz, int dtype, int device);
+T21_API int t21_plan_destroy(t21_plan* plan);
 
-/* Bytes of caller-provided workspace t21_ps_binned / t21_ps_nd need for n_fields
- * (1 = auto, 2 = cross) input cubes. */
-size_t t21_workspace_bytes(const t21_plan* plan, int n_fields);
+/* Bytes of caller-provided workspace t21_ps_binned (nbins = nk * max(nmu, 1)) or
+ * t21_ps_nd (nbins = 0) need for n_fields (1 = auto, 2 = cross) input cubes. */
+T21_API size_t t21_workspace_bytes(const t21_plan* plan, int n_fields, int nbins);
 
 /* power_spectrum_1d / cross_power_spectrum_1d / power_spectrum_mu / cross_power_spectrum_mu
  * (power_spectrum.py:137-174, 257-289, 292-332, 335-377) without the final division:
@@ -89,26 +95,26 @@ size_t t21_workspace_bytes(const t21_plan* plan, int n_fields);
  *   counts_out[nbins] int64 number of modes per bin
  * subtract_mean != 0: transform x - c with c ~ mean(x) estimated on the device and repair the
  * DC sample analytically (only changes rounding; DC keeps its true value). */
-int t21_ps_binned(const t21_plan* plan, const void* x1, const void* x2_or_null, int subtract_mean,
+T21_API int t21_ps_binned(const t21_plan* plan, const void* x1, const void* x2_or_null, int subtract_mean,
                   const t21_binspec* spec, double* sums_out, long long* counts_out,
                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* power_spectrum_nd / cross_power_spectrum_nd (power_spectrum.py:24-54, 57-95): the full
  * fftshifted power array, multiplied by `scale`, written as out_dtype (T21_F32/T21_F64). */
-int t21_ps_nd(const t21_plan* plan, const void* x1, const void* x2_or_null, int subtract_mean,
+T21_API int t21_ps_nd(const t21_plan* plan, const void* x1, const void* x2_or_null, int subtract_mean,
               double scale, void* out, int out_dtype, void* workspace, size_t workspace_bytes,
               void* stream);
 
 /* radial_average / mu_binning (power_spectrum.py:98-134, 380-435) on a caller-supplied
  * fftshifted array of spec->n elements (1-/2-D arrays are padded with leading 1s). */
-int t21_bin_only(const void* p_shifted, int dtype, const t21_binspec* spec, double* sums_out,
+T21_API int t21_bin_only(const void* p_shifted, int dtype, const t21_binspec* spec, double* sums_out,
                  long long* counts_out, void* workspace, size_t workspace_bytes, void* stream);
-size_t t21_bin_only_workspace_bytes(const t21_binspec* spec);
+T21_API size_t t21_bin_only_workspace_bytes(const t21_binspec* spec);
 
-const char* t21_last_error(void);
+T21_API const char* t21_last_error(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
-unsigned long long t21_launch_count(void);
-int t21_version(void);
+T21_API unsigned long long t21_launch_count(void);
+T21_API int t21_version(void);
 
 #ifdef __cplusplus
 }

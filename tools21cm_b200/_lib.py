@@ -44,40 +44,59 @@ class BinSpecC(C.Structure):
     ]
 
 
-def pack_binspec(spec, to_buffer):
+def pack_binspec(spec, upload):
     """Flatten a ``binspec.BinSpec`` into (BinSpecC, keepalive).
 
-    ``to_buffer(np.ndarray) -> (address, owner)`` places one table where the consumer can
-    read it: identity for the CPU emulator, a host->device copy for the CUDA library."""
-    keep = []
+    All tables go into one 256-byte-aligned blob so a spec costs a single host->device copy.
+    ``upload(np.ndarray[uint8]) -> (base_address, owner)`` places the blob where the consumer
+    reads it: identity for the CPU emulator, one H2D copy for the CUDA library."""
+    parts = []
+    size = 0
 
     def put(a, dtype):
-        addr, owner = to_buffer(np.ascontiguousarray(a, dtype=dtype))
-        keep.append(owner)
-        return addr
+        nonlocal size
+        a = np.ascontiguousarray(a, dtype=dtype)
+        off = size
+        parts.append((off, a))
+        size = (off + a.nbytes + 255) // 256 * 256
+        return off
+
+    offs = {}
+    for d in range(3):
+        offs["s%d" % d] = put(spec.tab_s[d], np.float64)
+        offs["sf%d" % d] = put(spec.tab_s[d], np.float32)
+    offs["los"] = put(spec.tab_los, np.float64)
+    offs["losf"] = put(spec.tab_los, np.float32)
+    offs["thr"] = put(spec.thr, np.float64)
+    offs["mu"] = put(spec.mu_edges if spec.nmu else np.zeros(1), np.float64)
+    offs["klut"] = put(spec.k_lut, np.uint16)
+    offs["mulut"] = put(spec.mu_lut if spec.nmu else np.zeros(1, np.uint16), np.uint16)
+    blob = np.zeros(max(size, 256), dtype=np.uint8)
+    for off, a in parts:
+        blob[off:off + a.nbytes] = a.view(np.uint8).reshape(-1)
+    base, owner = upload(blob)
 
     c = BinSpecC()
     for d in range(3):
         c.n[d] = int(spec.shape[d])
         c.zero_idx[d] = int(spec.zero_idx[d])
         c.nyq_idx[d] = int(spec.nyq_idx[d])
-        c.tab_s[d] = put(spec.tab_s[d], np.float64)
-        c.tab_sf[d] = put(spec.tab_s[d], np.float32)
+        c.tab_s[d] = base + offs["s%d" % d]
+        c.tab_sf[d] = base + offs["sf%d" % d]
     c.nk, c.nmu, c.los_axis = int(spec.nk), int(spec.nmu), int(spec.los_axis)
     c.absolute_mus, c.exclude_zero = int(spec.absolute_mus), int(spec.exclude_zero)
-    c.tab_los = put(spec.tab_los, np.float64)
-    c.tab_losf = put(spec.tab_los, np.float32)
-    c.thr = put(spec.thr, np.float64)
-    c.mu_edges = put(spec.mu_edges if spec.nmu else np.zeros(1), np.float64)
+    c.tab_los = base + offs["los"]
+    c.tab_losf = base + offs["losf"]
+    c.thr = base + offs["thr"]
+    c.mu_edges = base + offs["mu"]
     c.s_nan = float(spec.s_nan)
-    c.k_lut = put(spec.k_lut, np.uint16)
+    c.k_lut = base + offs["klut"]
     c.k_cells = int(spec.k_lut.size)
-    inv = np.float32(spec.k_lut_inv)
-    c.k_lut_inv = float(inv)
+    c.k_lut_inv = float(np.float32(spec.k_lut_inv))
     c.k_lut_c0 = float(np.float32(-spec.k_lut_u0 * spec.k_lut_inv))
-    c.mu_lut = put(spec.mu_lut if spec.nmu else np.zeros(1, np.uint16), np.uint16)
+    c.mu_lut = base + offs["mulut"]
     c.mu_cells = int(spec.mu_lut.size) if spec.nmu else 1
-    return c, keep
+    return c, owner
 
 
 def host_buffer(a):

@@ -1,0 +1,279 @@
+// C ABI of libt21ps.so (declared in include/t21ps.h): plans, workspace layout, and the
+// three entry points that chain the passes on the caller's stream.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "t21_internal.h"
+#include "t21_tables.h"
+
+namespace t21 {
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return T21_ECUDA;
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int device_sm_count() {
+    static int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached = n;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace t21
+
+using namespace t21;
+
+struct t21_plan {
+    int n[3];
+    int dtype;
+    int device;
+    int nzh, pitch;
+    int fast[3];          // axis handled by the Stockham kernels
+    void* tw[3];          // stage twiddles per axis (z: for nz/2), device
+    void* twr;            // exp(-2 pi i k / nz), k = 0..nz/2, device
+    int max_grid;         // capacity (in CTAs) of the partial-histogram buffers
+};
+
+struct WsLayout {
+    size_t w[2], offs, part_sum, part_cnt, total;
+    int nbins_cap;
+};
+
+static WsLayout ws_layout(const t21_plan* p, int nf, int nbins) {
+    WsLayout L;
+    memset(&L, 0, sizeof(L));
+    const size_t esz = (p->dtype == T21_F32 ? 8 : 16);
+    const size_t wbytes = align_up((size_t)p->n[0] * p->n[1] * p->pitch * esz, 256);
+    size_t o = 0;
+    for (int f = 0; f < nf; ++f) { L.w[f] = o; o += wbytes; }
+    L.offs = o; o += 256;
+    L.nbins_cap = nbins > kSmemHistMaxBins ? 0 : nbins;
+    L.part_sum = o; o += align_up((size_t)p->max_grid * L.nbins_cap * sizeof(double), 256);
+    L.part_cnt = o; o += align_up((size_t)p->max_grid * L.nbins_cap * sizeof(unsigned), 256);
+    L.total = o;
+    return L;
+}
+
+template <typename T>
+static int upload(const std::vector<cx<T>>& v, void** out) {
+    T21_CUDA_OK(cudaMalloc(out, v.size() * sizeof(cx<T>)));
+    T21_CUDA_OK(cudaMemcpy(*out, v.data(), v.size() * sizeof(cx<T>), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+template <typename T>
+static int build_tables(t21_plan* p) {
+    for (int d = 0; d < 3; ++d) {
+        if (!p->fast[d]) continue;
+        const int len = d == 2 ? p->n[2] / 2 : p->n[d];
+        if (int rc = upload<T>(build_stage_twiddles<T>(len), &p->tw[d])) return rc;
+    }
+    if (p->fast[2])
+        if (int rc = upload<T>(build_roots<T>(p->n[2], p->n[2] / 2 + 1), &p->twr)) return rc;
+    return 0;
+}
+
+extern "C" {
+
+int t21_version(void) { return 100; }
+const char* t21_last_error(void) { return g_err; }
+unsigned long long t21_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int t21_plan_create(t21_plan** out, int nx, int ny, int nz, int dtype, int device) {
+    if (!out) { set_error("plan pointer is null"); return T21_EINVAL; }
+    *out = nullptr;
+    if (nx < 1 || ny < 1 || nz < 1) { set_error("bad shape %dx%dx%d", nx, ny, nz); return T21_EINVAL; }
+    if (dtype != T21_F32 && dtype != T21_F64) { set_error("bad dtype %d", dtype); return T21_EINVAL; }
+    int cur = 0;
+    T21_CUDA_OK(cudaGetDevice(&cur));
+    if (cur != device) T21_CUDA_OK(cudaSetDevice(device));
+    t21_plan* p = new t21_plan();
+    memset(p, 0, sizeof(*p));
+    p->n[0] = nx; p->n[1] = ny; p->n[2] = nz;
+    p->dtype = dtype;
+    p->device = device;
+    p->nzh = nz / 2 + 1;
+    p->pitch = (int)align_up((size_t)p->nzh, 16);
+    p->fast[0] = fast_len(nx);
+    p->fast[1] = fast_len(ny);
+    p->fast[2] = fast_len(nz);
+    p->max_grid = device_sm_count() * 8;
+    int rc = 0;
+    if (!(p->fast[0] && p->fast[1] && p->fast[2])) {
+        set_error("shape %dx%dx%d: every axis must be a power of two in [%d, %d] for now", nx, ny, nz, kMinFast, kMaxFast);
+        rc = T21_EINVAL;
+    }
+    if (!rc) rc = dtype == T21_F32 ? build_tables<float>(p) : build_tables<double>(p);
+    if (cur != device) cudaSetDevice(cur);
+    if (rc) { t21_plan_destroy(p); return rc; }
+    *out = p;
+    return T21_OK;
+}
+
+int t21_plan_destroy(t21_plan* p) {
+    if (!p) return T21_OK;
+    for (int d = 0; d < 3; ++d) if (p->tw[d]) cudaFree(p->tw[d]);
+    if (p->twr) cudaFree(p->twr);
+    delete p;
+    return T21_OK;
+}
+
+size_t t21_workspace_bytes(const t21_plan* p, int n_fields, int nbins) {
+    if (!p || n_fields < 1 || n_fields > 2 || nbins < 0) return 0;
+    return ws_layout(p, n_fields, nbins).total;
+}
+
+// z and y passes of every field; leaves the half spectra in the workspace
+static int forward_zy(const t21_plan* p, const void* const x[2], int nf, int subtract_mean, unsigned char* ws,
+                      const WsLayout& L, const void* offs[2], cudaStream_t st) {
+    const size_t rsz = p->dtype == T21_F32 ? 4 : 8;
+    const long long ntot = (long long)p->n[0] * p->n[1] * p->n[2];
+    for (int f = 0; f < nf; ++f) {
+        offs[f] = nullptr;
+        if (subtract_mean) {
+            void* o = ws + L.offs + f * rsz;
+            if (int rc = launch_mean_estimate(p->dtype, x[f], ntot, o, st)) return rc;
+            offs[f] = o;
+        }
+        ZArgs z{x[f], ws + L.w[f], (long long)p->n[0] * p->n[1], p->n[2], p->pitch, offs[f], p->tw[2], p->twr};
+        if (int rc = launch_zpass(p->dtype, z, st)) return rc;
+        YArgs y{ws + L.w[f], (long long)p->n[0], p->n[1], p->nzh, p->pitch, p->tw[1]};
+        if (int rc = launch_ypass(p->dtype, y, st)) return rc;
+    }
+    return 0;
+}
+
+static int check_common(const t21_plan* p, const void* x1, void* ws, size_t need, size_t have) {
+    if (!p || !x1 || !ws) { set_error("null plan, input or workspace"); return T21_EINVAL; }
+    if (have < need) { set_error("workspace too small: %zu < %zu bytes", have, need); return T21_ENOMEM; }
+    if (((uintptr_t)x1 & 15) || ((uintptr_t)ws & 255)) { set_error("input must be 16-byte and workspace 256-byte aligned"); return T21_EINVAL; }
+    int cur = 0;
+    T21_CUDA_OK(cudaGetDevice(&cur));
+    if (cur != p->device) { set_error("plan was made for device %d, current device is %d", p->device, cur); return T21_EINVAL; }
+    return 0;
+}
+
+int t21_ps_binned(const t21_plan* p, const void* x1, const void* x2, int subtract_mean, const t21_binspec* spec,
+                  double* sums_out, long long* counts_out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!spec || !sums_out || !counts_out) { set_error("null spec or outputs"); return T21_EINVAL; }
+    const int nf = x2 ? 2 : 1;
+    const int nbins = spec->nk * (spec->nmu > 0 ? spec->nmu : 1);
+    if (nbins < 1) { set_error("no bins"); return T21_EINVAL; }
+    if (p && (spec->n[0] != p->n[0] || spec->n[1] != p->n[1] || spec->n[2] != p->n[2])) {
+        set_error("bin spec shape does not match the plan"); return T21_EINVAL;
+    }
+    if (x2 && ((uintptr_t)x2 & 15)) { set_error("second input must be 16-byte aligned"); return T21_EINVAL; }
+    const WsLayout L = p ? ws_layout(p, nf, nbins) : WsLayout();
+    if (int rc = check_common(p, x1, workspace, L.total, workspace_bytes)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* ws = (unsigned char*)workspace;
+    const void* x[2] = {x1, x2};
+    const void* offs[2] = {nullptr, nullptr};
+    if (int rc = forward_zy(p, x, nf, subtract_mean, ws, L, offs, st)) return rc;
+
+    XArgs a;
+    memset(&a, 0, sizeof(a));
+    a.w[0] = ws + L.w[0];
+    a.w[1] = nf == 2 ? ws + L.w[1] : nullptr;
+    a.nf = nf;
+    a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch;
+    a.tw = p->tw[0];
+    a.offset[0] = offs[0]; a.offset[1] = offs[1];
+    a.ntot = (double)p->n[0] * p->n[1] * p->n[2];
+    a.bins = spec;
+    a.nbins = nbins;
+    a.hist_global = L.nbins_cap == 0;
+    a.part_sum = (double*)(ws + L.part_sum);
+    a.part_cnt = (unsigned*)(ws + L.part_cnt);
+    a.gsum = sums_out;
+    a.gcnt = (unsigned long long*)counts_out;
+    a.max_grid = p->max_grid;
+    if (a.hist_global)
+        if (int rc = launch_zero_hist(sums_out, counts_out, nbins, st)) return rc;
+    int rc = p->dtype == T21_F32 ? launch_xpass_f32_bin(a, st) : launch_xpass_f64_bin(a, st);
+    if (rc) return rc;
+    if (!a.hist_global)
+        return launch_reduce_partials(a.part_sum, a.part_cnt, a.grid_used, nbins, sums_out, counts_out, st);
+    return T21_OK;
+}
+
+int t21_ps_nd(const t21_plan* p, const void* x1, const void* x2, int subtract_mean, double scale, void* out,
+              int out_dtype, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!out) { set_error("null output"); return T21_EINVAL; }
+    if (out_dtype != T21_F32 && out_dtype != T21_F64) { set_error("bad output dtype"); return T21_EINVAL; }
+    const int nf = x2 ? 2 : 1;
+    if (x2 && ((uintptr_t)x2 & 15)) { set_error("second input must be 16-byte aligned"); return T21_EINVAL; }
+    const WsLayout L = p ? ws_layout(p, nf, 0) : WsLayout();
+    if (int rc = check_common(p, x1, workspace, L.total, workspace_bytes)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* ws = (unsigned char*)workspace;
+    const void* x[2] = {x1, x2};
+    const void* offs[2] = {nullptr, nullptr};
+    if (int rc = forward_zy(p, x, nf, subtract_mean, ws, L, offs, st)) return rc;
+    XArgs a;
+    memset(&a, 0, sizeof(a));
+    a.w[0] = ws + L.w[0];
+    a.w[1] = nf == 2 ? ws + L.w[1] : nullptr;
+    a.nf = nf;
+    a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch;
+    a.tw = p->tw[0];
+    a.offset[0] = offs[0]; a.offset[1] = offs[1];
+    a.ntot = (double)p->n[0] * p->n[1] * p->n[2];
+    a.nd_out = out; a.nd_f64 = out_dtype == T21_F64; a.scale = scale;
+    a.max_grid = p->max_grid;
+    return p->dtype == T21_F32 ? launch_xpass_f32_nd(a, st) : launch_xpass_f64_nd(a, st);
+}
+
+size_t t21_bin_only_workspace_bytes(const t21_binspec* spec) {
+    if (!spec) return 0;
+    const int nbins = spec->nk * (spec->nmu > 0 ? spec->nmu : 1);
+    if (nbins > kSmemHistMaxBins) return 256;
+    const size_t g = (size_t)device_sm_count() * 8;
+    return align_up(g * nbins * sizeof(double), 256) + align_up(g * nbins * sizeof(unsigned), 256);
+}
+
+int t21_bin_only(const void* p_shifted, int dtype, const t21_binspec* spec, double* sums_out, long long* counts_out,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+    if (!p_shifted || !spec || !sums_out || !counts_out || !workspace) { set_error("null argument"); return T21_EINVAL; }
+    if (dtype != T21_F32 && dtype != T21_F64) { set_error("bad dtype %d", dtype); return T21_EINVAL; }
+    const int nbins = spec->nk * (spec->nmu > 0 ? spec->nmu : 1);
+    if (nbins < 1) { set_error("no bins"); return T21_EINVAL; }
+    const size_t need = t21_bin_only_workspace_bytes(spec);
+    if (workspace_bytes < need) { set_error("workspace too small: %zu < %zu bytes", workspace_bytes, need); return T21_ENOMEM; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int max_grid = device_sm_count() * 8;
+    double* part_sum = (double*)workspace;
+    unsigned* part_cnt = (unsigned*)((unsigned char*)workspace + align_up((size_t)max_grid * nbins * sizeof(double), 256));
+    const bool global = nbins > kSmemHistMaxBins;
+    if (global)
+        if (int rc = launch_zero_hist(sums_out, counts_out, nbins, st)) return rc;
+    int grid = 0;
+    if (int rc = launch_bin_only(p_shifted, dtype, *spec, part_sum, part_cnt, max_grid, sums_out, counts_out, &grid, st))
+        return rc;
+    if (!global) return launch_reduce_partials(part_sum, part_cnt, grid, nbins, sums_out, counts_out, st);
+    return T21_OK;
+}
+
+}  // extern "C"

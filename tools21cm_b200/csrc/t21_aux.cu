@@ -1,0 +1,153 @@
+// Small kernels around the three passes: mean-offset estimate, histogram reduction,
+// and element-wise binning of caller-supplied arrays (radial_average / mu_binning).
+#include <string.h>
+#include "t21_launch.cuh"
+
+namespace t21 {
+
+// ---- mean offset --------------------------------------------------------------------
+// c ~ mean(x) from a strided sample (<= 65536 values, odd stride so it walks every axis).
+// The FFT of x - c differs from the FFT of x only in the DC sample, which the X pass
+// repairs analytically, so c only needs to be close to the mean: it is there to keep
+// the fp32 partial sums small, not to define the result.
+template <typename T>
+__global__ void __launch_bounds__(1024) mean_estimate_kernel(const T* __restrict__ x, long long n, T* out) {
+    const long long want = n < 65536 ? n : 65536;
+    const long long stride = (n / want) | 1;
+    const long long count = (n - 1) / stride + 1;
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < count; i += 1024) s += (double)x[i * stride];
+    __shared__ double red[32];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = red[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) *out = (T)(s / (double)count);
+    }
+}
+
+int launch_mean_estimate(int dtype, const void* x, long long n, void* offset_out, cudaStream_t st) {
+    if (dtype == T21_F32) mean_estimate_kernel<float><<<1, 1024, 0, st>>>((const float*)x, n, (float*)offset_out);
+    else mean_estimate_kernel<double><<<1, 1024, 0, st>>>((const double*)x, n, (double*)offset_out);
+    count_launch();
+    T21_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---- deterministic inter-CTA reduction ------------------------------------------------
+// one thread per bin, partials added in CTA order
+__global__ void reduce_partials_kernel(const double* __restrict__ part_sum, const unsigned* __restrict__ part_cnt,
+                                       int nparts, int nbins, double* __restrict__ sums, long long* __restrict__ counts) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbins) return;
+    double s = 0.0;
+    long long c = 0;
+    for (int p = 0; p < nparts; ++p) {
+        s += part_sum[(size_t)p * nbins + b];
+        c += part_cnt[(size_t)p * nbins + b];
+    }
+    sums[b] = s;
+    counts[b] = c;
+}
+
+int launch_reduce_partials(const double* part_sum, const unsigned* part_cnt, int nparts, int nbins,
+                           double* sums_out, long long* counts_out, cudaStream_t st) {
+    reduce_partials_kernel<<<(nbins + 127) / 128, 128, 0, st>>>(part_sum, part_cnt, nparts, nbins, sums_out, counts_out);
+    count_launch();
+    T21_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+__global__ void zero_hist_kernel(double* sums, long long* counts, int nbins) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nbins) { sums[b] = 0.0; counts[b] = 0; }
+}
+int launch_zero_hist(double* sums, long long* counts, int nbins, cudaStream_t st) {
+    zero_hist_kernel<<<(nbins + 127) / 128, 128, 0, st>>>(sums, counts, nbins);
+    count_launch();
+    T21_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---- element-wise binning of a full (fftshifted) array ---------------------------------
+// Each thread owns runs of kRun consecutive z samples (neighbours share a bin most of the
+// time, so the run accumulator rarely touches the histogram).
+constexpr int kRun = 16;
+constexpr int kBinThreads = 256;
+
+template <typename T, int HK>
+__global__ void __launch_bounds__(kBinThreads)
+bin_only_kernel(const T* __restrict__ p, const __grid_constant__ t21_binspec B, int nbins,
+                double* __restrict__ part_sum, unsigned* __restrict__ part_cnt, double* gsum,
+                unsigned long long* gcnt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* hs = reinterpret_cast<double*>(smem_raw);
+    unsigned* hc = reinterpret_cast<unsigned*>(hs + nbins);
+    if (HK == 0) {
+        for (int b = threadIdx.x; b < nbins; b += kBinThreads) { hs[b] = 0.0; hc[b] = 0u; }
+        __syncthreads();
+    }
+    const long long n2 = B.n[2], n1 = B.n[1];
+    const long long total = (long long)B.n[0] * n1 * n2;
+    const long long nruns = (total + kRun - 1) / kRun;
+    RunAcc acc;
+    run_init(acc);
+    SmemHist sh{hs, hc};
+    GlobalHist gh{gsum, gcnt};
+    for (long long run = (long long)blockIdx.x * kBinThreads + threadIdx.x; run < nruns;
+         run += (long long)gridDim.x * kBinThreads) {
+        long long o = run * kRun;
+        int iz = (int)(o % n2);
+        long long t = o / n2;
+        int iy = (int)(t % n1);
+        int ix = (int)(t / n1);
+        const long long end = (o + kRun < total) ? o + kRun : total;
+        for (; o < end; ++o) {
+            const ModeBins mb = classify(B, ix, iy, iz, false);
+            const double v = (double)p[o];
+            if (HK == 0) run_add(acc, sh, mb.own, v, mb.own_w);
+            else run_add(acc, gh, mb.own, v, mb.own_w);
+            if (++iz == n2) { iz = 0; if (++iy == n1) { iy = 0; ++ix; } }
+        }
+    }
+    if (HK == 0) {
+        run_flush(acc, sh);
+        __syncthreads();
+        for (int b = threadIdx.x; b < nbins; b += kBinThreads) {
+            part_sum[(size_t)blockIdx.x * nbins + b] = hs[b];
+            part_cnt[(size_t)blockIdx.x * nbins + b] = hc[b];
+        }
+    } else {
+        run_flush(acc, gh);
+    }
+}
+
+int launch_bin_only(const void* p, int dtype, const t21_binspec& spec, double* part_sum, unsigned* part_cnt,
+                    int max_grid, double* gsum, long long* gcnt, int* grid_used, cudaStream_t st) {
+    const int nbins = spec.nk * (spec.nmu > 0 ? spec.nmu : 1);
+    const bool global = nbins > kSmemHistMaxBins;   // then gsum/gcnt are the pre-zeroed final outputs
+    const long long total = (long long)spec.n[0] * spec.n[1] * spec.n[2];
+    const long long nruns = (total + kRun - 1) / kRun;
+    long long g = (nruns + kBinThreads - 1) / kBinThreads;
+    const long long cap = (long long)device_sm_count() * 8;
+    if (g > cap) g = cap;
+    if (!global && g > max_grid) g = max_grid;
+    if (g < 1) g = 1;
+    const size_t smem = global ? 0 : (size_t)nbins * (sizeof(double) + sizeof(unsigned));
+    unsigned long long* gc = reinterpret_cast<unsigned long long*>(gcnt);
+    if (dtype == T21_F32) {
+        if (global) bin_only_kernel<float, 1><<<(int)g, kBinThreads, smem, st>>>((const float*)p, spec, nbins, nullptr, nullptr, gsum, gc);
+        else bin_only_kernel<float, 0><<<(int)g, kBinThreads, smem, st>>>((const float*)p, spec, nbins, part_sum, part_cnt, nullptr, nullptr);
+    } else {
+        if (global) bin_only_kernel<double, 1><<<(int)g, kBinThreads, smem, st>>>((const double*)p, spec, nbins, nullptr, nullptr, gsum, gc);
+        else bin_only_kernel<double, 0><<<(int)g, kBinThreads, smem, st>>>((const double*)p, spec, nbins, part_sum, part_cnt, nullptr, nullptr);
+    }
+    count_launch();
+    T21_CUDA_OK(cudaGetLastError());
+    *grid_used = (int)g;
+    return 0;
+}
+
+}  // namespace t21

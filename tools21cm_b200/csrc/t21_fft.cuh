@@ -34,20 +34,36 @@ constexpr double cos32(int i) {
 }
 constexpr double sin32(int i) { return cos32((i + 24) & 31); }
 
-// v *= exp(-2*pi*i*k/R), with the trivial cases folded after unrolling
-template <int R, typename T>
-T21_HD cx<T> rot(cx<T> v, int k) {
-    const int idx = k * (32 / R);  // in 32nds of a turn
-    if (idx == 0) return v;
-    if (idx == 8) return cmake<T>(v.y, -v.x);                       // * -i
-    if (idx == 16) return cmake<T>(-v.x, -v.y);
-    if (idx == 24) return cmake<T>(-v.y, v.x);                      // * +i
-    const T h = (T)kCos32[4];  // sqrt(1/2)
-    if (idx == 4) return cmake<T>((v.x + v.y) * h, (v.y - v.x) * h);    // * (1-i)/sqrt2
-    if (idx == 12) return cmake<T>((v.y - v.x) * h, -(v.x + v.y) * h);  // * (-1-i)/sqrt2
-    const T c = (T)cos32(idx), s = (T)sin32(idx);
-    // general: (x + iy)(c - is) = (xc + ys) + i(yc - xs)
-    return cmake<T>(v.x * c + v.y * s, v.y * c - v.x * s);
+// v *= exp(-2*pi*i*K/R).  K is a template parameter so the constants are evaluated by the
+// front end (device code may not index a host constexpr array with a run-time value).
+template <int R, int K, typename T>
+T21_HD cx<T> rot(cx<T> v) {
+    constexpr int idx = K * (32 / R);  // in 32nds of a turn
+    if constexpr (idx == 0) {
+        return v;
+    } else if constexpr (idx == 8) {
+        return cmake<T>(v.y, -v.x);                        // * -i
+    } else if constexpr (idx == 4) {
+        constexpr T h = (T)0.70710678118654752440084436210485;
+        return cmake<T>((v.x + v.y) * h, (v.y - v.x) * h);     // * (1-i)/sqrt2
+    } else if constexpr (idx == 12) {
+        constexpr T h = (T)0.70710678118654752440084436210485;
+        return cmake<T>((v.y - v.x) * h, -(v.x + v.y) * h);    // * (-1-i)/sqrt2
+    } else {
+        constexpr T c = (T)cos32(idx), s = (T)sin32(idx);
+        // (x + iy)(c - is) = (xc + ys) + i(yc - xs)
+        return cmake<T>(v.x * c + v.y * s, v.y * c - v.x * s);
+    }
+}
+
+template <int R, typename T, int K = 0>
+T21_HD void dft_combine(cx<T>* v, const cx<T>* e, const cx<T>* o) {
+    if constexpr (K < R / 2) {
+        const cx<T> t = rot<R, K, T>(o[K]);
+        v[K] = cadd(e[K], t);
+        v[K + R / 2] = csub(e[K], t);
+        dft_combine<R, T, K + 1>(v, e, o);
+    }
 }
 
 template <int R, typename T>
@@ -60,12 +76,7 @@ struct DFT {
         for (int i = 0; i < R / 2; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
         DFT<R / 2, T>::run(e);
         DFT<R / 2, T>::run(o);
-#pragma unroll
-        for (int k = 0; k < R / 2; ++k) {
-            cx<T> t = rot<R, T>(o[k], k);
-            v[k] = cadd(e[k], t);
-            v[k + R / 2] = csub(e[k], t);
-        }
+        dft_combine<R, T>(v, e, o);
     }
 };
 template <typename T>

@@ -1,0 +1,71 @@
+// Internal, type-erased interfaces between the translation units of libt21ps.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/t21ps.h"
+
+namespace t21 {
+
+// widest pow2 pencil the Stockham kernels are instantiated for; other lengths take the
+// generic DFT kernels (t21_generic.cu)
+constexpr int kMinFast = 8;
+constexpr int kMaxFast = 4096;
+inline bool fast_len(int n) { return n >= kMinFast && n <= kMaxFast && (n & (n - 1)) == 0; }
+
+// columns of the half spectrum a strided CTA owns (WZ * sizeof(complex) contiguous bytes per row)
+template <typename T, int N>
+struct WZFor {
+    static constexpr int value = sizeof(T) == 4 ? (N <= 512 ? 16 : (N <= 2048 ? 8 : 4))
+                                                : (N <= 512 ? 8 : (N <= 2048 ? 4 : 2));
+};
+
+struct ZArgs {
+    const void* in; void* out; long long nrows; int nz; int pitch;
+    const void* offset; const void* tw; const void* twr;
+};
+struct YArgs {
+    void* w; long long nouter; int ny; int nzh; int pitch; const void* tw;
+};
+struct XArgs {
+    const void* w[2]; int nf; int nx, ny, nz, nzh, pitch;
+    const void* tw; const void* offset[2]; double ntot;
+    const t21_binspec* bins;                 // MODE_BIN
+    void* nd_out; int nd_f64; double scale;  // MODE_ND
+    // histogram plumbing (MODE_BIN)
+    int nbins; int hist_global;              // 1: accumulate straight into gsum/gcnt
+    double* part_sum; unsigned* part_cnt;    // [grid][nbins] per-CTA partials
+    double* gsum; unsigned long long* gcnt;
+    int max_grid;                            // capacity of the partial buffers, in CTAs
+    int grid_used;                           // out
+};
+
+int launch_zpass(int dtype, const ZArgs& a, cudaStream_t st);
+int launch_ypass(int dtype, const YArgs& a, cudaStream_t st);
+int launch_xpass_f32_bin(XArgs& a, cudaStream_t st);
+int launch_xpass_f32_nd(XArgs& a, cudaStream_t st);
+int launch_xpass_f64_bin(XArgs& a, cudaStream_t st);
+int launch_xpass_f64_nd(XArgs& a, cudaStream_t st);
+
+// t21_aux.cu
+int launch_mean_estimate(int dtype, const void* x, long long n, void* offset_out, cudaStream_t st);
+int launch_reduce_partials(const double* part_sum, const unsigned* part_cnt, int nparts, int nbins,
+                           double* sums_out, long long* counts_out, cudaStream_t st);
+int launch_zero_hist(double* sums, long long* counts, int nbins, cudaStream_t st);
+int launch_bin_only(const void* p, int dtype, const t21_binspec& spec, double* part_sum, unsigned* part_cnt,
+                    int max_grid, double* gsum, long long* gcnt, int* grid_used, cudaStream_t st);
+
+// error plumbing (t21_api.cu)
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+void count_launch();
+
+constexpr int kSmemHistMaxBins = 2048;   // CTA histograms up to this many bins live in shared memory
+int device_sm_count();
+
+}  // namespace t21
+
+#define T21_CUDA_OK(expr)                                              \
+    do {                                                               \
+        cudaError_t e__ = (expr);                                      \
+        if (e__ != cudaSuccess) return ::t21::cuda_fail(e__, #expr);   \
+    } while (0)

@@ -1,0 +1,165 @@
+// __global__ wrappers that run the phase-structured pass bodies, and their launchers.
+#pragma once
+#include "t21_internal.h"
+#include "t21_passes.cuh"
+
+namespace t21 {
+
+template <class K, typename T, int PH = 0>
+__device__ __forceinline__ void dev_phases(const typename K::Params& p, long long cta, int tid,
+                                           typename K::Regs& r, cx<T>* smem) {
+    K::template phase<PH>(p, cta, tid, r, smem);
+    if constexpr (PH + 1 < K::NPHASE) {
+        __syncthreads();
+        dev_phases<K, T, PH + 1>(p, cta, tid, r, smem);
+    }
+}
+template <class K, typename T, class Hist, int PH = 0>
+__device__ __forceinline__ void dev_phases_hist(const typename K::Params& p, long long tile, int tid,
+                                                typename K::Regs& r, cx<T>* smem, Hist& h) {
+    K::template phase<PH>(p, tile, tid, r, smem, h);
+    if constexpr (PH + 1 < K::NPHASE) {
+        __syncthreads();
+        dev_phases_hist<K, T, Hist, PH + 1>(p, tile, tid, r, smem, h);
+    }
+}
+
+// one CTA per tile (Z and Y passes)
+template <class K, typename T>
+__global__ void __launch_bounds__(K::THREADS) tile_kernel(const __grid_constant__ typename K::Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typename K::Regs r;
+    dev_phases<K, T>(p, (long long)blockIdx.x, (int)threadIdx.x, r, reinterpret_cast<cx<T>*>(smem_raw));
+}
+
+struct NoHist {
+    __device__ void add(int, double, unsigned) {}
+};
+
+// persistent X pass: each CTA walks tiles blockIdx.x, +gridDim.x, ... and keeps its histogram
+// in shared memory until the end (HK = 0), accumulates into global memory (HK = 1), or has no
+// histogram at all (HK = 2, n-D store).
+template <class K, typename T, int HK>
+__global__ void __launch_bounds__(K::THREADS)
+xpass_kernel(const __grid_constant__ typename K::Params p, int nbins, double* __restrict__ part_sum,
+             unsigned* __restrict__ part_cnt, double* gsum, unsigned long long* gcnt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* ex = reinterpret_cast<cx<T>*>(smem_raw);
+    const int tid = threadIdx.x;
+    typename K::Regs r;
+    run_init(r.acc[0]);
+    run_init(r.acc[1]);
+    if constexpr (HK == 0) {
+        double* hs = reinterpret_cast<double*>(smem_raw + sizeof(cx<T>) * K::SMEM_ELEMS);
+        unsigned* hc = reinterpret_cast<unsigned*>(hs + nbins);
+        for (int b = tid; b < nbins; b += K::THREADS) { hs[b] = 0.0; hc[b] = 0u; }
+        __syncthreads();
+        SmemHist hist{hs, hc};
+        for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
+            dev_phases_hist<K, T, SmemHist>(p, tile, tid, r, ex, hist);
+        run_flush(r.acc[0], hist);
+        run_flush(r.acc[1], hist);
+        __syncthreads();
+        for (int b = tid; b < nbins; b += K::THREADS) {
+            part_sum[(size_t)blockIdx.x * nbins + b] = hs[b];
+            part_cnt[(size_t)blockIdx.x * nbins + b] = hc[b];
+        }
+    } else if constexpr (HK == 1) {
+        GlobalHist hist{gsum, gcnt};
+        for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
+            dev_phases_hist<K, T, GlobalHist>(p, tile, tid, r, ex, hist);
+        run_flush(r.acc[0], hist);
+        run_flush(r.acc[1], hist);
+    } else {
+        NoHist hist;
+        for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
+            dev_phases_hist<K, T, NoHist>(p, tile, tid, r, ex, hist);
+    }
+}
+
+template <class Kern>
+inline int ensure_smem(Kern kern, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        T21_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    }
+    return 0;
+}
+
+template <class K, typename T>
+inline int launch_tiles(const typename K::Params& p, long long nctas, cudaStream_t st) {
+    if (nctas <= 0) return 0;
+    if (nctas > 2147483647LL) { set_error("grid too large"); return T21_EINVAL; }
+    const size_t smem = sizeof(cx<T>) * K::SMEM_ELEMS;
+    auto kern = tile_kernel<K, T>;
+    if (int rc = ensure_smem(kern, smem)) return rc;
+    kern<<<(unsigned)nctas, K::THREADS, smem, st>>>(p);
+    count_launch();
+    T21_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <class K, typename T>
+inline int launch_x(XArgs& a, cudaStream_t st) {
+    typename K::Params p;
+    memset(&p, 0, sizeof(p));
+    p.w[0] = (const cx<T>*)a.w[0];
+    p.w[1] = (const cx<T>*)a.w[1];
+    p.ny = a.ny; p.nz = a.nz; p.nzh = a.nzh; p.pitch = a.pitch;
+    constexpr int WZ = K::THREADS / K::S::TP;
+    p.nchunks = (a.nzh + WZ - 1) / WZ;
+    p.ntiles = (long long)a.ny * p.nchunks;
+    p.tw = (const cx<T>*)a.tw;
+    p.offset[0] = (const T*)a.offset[0];
+    p.offset[1] = (const T*)a.offset[1];
+    p.ntot = a.ntot;
+    if (a.bins) p.bins = *a.bins;
+    p.nd_out = a.nd_out; p.nd_f64 = a.nd_f64; p.scale = a.scale;
+
+    const bool is_bin = a.bins != nullptr;
+    const int hk = !is_bin ? 2 : (a.hist_global ? 1 : 0);
+    size_t smem = sizeof(cx<T>) * K::SMEM_ELEMS;
+    if (hk == 0) smem += (size_t)a.nbins * (sizeof(double) + sizeof(unsigned));
+    int occ = 0, grid = 0;
+#define T21_LAUNCH_HK(HKV)                                                                              \
+    {                                                                                                   \
+        auto kern = xpass_kernel<K, T, HKV>;                                                            \
+        if (int rc = ensure_smem(kern, smem)) return rc;                                                \
+        T21_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K::THREADS, smem));       \
+        if (occ < 1) { set_error("x pass does not fit on an SM (smem %zu)", smem); return T21_EINVAL; } \
+        long long g = (long long)occ * device_sm_count();                                               \
+        if (g > p.ntiles) g = p.ntiles;                                                                 \
+        if (HKV == 0 && g > a.max_grid) g = a.max_grid;                                                 \
+        grid = (int)g;                                                                                  \
+        kern<<<grid, K::THREADS, smem, st>>>(p, a.nbins, a.part_sum, a.part_cnt, a.gsum, a.gcnt);        \
+    }
+    if constexpr (K::kMode == MODE_BIN) {
+        if (hk == 0) T21_LAUNCH_HK(0) else if (hk == 1) T21_LAUNCH_HK(1)
+        else { set_error("binning pass called without a bin spec"); return T21_EINVAL; }
+    } else {
+        if (hk != 2) { set_error("n-D pass called with a bin spec"); return T21_EINVAL; }
+        T21_LAUNCH_HK(2)
+    }
+#undef T21_LAUNCH_HK
+    count_launch();
+    T21_CUDA_OK(cudaGetLastError());
+    a.grid_used = grid;
+    return 0;
+}
+
+// switch over the instantiated pencil lengths
+#define T21_FOR_FAST_N(n, MACRO)          \
+    switch (n) {                          \
+        case 8: MACRO(8); break;          \
+        case 16: MACRO(16); break;        \
+        case 32: MACRO(32); break;        \
+        case 64: MACRO(64); break;        \
+        case 128: MACRO(128); break;      \
+        case 256: MACRO(256); break;      \
+        case 512: MACRO(512); break;      \
+        case 1024: MACRO(1024); break;    \
+        case 2048: MACRO(2048); break;    \
+        case 4096: MACRO(4096); break;    \
+        default: set_error("length %d is not instantiated", n); return T21_EINVAL; \
+    }
+
+}  // namespace t21

@@ -173,6 +173,7 @@ struct XPass {
     static constexpr int THREADS = S::THREADS;
     static constexpr int SMEM_ELEMS = S::SMEM_ELEMS;
     static constexpr int NPHASE = NF * S::FFT_PHASES;   // the last phase of the last field holds the epilogue
+    static constexpr int kMode = MODE;
 
     struct Params {
         const cx<T>* w[2];    // [NX][ny][pitch] per field

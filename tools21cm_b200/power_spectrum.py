@@ -1,0 +1,526 @@
+"""Drop-in replacements for the estimators of tools21cm's ``power_spectrum.py``.
+
+Same names, positional order, defaults, ``**kwargs(boxsize)`` alias and return tuples as
+the reference (``/root/reference/src/tools21cm/power_spectrum.py``, cited per function).
+The arithmetic runs on the GPU through the C ABI in ``include/t21ps.h`` (hand-written
+sm_100a kernels, no cuFFT, no CPU fallback): this module only validates arguments,
+builds the float64 bin tables (``binspec.py``), owns device memory through torch
+tensors, and divides the returned sums by the mode counts.
+
+Inputs may be numpy arrays (results come back as numpy float64, exactly like the
+reference) or torch tensors on the CPU or on a CUDA device (no host round trip for the
+cube; small outputs still come back as numpy float64, n-D outputs stay on the device).
+float32 input is transformed in fp32, everything else in fp64 (the reference always
+uses float64; ``set_precision`` overrides the choice).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+
+from . import _lib
+from . import binspec as _bs
+from ._lib import T21_F32, T21_F64
+
+__all__ = ["power_spectrum_nd", "cross_power_spectrum_nd", "radial_average", "power_spectrum_1d",
+           "cross_power_spectrum_1d", "power_spectrum_mu", "cross_power_spectrum_mu", "mu_binning",
+           "dimensionless_ps", "anisotropy_ratio_r_mu", "get_k", "get_kbins", "apply_window",
+           "set_precision"]
+
+_PRECISION = None  # None: follow the input dtype; 'float32' / 'float64': force
+
+
+def set_precision(precision=None):
+    """Force the transform precision ('float32', 'float64') or follow the input dtype (None)."""
+    global _PRECISION
+    if precision not in (None, "float32", "float64"):
+        raise ValueError("precision must be None, 'float32' or 'float64'")
+    _PRECISION = precision
+
+
+# ----------------------------------------------------------------------------------------
+# device state: plans, workspace, uploaded bin specs (one per CUDA device)
+# ----------------------------------------------------------------------------------------
+def _torch():
+    import torch
+    return torch
+
+
+class _Device:
+    def __init__(self, index):
+        self.index = index
+        self.plans = {}
+        self.specs = OrderedDict()
+        self.ws = None
+
+    def plan(self, shape, dtype):
+        key = (tuple(shape), dtype)
+        p = self.plans.get(key)
+        if p is None:
+            lib = _lib.load()
+            h = C.c_void_p()
+            _lib.check(lib.t21_plan_create(C.byref(h), shape[0], shape[1], shape[2], dtype, self.index),
+                       "t21_plan_create")
+            p = self.plans[key] = h
+        return p
+
+    def workspace(self, nbytes):
+        torch = _torch()
+        if self.ws is None or self.ws.numel() < nbytes:
+            self.ws = None
+            self.ws = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda:%d" % self.index)
+        return self.ws
+
+    def spec(self, key, builder):
+        hit = self.specs.get(key)
+        if hit is not None:
+            self.specs.move_to_end(key)
+            return hit
+        torch = _torch()
+        spec = builder()
+
+        def upload(blob):
+            t = torch.from_numpy(blob).to("cuda:%d" % self.index)
+            return t.data_ptr(), t
+
+        cspec, owner = _lib.pack_binspec(spec, upload)
+        hit = (spec, cspec, owner)
+        self.specs[key] = hit
+        while len(self.specs) > 64:
+            self.specs.popitem(last=False)
+        return hit
+
+
+_DEVICES = {}
+
+
+def _device(index):
+    d = _DEVICES.get(index)
+    if d is None:
+        d = _DEVICES[index] = _Device(index)
+    return d
+
+
+def _require_cuda():
+    torch = _torch()
+    _lib.load()
+    if not torch.cuda.is_available():
+        raise RuntimeError("tools21cm_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def _stage(arr):
+    """-> (contiguous CUDA tensor of float32/float64, was_numpy).  Never copies back."""
+    torch = _require_cuda()
+    was_numpy = not isinstance(arr, torch.Tensor)
+    if was_numpy:
+        a = np.asarray(arr)
+        if _PRECISION is not None:
+            want = np.dtype(_PRECISION)
+        else:
+            want = np.dtype(np.float32) if a.dtype == np.float32 else np.dtype(np.float64)
+        a = np.ascontiguousarray(a, dtype=want)
+        t = torch.from_numpy(a).to("cuda", non_blocking=False)
+    else:
+        t = arr
+        if _PRECISION is not None:
+            want = torch.float32 if _PRECISION == "float32" else torch.float64
+        else:
+            want = torch.float32 if t.dtype == torch.float32 else torch.float64
+        if not t.is_cuda:
+            t = t.to("cuda", non_blocking=True)
+        if t.dtype != want:
+            t = t.to(want)
+        t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    return t, was_numpy
+
+
+def _dtype_code(t):
+    return T21_F32 if t.dtype == _torch().float32 else T21_F64
+
+
+def _freeze(v):
+    if isinstance(v, np.ndarray):
+        return ("nd", v.dtype.str, v.shape, v.tobytes())
+    if isinstance(v, (list, tuple)):
+        return tuple(_freeze(x) for x in v)
+    return v
+
+
+def _stream_ptr(torch, dev_index):
+    return C.c_void_p(torch.cuda.current_stream(dev_index).cuda_stream)
+
+
+def _fused_binned(fields, spec_key, spec_builder):
+    """Run t21_ps_binned on one or two staged cubes.  Returns (spec, sums, counts) as numpy."""
+    torch = _torch()
+    x = fields[0]
+    if x.dim() != 3:
+        raise NotImplementedError("the fused estimator handles 3-dimensional cubes; got %d-D" % x.dim())
+    dev = _device(x.device.index)
+    with torch.cuda.device(x.device):
+        lib = _lib.load()
+        code = _dtype_code(x)
+        plan = dev.plan(tuple(x.shape), code)
+        spec, cspec, _owner = dev.spec((tuple(x.shape), spec_key), spec_builder)
+        nb = spec.nbins
+        need = lib.t21_workspace_bytes(plan, len(fields), nb)
+        ws = dev.workspace(need)
+        sums = torch.empty(nb, dtype=torch.float64, device=x.device)
+        counts = torch.empty(nb, dtype=torch.int64, device=x.device)
+        x2 = fields[1].data_ptr() if len(fields) == 2 else None
+        rc = lib.t21_ps_binned(plan, x.data_ptr(), x2, 1 if code == T21_F32 else 0, C.byref(cspec),
+                               sums.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(),
+                               _stream_ptr(torch, x.device.index))
+        _lib.check(rc, "t21_ps_binned")
+        out = torch.empty(2 * nb, dtype=torch.float64, device=x.device)
+        out[:nb] = sums
+        out[nb:] = counts.to(torch.float64)
+        host = out.cpu().numpy()
+    return spec, host[:nb].copy(), host[nb:].copy()
+
+
+def _fused_nd(fields, scale, out_dtype):
+    torch = _torch()
+    x = fields[0]
+    if x.dim() != 3:
+        raise NotImplementedError("the fused estimator handles 3-dimensional cubes; got %d-D" % x.dim())
+    dev = _device(x.device.index)
+    with torch.cuda.device(x.device):
+        lib = _lib.load()
+        code = _dtype_code(x)
+        plan = dev.plan(tuple(x.shape), code)
+        need = lib.t21_workspace_bytes(plan, len(fields), 0)
+        ws = dev.workspace(need)
+        out = torch.empty(tuple(x.shape), dtype=out_dtype, device=x.device)
+        x2 = fields[1].data_ptr() if len(fields) == 2 else None
+        rc = lib.t21_ps_nd(plan, x.data_ptr(), x2, 1 if code == T21_F32 else 0, float(scale), out.data_ptr(),
+                           T21_F32 if out_dtype == torch.float32 else T21_F64, ws.data_ptr(), ws.numel(),
+                           _stream_ptr(torch, x.device.index))
+        _lib.check(rc, "t21_ps_nd")
+    return out
+
+
+def _bin_only(arr_t, spec_key, spec_builder):
+    torch = _torch()
+    dev = _device(arr_t.device.index)
+    with torch.cuda.device(arr_t.device):
+        lib = _lib.load()
+        spec, cspec, _owner = dev.spec((tuple(arr_t.shape), spec_key), spec_builder)
+        nb = spec.nbins
+        need = lib.t21_bin_only_workspace_bytes(C.byref(cspec))
+        ws = dev.workspace(need)
+        sums = torch.empty(nb, dtype=torch.float64, device=arr_t.device)
+        counts = torch.empty(nb, dtype=torch.int64, device=arr_t.device)
+        rc = lib.t21_bin_only(arr_t.data_ptr(), _dtype_code(arr_t), C.byref(cspec), sums.data_ptr(),
+                              counts.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(torch, arr_t.device.index))
+        _lib.check(rc, "t21_bin_only")
+        s = sums.cpu().numpy()
+        c = counts.cpu().numpy().astype("float")
+    return spec, s, c
+
+
+def _finish(sums, counts, scale):
+    with np.errstate(all="ignore"):   # reference __init__.py:94-95: empty bins are NaN, silently
+        return sums * scale / counts
+
+
+# ----------------------------------------------------------------------------------------
+# host helpers the reference exposes (numpy, not on the hot path)
+# ----------------------------------------------------------------------------------------
+_get_dims = _bs.get_dims
+
+
+def apply_window(input_array, window):
+    """Taper along the last axis, in place like the reference (power_spectrum.py:12-21)."""
+    if window is None:
+        return input_array
+    from scipy.signal import windows
+    name = window.lower()   # an ndarray window fails here, exactly as in the reference
+    if name == "blackmanharris":
+        w = windows.blackmanharris(input_array.shape[-1])[None, None, :]
+    elif name == "tukey":
+        w = windows.tukey(input_array.shape[-1])[None, None, :]
+    else:
+        w = window
+    if isinstance(input_array, np.ndarray):
+        input_array *= w
+    else:
+        torch = _torch()
+        input_array *= torch.as_tensor(w, dtype=input_array.dtype, device=input_array.device)
+    return input_array
+
+
+def _get_k(input_array, box_dims):
+    """Full k grids on the host, for the sibling modules that import it (power_spectrum.py:449-478)."""
+    shape = tuple(input_array.shape)
+    nd = len(shape)
+    kax = [_bs.k_axis_shifted(shape[d], box_dims[d], nd) for d in range(nd)]
+    if nd == 1:
+        return [kax[0]], kax[0]
+    if nd == 2:
+        kx, ky = np.broadcast_arrays(kax[0][:, None], kax[1][None, :])
+        return [kx.copy(), ky.copy()], np.sqrt(kx ** 2 + ky ** 2)
+    kx, ky, kz = np.broadcast_arrays(kax[0][:, None, None], kax[1][None, :, None], kax[2][None, None, :])
+    return [kx.copy(), ky.copy(), kz.copy()], np.sqrt(kx ** 2 + ky ** 2 + kz ** 2)
+
+
+def _get_mu(k_comp, k, los_axis, absolute_mus):
+    """power_spectrum.py:481-502."""
+    if los_axis not in (0, 1, 2):
+        raise Exception("Your space is not %d-dimensional!" % los_axis)
+    with np.errstate(all="ignore"):
+        mu = np.abs(k_comp[los_axis] / k) if absolute_mus else k_comp[los_axis] / np.abs(k)
+    mu[np.where(k < 0.001)] = np.nan
+    return mu
+
+
+def _get_kbins(kbins, box_dims, k, binning="log", breakpoint=0.1, kmin=None, kmax=None):
+    """power_spectrum.py:505-519."""
+    if isinstance(kbins, int):
+        if kmin is None and kmax is None:
+            return _bs.make_k_edges(kbins, box_dims, k.max(), binning, breakpoint)
+        kmin = 2.0 * np.pi / min(box_dims) if kmin is None else kmin
+        kmax = k.max() if kmax is None else kmax
+        if binning == "linear":
+            return np.linspace(kmin, kmax, kbins + 1)
+        if binning == "log":
+            return 10 ** np.linspace(np.log10(kmin), np.log10(kmax), kbins + 1)
+        lo = np.linspace(kmin, kmax, kbins + 1)
+        hi = 10 ** np.linspace(np.log10(kmin), np.log10(kmax), kbins + 1)
+        return np.hstack((lo[lo < breakpoint], hi[hi > breakpoint]))
+    return kbins
+
+
+def _get_nonzero_idx(ps_shape, los_axis):
+    """power_spectrum.py:563-575."""
+    idx = np.indices(ps_shape)
+    perp = [a for a in (0, 1, 2) if a != los_axis] if los_axis in (0, 1) else [0, 1]
+    return np.invert((idx[perp[0]] == ps_shape[perp[0]] / 2) * (idx[perp[1]] == ps_shape[perp[1]] / 2))
+
+
+def get_k(input_array, box_dims):
+    """power_spectrum.py:437-439."""
+    return _get_k(input_array, _get_dims(box_dims, input_array.shape))
+
+
+def get_kbins(kbins, box_dims, k=None, array=None, binning="log"):
+    """power_spectrum.py:441-445."""
+    assert k is not None or array is not None
+    box_dims = _get_dims(box_dims, array.shape)
+    if k is None:
+        _, k = _get_k(array, box_dims)
+    return _get_kbins(kbins, box_dims, k, binning=binning)
+
+
+# ----------------------------------------------------------------------------------------
+# n-D spectra
+# ----------------------------------------------------------------------------------------
+def power_spectrum_nd(input_array, box_dims=None, verbose=False, **kwargs):
+    """Power spectrum on the fftshifted grid (reference power_spectrum.py:24-54).
+
+    numpy in -> numpy float64 out.  torch tensor in -> CUDA tensor out (dtype of the
+    transform unless ``out_dtype=`` is given)."""
+    if kwargs.get("boxsize") is not None:
+        box_dims = kwargs.get("boxsize")
+    box_dims = _get_dims(box_dims, input_array.shape)
+    if verbose:
+        print("Calculating power spectrum...")
+    x, was_numpy = _stage(input_array)
+    torch = _torch()
+    out_dtype = kwargs.get("out_dtype") or (torch.float64 if was_numpy else x.dtype)
+    out = _fused_nd([x], _bs.volume_scale(tuple(x.shape), box_dims), out_dtype)
+    if verbose:
+        print("...done")
+    return out.cpu().numpy() if was_numpy else out
+
+
+def cross_power_spectrum_nd(input_array1, input_array2, box_dims, **kwargs):
+    """Cross power spectrum on the fftshifted grid (reference power_spectrum.py:57-95)."""
+    assert (tuple(input_array1.shape) == tuple(input_array2.shape))
+    if kwargs.get("boxsize") is not None:
+        box_dims = kwargs.get("boxsize")
+    box_dims = _get_dims(box_dims, input_array1.shape)
+    a, was_numpy = _stage(input_array1)
+    b, _ = _stage(input_array2)
+    if b.dtype != a.dtype:
+        torch = _torch()
+        a, b = a.to(torch.float64), b.to(torch.float64)
+    torch = _torch()
+    out_dtype = kwargs.get("out_dtype") or (torch.float64 if was_numpy else a.dtype)
+    out = _fused_nd([a, b], _bs.volume_scale(tuple(a.shape), box_dims), out_dtype)
+    return out.cpu().numpy() if was_numpy else out
+
+
+# ----------------------------------------------------------------------------------------
+# stand-alone binning of caller-supplied fftshifted arrays
+# ----------------------------------------------------------------------------------------
+def radial_average(input_array, box_dims, kbins=10, binning="log", breakpoint=0.1, **kwargs):
+    """Shell average of an fftshifted 1-, 2- or 3-D array (reference power_spectrum.py:98-134).
+    Returns (mean, bin centres, n_modes)."""
+    if kwargs.get("boxsize") is not None:
+        box_dims = kwargs.get("boxsize")
+    box_dims = _get_dims(box_dims, input_array.shape)
+    t, _ = _stage(input_array)
+    shape = tuple(t.shape)
+    key = ("ravg", _freeze(list(box_dims)), _freeze(kbins), binning, breakpoint)
+    spec, sums, counts = _bin_only(t, key, lambda: _bs.build_binspec(
+        shape, box_dims, kbins, binning=binning, breakpoint=breakpoint, order="shifted"))
+    return _finish(sums, counts, 1.0), spec.k_centres(), counts
+
+
+def mu_binning(powerspectrum, los_axis=0, mubins=20, kbins=10, box_dims=None, weights=None,
+               exclude_zero_modes=True, binning="log", absolute_mus=True):
+    """(k, mu) averages of an fftshifted 3-D array (reference power_spectrum.py:380-435).
+    Like the reference it zeroes the centre sample of its input in place."""
+    if weights is not None:
+        # the reference cannot use weights either: an array fails at `weights != None`
+        # (power_spectrum.py:386), a scalar at `weights[idx]` (:433)
+        if np.ndim(weights) > 0:
+            raise ValueError("The truth value of an array with more than one element is ambiguous. "
+                             "Use a.any() or a.all()")
+        raise TypeError("'%s' object is not subscriptable" % type(weights).__name__)
+    assert (len(powerspectrum.shape) == 3)
+    box_dims = _get_dims(box_dims, powerspectrum.shape)
+    centre = tuple((np.array(powerspectrum.shape) / 2).astype(int))
+    powerspectrum[centre] = 0.0                                   # :414
+    t, _ = _stage(powerspectrum)
+    shape = tuple(t.shape)
+    key = ("mubin", _freeze(list(box_dims)), _freeze(kbins), _freeze(mubins), los_axis, binning,
+           bool(absolute_mus), bool(exclude_zero_modes))
+    spec, sums, counts = _bin_only(t, key, lambda: _bs.build_binspec(
+        shape, box_dims, kbins, binning=binning, mubins=mubins, los_axis=los_axis, absolute_mus=absolute_mus,
+        exclude_zero_modes=exclude_zero_modes, last_bin_closed=False, order="shifted"))
+    nmu, nk = spec.nmu, spec.nk
+    return (_finish(sums, counts, 1.0).reshape(nmu, nk), spec.mu_centres(), spec.k_centres(),
+            counts.reshape(nmu, nk))
+
+
+# ----------------------------------------------------------------------------------------
+# fused estimators
+# ----------------------------------------------------------------------------------------
+def _shell_estimate(fields, kbins, box_dims, binning, breakpoint):
+    shape = tuple(fields[0].shape)
+    key = ("1d", _freeze(list(box_dims)), _freeze(kbins), binning, breakpoint)
+    spec, sums, counts = _fused_binned(fields, key, lambda: _bs.build_binspec(
+        shape, box_dims, kbins, binning=binning, breakpoint=breakpoint))
+    return _finish(sums, counts, _bs.volume_scale(shape, box_dims)), spec.k_centres(), counts
+
+
+def _mu_estimate(fields, los_axis, mubins, kbins, box_dims, weights, exclude_zero_modes, absolute_mus):
+    if weights is not None:
+        if np.ndim(weights) > 0:
+            raise ValueError("The truth value of an array with more than one element is ambiguous. "
+                             "Use a.any() or a.all()")
+        raise TypeError("'%s' object is not subscriptable" % type(weights).__name__)
+    shape = tuple(fields[0].shape)
+    assert (len(shape) == 3)
+    key = ("mu", _freeze(list(box_dims)), _freeze(kbins), _freeze(mubins), los_axis, bool(absolute_mus),
+           bool(exclude_zero_modes))
+    spec, sums, counts = _fused_binned(fields, key, lambda: _bs.build_binspec(
+        shape, box_dims, kbins, binning="log", mubins=mubins, los_axis=los_axis, absolute_mus=absolute_mus,
+        exclude_zero_modes=exclude_zero_modes, last_bin_closed=False))
+    nmu, nk = spec.nmu, spec.nk
+    ps = _finish(sums, counts, _bs.volume_scale(shape, box_dims)).reshape(nmu, nk)
+    return ps, spec.mu_centres(), spec.k_centres(), counts.reshape(nmu, nk)
+
+
+def power_spectrum_1d(input_array_nd, kbins=100, box_dims=None, return_n_modes=False, binning="log",
+                      breakpoint=0.1, window=None, **kwargs):
+    """Spherically averaged power spectrum (reference power_spectrum.py:137-174).
+    Returns (Pk, k centres) or (Pk, k centres, n_modes)."""
+    input_array_nd = apply_window(input_array_nd, window)
+    if kwargs.get("boxsize") is not None:
+        box_dims = kwargs.get("boxsize")
+    box_dims = _get_dims(box_dims, input_array_nd.shape)
+    x, _ = _stage(input_array_nd)
+    ps, bins, n_modes = _shell_estimate([x], kbins, box_dims, binning, breakpoint)
+    if return_n_modes:
+        return ps, bins, n_modes
+    return ps, bins
+
+
+def cross_power_spectrum_1d(input_array1_nd, input_array2_nd, kbins=100, box_dims=None, return_n_modes=False,
+                            binning="log", breakpoint=0.1, **kwargs):
+    """Spherically averaged cross power spectrum (reference power_spectrum.py:257-289)."""
+    assert (tuple(input_array1_nd.shape) == tuple(input_array2_nd.shape))
+    if kwargs.get("boxsize") is not None:
+        box_dims = kwargs.get("boxsize")
+    box_dims = _get_dims(box_dims, input_array1_nd.shape)
+    a, _ = _stage(input_array1_nd)
+    b, _ = _stage(input_array2_nd)
+    if a.dtype != b.dtype:
+        torch = _torch()
+        a, b = a.to(torch.float64), b.to(torch.float64)
+    ps, bins, n_modes = _shell_estimate([a, b], kbins, box_dims, binning, breakpoint)
+    if return_n_modes:
+        return ps, bins, n_modes
+    return ps, bins
+
+
+def power_spectrum_mu(input_array, los_axis=0, mubins=20, kbins=10, box_dims=None, weights=None,
+                      exclude_zero_modes=True, return_n_modes=False, absolute_mus=True, **kwargs):
+    """P(k, mu) (reference power_spectrum.py:292-332; always log k bins, as there).
+    Returns (Pk[n_mu, n_k], mu centres, k centres[, n_modes])."""
+    if kwargs.get("boxsize") is not None:
+        box_dims = kwargs.get("boxsize")
+    box_dims = _get_dims(box_dims, input_array.shape)
+    x, _ = _stage(input_array)
+    ps, mu_bins, k_bins, n_modes = _mu_estimate([x], los_axis, mubins, kbins, box_dims, weights,
+                                                exclude_zero_modes, absolute_mus)
+    if return_n_modes:
+        return ps, mu_bins, k_bins, n_modes
+    return ps, mu_bins, k_bins
+
+
+def cross_power_spectrum_mu(input_array1, input_array2, los_axis=0, mubins=20, kbins=10, box_dims=None,
+                            weights=None, exclude_zero_modes=True, return_n_modes=False, absolute_mus=True,
+                            **kwargs):
+    """Cross P(k, mu) (reference power_spectrum.py:335-377)."""
+    assert (tuple(input_array1.shape) == tuple(input_array2.shape))
+    if kwargs.get("boxsize") is not None:
+        box_dims = kwargs.get("boxsize")
+    box_dims = _get_dims(box_dims, input_array1.shape)
+    a, _ = _stage(input_array1)
+    b, _ = _stage(input_array2)
+    if a.dtype != b.dtype:
+        torch = _torch()
+        a, b = a.to(torch.float64), b.to(torch.float64)
+    ps, mu_bins, k_bins, n_modes = _mu_estimate([a, b], los_axis, mubins, kbins, box_dims, weights,
+                                                exclude_zero_modes, absolute_mus)
+    if return_n_modes:
+        return ps, mu_bins, k_bins, n_modes
+    return ps, mu_bins, k_bins
+
+
+# ----------------------------------------------------------------------------------------
+# thin host post-processing on top of the estimators
+# ----------------------------------------------------------------------------------------
+def dimensionless_ps(data, kbins=100, box_dims=None, binning="log", factor=10):
+    """Delta^2(k) = P k^3 / 2 pi^2, interpolated from a finer binning (reference :536-561)."""
+    from scipy.interpolate import interp1d
+    pk, ks = power_spectrum_1d(data, kbins=kbins * factor, box_dims=box_dims, binning=binning)
+    f = interp1d(ks, pk * ks ** 3 / 2 / np.pi ** 2)
+    if binning == "log":
+        knew = 10 ** np.linspace(np.log10(ks[1]), np.log10(ks[-1]), kbins)
+    else:
+        knew = np.linspace(ks[1], ks[-1], kbins)
+    return f(knew), knew
+
+
+def anisotropy_ratio_r_mu(input_array, los_axis=0, mu_cut=0.5, mubins=20, kbins=10, box_dims=None, weights=None,
+                          exclude_zero_modes=True, return_n_modes=False, absolute_mus=True, **kwargs):
+    """r_mu(k) = <P(mu >= cut)> / <P(mu < cut)> - 1 (reference :578-613).  Returns (r_mu, k centres)."""
+    res = power_spectrum_mu(input_array, los_axis=los_axis, mubins=mubins, kbins=kbins, box_dims=box_dims,
+                            weights=weights, exclude_zero_modes=exclude_zero_modes, return_n_modes=False,
+                            absolute_mus=absolute_mus, **kwargs)
+    pk, mus, ks = res
+    with np.errstate(all="ignore"):
+        up = np.array([p[np.isfinite(p)].mean() for p in pk[mus >= mu_cut, :].T])
+        dn = np.array([p[np.isfinite(p)].mean() for p in pk[mus < mu_cut, :].T])
+        rmu = up / dn - 1.0
+    return rmu, ks

@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""Benchmark of the power-spectrum hot path (BASELINE.json metric: P(k) cubes/s at 1024^3 fp32).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size 1024]
+
+A step is one ``power_spectrum_1d`` (15 log bins, return_n_modes) over one synthetic toy-ionised
+21-cm brightness-temperature cube.  With N > 1 (torchrun, one rank per GPU) every rank transforms its
+own cube -- the "batches of coeval boxes, one per GPU" partition of the north star, no data-path
+collective -- and ``value`` is all cubes divided by the slowest rank's time ("scaling": "weak").
+
+Printed JSON (one line, rank 0): the driver contract plus
+  roofline      dominant kernel: algorithmic bytes per launch / CUDA-event duration vs the measured HBM peak
+  passes        the same for every pass, and for the whole pipeline (B_auto = 4N^3 + 4*8N^2(N/2+1) bytes)
+  e2e           the same call fed from pinned HOST memory, H2D copy and result read-back inside the timing
+  cpu_baseline  the CPU oracle (numpy/scipy port of the reference, 1 thread like the reference) on a bounded sample
+
+``--impl reference`` times that CPU port alone (rank 0 only) on the same metric/config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BOX_MPC = 500.0 / 0.7
+KBINS = 15
+CPU_SECONDS = {128: 0.34, 256: 3.1, 512: 17.5}   # survey measurements of the reference path, 1 thread
+
+
+def algorithmic_bytes(n):
+    c = 8 * n * n * (n // 2 + 1)
+    return {"z": 4 * n ** 3 + c, "y": 2 * c, "x": c, "pipeline": 4 * n ** 3 + 4 * c}
+
+
+def work_units(n):
+    """N^3 log2 N^3: how CPU time of the reference path scales between cube sizes."""
+    import math
+    return n ** 3 * 3 * math.log2(n)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md, MEASURED_PEAKS.json absent)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_seconds(n, repeats=1):
+    """Wall time of the CPU oracle (same scipy.fftpack / np.histogram calls as the reference) on an n^3 cube."""
+    import numpy as np
+    from oracle import ps_oracle          # the checker, timed as the CPU baseline -- never on the product path
+    from tools21cm_b200 import synthetic
+    cube = synthetic.gaussian_cube((n, n, n), seed=1234)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        with np.errstate(all="ignore"):
+            ps_oracle.power_spectrum_1d(cube, kbins=KBINS, box_dims=BOX_MPC, return_n_modes=True)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference is pure Python and
+    cannot travel to the GPU box) on the box's host cores.  One thread: scipy.fftpack and np.histogram
+    are single-threaded, exactly like the reference path."""
+    if rank != 0:
+        return
+    n = args.size
+    total = max(1, args.steps + args.warmup)
+    budget = 150.0 / total
+    sample = 128
+    for cand in (256, 512):
+        if CPU_SECONDS[cand] * 1.3 <= budget and cand <= n:
+            sample = cand
+    for _ in range(args.warmup):
+        cpu_oracle_seconds(sample)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_oracle_seconds(sample)
+    per_step = (time.perf_counter() - t0) / max(1, args.steps)
+    est = per_step * work_units(n) / work_units(sample)     # seconds per full-size cube
+    value = 1.0 / est
+    desc = ("power_spectrum_1d on one %d^3 cube per step (%.2f s), scaled to %d^3 by N^3 log N"
+            % (sample, per_step, n))
+    line = {
+        "impl": "reference", "metric": "P(k) cubes/sec at %d^3 fp32" % n, "value": value, "unit": "cubes/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": est * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(n),
+        "cpu_baseline": {"value": value, "unit": "cubes/s", "cores": 1, "kind": "port", "sample": desc,
+                         "host_cores": os.cpu_count()},
+        "e2e": {"value": value, "unit": "cubes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    return {"workload": "power_spectrum_1d, %d^3 fp32 toy-ionised dT cube, box_dims=500/0.7 cMpc, "
+                        "15 log kbins, return_n_modes" % n,
+            "cube": n, "kbins": KBINS, "binning": "log", "partition": "one cube per GPU, no collective",
+            "l2": "inputs (%.2f GB per cube) are larger than the 126 MB L2; no explicit flush" % (4 * n ** 3 / 1e9)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import tools21cm_b200 as t2c
+    from tools21cm_b200 import _lib, synthetic
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.size
+    lib = _lib.load()
+    x = synthetic.toy_dt_cube_torch((n, n, n), seed=1235 + rank, device=dev)
+
+    def step(inp):
+        return t2c.power_spectrum_1d(inp, kbins=KBINS, box_dims=BOX_MPC, return_n_modes=True)
+
+    for _ in range(args.warmup):
+        res = step(x)
+    barrier()
+
+    # ---- timed region: inputs resident in HBM ------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.t21_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        res = step(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = lib.t21_launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = world * args.steps / (ms / 1e3)
+
+    # ---- per-pass CUDA-event timing (same steps, events recorded between passes) ----------
+    import ctypes as C
+    lib.t21_profile(1)
+    acc = np.zeros(5)
+    buf = (C.c_float * 5)()
+    for _ in range(args.steps):
+        step(x)
+        lib.t21_profile_last(buf, 5)
+        acc += np.array(list(buf))
+    lib.t21_profile(0)
+    pass_ms = dict(zip(["mean", "z", "y", "x", "reduce"], (acc / args.steps).tolist()))
+    ab = algorithmic_bytes(n)
+    peak, peak_src = measured_peak()
+    passes = {}
+    for k in ("z", "y", "x"):
+        gbs = ab[k] / 1e9 / (pass_ms[k] / 1e3) if pass_ms[k] > 0 else 0.0
+        passes[k] = {"ms": pass_ms[k], "bytes": ab[k], "achieved_gbs": gbs, "frac": gbs / peak}
+    passes["mean"] = {"ms": pass_ms["mean"]}
+    passes["reduce"] = {"ms": pass_ms["reduce"]}
+    pipe_gbs = ab["pipeline"] / 1e9 / (ms_per_step / 1e3)
+    passes["pipeline"] = {"ms": ms_per_step, "bytes": ab["pipeline"], "achieved_gbs": pipe_gbs,
+                          "frac": pipe_gbs / peak, "frac_of_8TBs_nominal": pipe_gbs / 8000.0}
+    dom = max(("z", "y", "x"), key=lambda k: pass_ms[k])
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("%s_%d" % (dom, n))
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": {"z": "ZPass (tile_kernel)", "y": "YPass (tile_kernel)",
+                                           "x": "XPass (xpass_kernel)"}[dom],
+                "achieved": passes[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": passes[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                "share_of_step": pass_ms[dom] / max(1e-9, sum(pass_ms.values()))}
+
+    # ---- end to end: pinned host cube -> H2D -> estimator -> host result, all inside the timing ----
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((n, n, n), dtype=torch.float32, pin_memory=True)
+        host.copy_(x)
+        del x
+        torch.cuda.empty_cache()
+        for _ in range(2):
+            out = step(host)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.steps):
+            out = step(host)               # H2D of the cube + kernels + D2H of (ps, n_modes)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_e = e0.elapsed_time(e1)
+        wall_e = (time.perf_counter() - t0) * 1e3
+        ms_e = max(ms_e, wall_e)
+        if world > 1:
+            t = torch.tensor([ms_e], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e = float(t.item())
+        e2e = {"value": world * args.steps / (ms_e / 1e3), "unit": "cubes/s",
+               "h2d_bytes_per_step": 4 * n ** 3, "d2h_bytes_per_step": 2 * KBINS * 8,
+               "ms_per_step": ms_e / args.steps}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample = 512 if n >= 512 else n
+        sec = cpu_oracle_seconds(sample)
+        est = sec * work_units(n) / work_units(sample)
+        cpu = {"value": 1.0 / est, "unit": "cubes/s", "cores": 1, "kind": "port",
+               "sample": "oracle power_spectrum_1d on one %d^3 cube: %.2f s, scaled to %d^3 by N^3 log N "
+                         "(the full cube needs ~70 GB and minutes on the CPU path)" % (sample, sec, n),
+               "host_cores": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": "P(k) cubes/sec at %d^3 fp32" % n, "value": value, "unit": "cubes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(n), "clocks": clocks, "gpu_launches": int(launches),
+            "roofline": roofline, "passes": passes, "e2e": e2e, "cpu_baseline": cpu,
+            "n_modes_total": float(np.sum(res[2])),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

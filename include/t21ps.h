@@ -111,6 +111,12 @@ T21_API int t21_bin_only(const void* p_shifted, int dtype, const t21_binspec* sp
                  long long* counts_out, void* workspace, size_t workspace_bytes, void* stream);
 T21_API size_t t21_bin_only_workspace_bytes(const t21_binspec* spec);
 
+/* Per-pass timing for benchmarks: t21_profile(1) makes every call record CUDA events on the
+ * caller's stream between passes; t21_profile_last fills ms_out[0..4] with the milliseconds of
+ * {mean estimate, z pass, y pass, x pass, reduce} of the last call and returns 5. */
+T21_API int t21_profile(int enable);
+T21_API int t21_profile_last(float* ms_out, int cap);
+
 T21_API const char* t21_last_error(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 T21_API unsigned long long t21_launch_count(void);

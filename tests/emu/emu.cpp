@@ -78,10 +78,10 @@ static void xpass(const cx<T>* w0, const cx<T>* w1, int ny, int nz, int pitch, c
         std::vector<unsigned> hc(nb, 0u);
         SmemHist hist{hs.data(), hc.data()};
         std::vector<typename K::Regs> regs(K::THREADS);
-        for (auto& r : regs) { run_init(r.acc[0]); run_init(r.acc[1]); }
+        for (auto& r : regs) acc_init(r.acc);
         for (long long tile = cta; tile < p.ntiles; tile += nctas_emulated)
             run_hist<K, T, SmemHist>(p, tile, regs, smem.data(), hist);
-        for (auto& r : regs) { run_flush(r.acc[0], hist); run_flush(r.acc[1], hist); }
+        for (auto& r : regs) acc_flush(r.acc, hist);
         if (MODE == MODE_BIN)
             for (int b = 0; b < nb; ++b) { sums[b] += hs[b]; counts[b] += hc[b]; }
     }

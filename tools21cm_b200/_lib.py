@@ -131,6 +131,10 @@ def load():
     lib.t21_bin_only.restype = i32
     lib.t21_bin_only_workspace_bytes.argtypes = [C.POINTER(BinSpecC)]
     lib.t21_bin_only_workspace_bytes.restype = sz
+    lib.t21_profile.argtypes = [i32]
+    lib.t21_profile.restype = i32
+    lib.t21_profile_last.argtypes = [C.POINTER(C.c_float), i32]
+    lib.t21_profile_last.restype = i32
     lib.t21_last_error.argtypes = []
     lib.t21_last_error.restype = C.c_char_p
     lib.t21_launch_count.argtypes = []

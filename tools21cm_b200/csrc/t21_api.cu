@@ -41,6 +41,35 @@ int device_sm_count() {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// ---- optional per-pass timing (bench.py's roofline block) ------------------------------
+// When enabled, every public call records a CUDA event on the caller's stream after each
+// pass; t21_profile_last() turns them into per-slot durations.  Off by default.
+enum { SLOT_MEAN = 0, SLOT_Z, SLOT_Y, SLOT_X, SLOT_REDUCE, SLOT_COUNT };
+struct Prof {
+    bool on = false;
+    static constexpr int kMax = 16;
+    cudaEvent_t ev[kMax + 1];
+    int slot[kMax];
+    int n = 0;          // segments recorded in the last call
+    bool made = false;
+};
+static Prof g_prof;
+
+static void prof_begin(cudaStream_t st) {
+    if (!g_prof.on) return;
+    if (!g_prof.made) {
+        for (int i = 0; i <= Prof::kMax; ++i) cudaEventCreate(&g_prof.ev[i]);
+        g_prof.made = true;
+    }
+    g_prof.n = 0;
+    cudaEventRecord(g_prof.ev[0], st);
+}
+static void prof_mark(cudaStream_t st, int slot) {
+    if (!g_prof.on || g_prof.n >= Prof::kMax) return;
+    g_prof.slot[g_prof.n] = slot;
+    cudaEventRecord(g_prof.ev[++g_prof.n], st);
+}
+
 }  // namespace t21
 
 using namespace t21;
@@ -156,11 +185,14 @@ static int forward_zy(const t21_plan* p, const void* const x[2], int nf, int sub
             void* o = ws + L.offs + f * rsz;
             if (int rc = launch_mean_estimate(p->dtype, x[f], ntot, o, st)) return rc;
             offs[f] = o;
+            prof_mark(st, SLOT_MEAN);
         }
         ZArgs z{x[f], ws + L.w[f], (long long)p->n[0] * p->n[1], p->n[2], p->pitch, offs[f], p->tw[2], p->twr};
         if (int rc = launch_zpass(p->dtype, z, st)) return rc;
+        prof_mark(st, SLOT_Z);
         YArgs y{ws + L.w[f], (long long)p->n[0], p->n[1], p->nzh, p->pitch, p->tw[1]};
         if (int rc = launch_ypass(p->dtype, y, st)) return rc;
+        prof_mark(st, SLOT_Y);
     }
     return 0;
 }
@@ -191,6 +223,7 @@ int t21_ps_binned(const t21_plan* p, const void* x1, const void* x2, int subtrac
     unsigned char* ws = (unsigned char*)workspace;
     const void* x[2] = {x1, x2};
     const void* offs[2] = {nullptr, nullptr};
+    prof_begin(st);
     if (int rc = forward_zy(p, x, nf, subtract_mean, ws, L, offs, st)) return rc;
 
     XArgs a;
@@ -214,9 +247,12 @@ int t21_ps_binned(const t21_plan* p, const void* x1, const void* x2, int subtrac
         if (int rc = launch_zero_hist(sums_out, counts_out, nbins, st)) return rc;
     int rc = p->dtype == T21_F32 ? launch_xpass_f32_bin(a, st) : launch_xpass_f64_bin(a, st);
     if (rc) return rc;
-    if (!a.hist_global)
-        return launch_reduce_partials(a.part_sum, a.part_cnt, a.grid_used, nbins, sums_out, counts_out, st);
-    return T21_OK;
+    prof_mark(st, SLOT_X);
+    if (!a.hist_global) {
+        rc = launch_reduce_partials(a.part_sum, a.part_cnt, a.grid_used, nbins, sums_out, counts_out, st);
+        prof_mark(st, SLOT_REDUCE);
+    }
+    return rc;
 }
 
 int t21_ps_nd(const t21_plan* p, const void* x1, const void* x2, int subtract_mean, double scale, void* out,
@@ -231,6 +267,7 @@ int t21_ps_nd(const t21_plan* p, const void* x1, const void* x2, int subtract_me
     unsigned char* ws = (unsigned char*)workspace;
     const void* x[2] = {x1, x2};
     const void* offs[2] = {nullptr, nullptr};
+    prof_begin(st);
     if (int rc = forward_zy(p, x, nf, subtract_mean, ws, L, offs, st)) return rc;
     XArgs a;
     memset(&a, 0, sizeof(a));
@@ -243,7 +280,29 @@ int t21_ps_nd(const t21_plan* p, const void* x1, const void* x2, int subtract_me
     a.ntot = (double)p->n[0] * p->n[1] * p->n[2];
     a.nd_out = out; a.nd_f64 = out_dtype == T21_F64; a.scale = scale;
     a.max_grid = p->max_grid;
-    return p->dtype == T21_F32 ? launch_xpass_f32_nd(a, st) : launch_xpass_f64_nd(a, st);
+    const int rc = p->dtype == T21_F32 ? launch_xpass_f32_nd(a, st) : launch_xpass_f64_nd(a, st);
+    prof_mark(st, SLOT_X);
+    return rc;
+}
+
+int t21_profile(int enable) {
+    g_prof.on = enable != 0;
+    return T21_OK;
+}
+
+// ms_out[0..4] = milliseconds spent in {mean estimate, z pass, y pass, x pass, reduce} during the
+// last profiled call (summed over fields).  Blocks until that call has finished.
+int t21_profile_last(float* ms_out, int cap) {
+    if (!ms_out || cap < SLOT_COUNT) { set_error("need room for %d slots", (int)SLOT_COUNT); return T21_EINVAL; }
+    for (int i = 0; i < cap; ++i) ms_out[i] = 0.f;
+    if (!g_prof.made || g_prof.n == 0) return 0;
+    T21_CUDA_OK(cudaEventSynchronize(g_prof.ev[g_prof.n]));
+    for (int i = 0; i < g_prof.n; ++i) {
+        float ms = 0.f;
+        T21_CUDA_OK(cudaEventElapsedTime(&ms, g_prof.ev[i], g_prof.ev[i + 1]));
+        ms_out[g_prof.slot[i]] += ms;
+    }
+    return SLOT_COUNT;
 }
 
 size_t t21_bin_only_workspace_bytes(const t21_binspec* spec) {

@@ -8,9 +8,8 @@
 //              domain (binspec.py), k = sqrt(s), mu = k_los / k (power_spectrum.py:498),
 //              half-open comparisons (:424-428) -- so mode counts are bit-identical.
 //
-// RunAcc:  a thread walks its modes in order of |k_x|; neighbours mostly share a bin, so
-//   it keeps (bin, sum, count) in registers and only touches the CTA histogram when the
-//   bin changes ("warp-aggregated atomics" degenerate to one atomic per run).
+// Accumulation: see WarpBins (X pass: warp-uniform bin cache, one histogram update per
+//   eviction) and RunAcc (per-thread run-length accumulator for slowly varying bins).
 #pragma once
 #include "t21_common.cuh"
 #include "../../include/t21ps.h"
@@ -133,7 +132,9 @@ T21_HD ModeBins classify(const t21_binspec& B, int ix, int iy, int iz, bool has_
     return r;
 }
 
-// ---- run-length accumulator ----------------------------------------------------------
+// ---- accumulators ---------------------------------------------------------------------
+// RunAcc: per-thread run-length accumulator.  Used where one thread walks modes whose bin
+// changes slowly (t21_bin_only: consecutive z samples) and by the CPU replay of the X pass.
 struct RunAcc {
     int bin;
     unsigned cnt;
@@ -155,7 +156,122 @@ T21_HD void run_add(RunAcc& a, Hist& h, int bin, double p, int w) {
     a.cnt += (unsigned)w;
 }
 
-// CTA histogram in shared memory (device) / plain arrays (host emulation)
+// WarpBins: what the X pass uses on the device.  In the X pass the 32 lanes of a warp hold
+// neighbouring modes (16 adjacent kz x 2 adjacent kx for the same register slot), which almost
+// always share a bin, while the 16 slots of one thread are spread over all kx and do not.
+// So the bin ids are kept WARP-UNIFORM in a small cache, each lane keeps a private partial
+// sum per cache entry, and the shared histogram is touched only when an entry is evicted:
+// one shuffle reduction and one add by lane 0 ("warp-aggregated atomics").  Lanes whose bin
+// differs from the leader's are served in a second trip of the loop; nobody ever issues a
+// per-lane atomic.  Every lane of the warp must call add() the same number of times.
+constexpr int kWarpBinEntries = 4;
+struct WarpBins {
+#if T21_DEVICE_CODE
+    int bin[kWarpBinEntries];        // warp-uniform, -1 = empty
+    unsigned cnt[kWarpBinEntries];   // per lane
+    double sum[kWarpBinEntries];     // per lane
+    int victim;                      // warp-uniform round-robin pointer
+#else
+    RunAcc run;
+#endif
+};
+
+T21_HD void warpbins_init(WarpBins& a) {
+#if T21_DEVICE_CODE
+#pragma unroll
+    for (int c = 0; c < kWarpBinEntries; ++c) { a.bin[c] = -1; a.cnt[c] = 0; a.sum[c] = 0.0; }
+    a.victim = 0;
+#else
+    run_init(a.run);
+#endif
+}
+
+#if T21_DEVICE_CODE
+template <class Hist>
+__device__ __forceinline__ void warpbins_evict(WarpBins& a, Hist& h, int c) {
+    // c is a compile-time constant at every call site (unrolled), so a.*[c] stay in registers
+    double s = a.sum[c];
+    unsigned n = a.cnt[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+    }
+    if ((threadIdx.x & 31) == 0 && n) h.add(a.bin[c], s, n);
+    a.sum[c] = 0.0;
+    a.cnt[c] = 0;
+}
+#endif
+
+// valid: this lane has a mode to add (false for padding lanes); bin < 0 means "in no bin"
+template <class Hist>
+T21_HD void warpbins_add(WarpBins& a, Hist& h, int bin, double p, int w, bool valid) {
+#if T21_DEVICE_CODE
+    unsigned todo = __ballot_sync(0xffffffffu, valid && bin >= 0);
+    while (todo) {                                   // warp-uniform loop: one trip per distinct bin
+        const int leader = __ffs(todo) - 1;
+        const int ref = __shfl_sync(0xffffffffu, bin, leader);
+        const bool mine = valid && bin == ref;
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+        bool hit = false;
+#pragma unroll
+        for (int c = 0; c < kWarpBinEntries; ++c) {
+            if (!hit && a.bin[c] == ref) {           // warp-uniform branch
+                hit = true;
+                if (mine) { a.sum[c] += (w == 2) ? (p + p) : p; a.cnt[c] += (unsigned)w; }
+            }
+        }
+        if (!hit) {
+#pragma unroll
+            for (int c = 0; c < kWarpBinEntries; ++c) {
+                if (c == a.victim) {                 // warp-uniform branch
+                    if (a.bin[c] >= 0) warpbins_evict(a, h, c);
+                    a.bin[c] = ref;
+                    if (mine) { a.sum[c] = (w == 2) ? (p + p) : p; a.cnt[c] = (unsigned)w; }
+                }
+            }
+            a.victim = (a.victim + 1 == kWarpBinEntries) ? 0 : a.victim + 1;
+        }
+    }
+#else
+    if (valid) run_add(a.run, h, bin, p, w);
+#endif
+}
+
+template <class Hist>
+T21_HD void warpbins_flush(WarpBins& a, Hist& h) {
+#if T21_DEVICE_CODE
+#pragma unroll
+    for (int c = 0; c < kWarpBinEntries; ++c)
+        if (a.bin[c] >= 0) { warpbins_evict(a, h, c); a.bin[c] = -1; }
+#else
+    run_flush(a.run, h);
+#endif
+}
+
+// ThreadBins: per-thread run-length accumulators (own / twin).  Used by CTAs smaller than a
+// warp (pencils shorter than 32 samples, where speed is irrelevant) and by the CPU replay.
+struct ThreadBins {
+    RunAcc run[2];
+};
+
+// one interface over both accumulators; `which` = 0 for the stored mode, 1 for its twin
+T21_HD void acc_init(WarpBins& a) { warpbins_init(a); }
+T21_HD void acc_init(ThreadBins& a) { run_init(a.run[0]); run_init(a.run[1]); }
+template <class Hist>
+T21_HD void acc_add(WarpBins& a, Hist& h, int, int bin, double p, int w, bool valid) {
+    warpbins_add(a, h, bin, p, w, valid);
+}
+template <class Hist>
+T21_HD void acc_add(ThreadBins& a, Hist& h, int which, int bin, double p, int w, bool valid) {
+    if (valid) run_add(a.run[which], h, bin, p, w);
+}
+template <class Hist>
+T21_HD void acc_flush(WarpBins& a, Hist& h) { warpbins_flush(a, h); }
+template <class Hist>
+T21_HD void acc_flush(ThreadBins& a, Hist& h) { run_flush(a.run[0], h); run_flush(a.run[1], h); }
+
+// CTA histogram in shared memory, updated with atomics (device) / plain arrays (host replay)
 struct SmemHist {
     double* sum;
     unsigned* cnt;
@@ -167,6 +283,13 @@ struct SmemHist {
         sum[bin] += s; cnt[bin] += c;
 #endif
     }
+};
+// One histogram per warp in shared memory: only lane 0 of the owning warp ever writes it, in
+// program order, so no atomics are needed and the result is bit-reproducible run to run.
+struct WarpPrivHist {
+    double* sum;      // already offset to this warp's copy
+    unsigned* cnt;
+    T21_HD void add(int bin, double s, unsigned c) { sum[bin] += s; cnt[bin] += c; }
 };
 // direct global accumulation, used when the histogram does not fit in shared memory
 struct GlobalHist {

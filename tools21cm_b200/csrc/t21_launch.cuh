@@ -41,35 +41,46 @@ struct NoHist {
 // histogram at all (HK = 2, n-D store).
 template <class K, typename T, int HK>
 __global__ void __launch_bounds__(K::THREADS)
-xpass_kernel(const __grid_constant__ typename K::Params p, int nbins, double* __restrict__ part_sum,
-             unsigned* __restrict__ part_cnt, double* gsum, unsigned long long* gcnt) {
+xpass_kernel(const __grid_constant__ typename K::Params p, int nbins, int warp_private,
+             double* __restrict__ part_sum, unsigned* __restrict__ part_cnt, double* gsum, unsigned long long* gcnt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<T>* ex = reinterpret_cast<cx<T>*>(smem_raw);
     const int tid = threadIdx.x;
     typename K::Regs r;
-    run_init(r.acc[0]);
-    run_init(r.acc[1]);
+    acc_init(r.acc);
     if constexpr (HK == 0) {
+        // shared-memory histogram: one copy per warp when that fits (plain adds by lane 0, summed
+        // in warp order at the end => bit-reproducible), otherwise one copy updated with atomics
+        constexpr int NW = (K::THREADS + 31) / 32;
+        const int copies = warp_private ? NW : 1;
         double* hs = reinterpret_cast<double*>(smem_raw + sizeof(cx<T>) * K::SMEM_ELEMS);
-        unsigned* hc = reinterpret_cast<unsigned*>(hs + nbins);
-        for (int b = tid; b < nbins; b += K::THREADS) { hs[b] = 0.0; hc[b] = 0u; }
+        unsigned* hc = reinterpret_cast<unsigned*>(hs + (size_t)copies * nbins);
+        for (int b = tid; b < copies * nbins; b += K::THREADS) { hs[b] = 0.0; hc[b] = 0u; }
         __syncthreads();
-        SmemHist hist{hs, hc};
-        for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
-            dev_phases_hist<K, T, SmemHist>(p, tile, tid, r, ex, hist);
-        run_flush(r.acc[0], hist);
-        run_flush(r.acc[1], hist);
+        if (warp_private) {
+            WarpPrivHist hist{hs + (size_t)(tid >> 5) * nbins, hc + (size_t)(tid >> 5) * nbins};
+            for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
+                dev_phases_hist<K, T, WarpPrivHist>(p, tile, tid, r, ex, hist);
+            acc_flush(r.acc, hist);
+        } else {
+            SmemHist hist{hs, hc};
+            for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
+                dev_phases_hist<K, T, SmemHist>(p, tile, tid, r, ex, hist);
+            acc_flush(r.acc, hist);
+        }
         __syncthreads();
         for (int b = tid; b < nbins; b += K::THREADS) {
-            part_sum[(size_t)blockIdx.x * nbins + b] = hs[b];
-            part_cnt[(size_t)blockIdx.x * nbins + b] = hc[b];
+            double s = 0.0;
+            unsigned c = 0;
+            for (int w = 0; w < copies; ++w) { s += hs[(size_t)w * nbins + b]; c += hc[(size_t)w * nbins + b]; }
+            part_sum[(size_t)blockIdx.x * nbins + b] = s;
+            part_cnt[(size_t)blockIdx.x * nbins + b] = c;
         }
     } else if constexpr (HK == 1) {
         GlobalHist hist{gsum, gcnt};
         for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
             dev_phases_hist<K, T, GlobalHist>(p, tile, tid, r, ex, hist);
-        run_flush(r.acc[0], hist);
-        run_flush(r.acc[1], hist);
+        acc_flush(r.acc, hist);
     } else {
         NoHist hist;
         for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
@@ -118,7 +129,11 @@ inline int launch_x(XArgs& a, cudaStream_t st) {
     const bool is_bin = a.bins != nullptr;
     const int hk = !is_bin ? 2 : (a.hist_global ? 1 : 0);
     size_t smem = sizeof(cx<T>) * K::SMEM_ELEMS;
-    if (hk == 0) smem += (size_t)a.nbins * (sizeof(double) + sizeof(unsigned));
+    // per-warp histogram copies when they are small (and the CTA is made of whole warps)
+    constexpr int NW = (K::THREADS + 31) / 32;
+    const int warp_private = (hk == 0 && K::THREADS % 32 == 0 &&
+                              (size_t)NW * a.nbins * (sizeof(double) + sizeof(unsigned)) <= 16 * 1024) ? 1 : 0;
+    if (hk == 0) smem += (size_t)(warp_private ? NW : 1) * a.nbins * (sizeof(double) + sizeof(unsigned));
     int occ = 0, grid = 0;
 #define T21_LAUNCH_HK(HKV)                                                                              \
     {                                                                                                   \
@@ -130,7 +145,7 @@ inline int launch_x(XArgs& a, cudaStream_t st) {
         if (g > p.ntiles) g = p.ntiles;                                                                 \
         if (HKV == 0 && g > a.max_grid) g = a.max_grid;                                                 \
         grid = (int)g;                                                                                  \
-        kern<<<grid, K::THREADS, smem, st>>>(p, a.nbins, a.part_sum, a.part_cnt, a.gsum, a.gcnt);        \
+        kern<<<grid, K::THREADS, smem, st>>>(p, a.nbins, warp_private, a.part_sum, a.part_cnt, a.gsum, a.gcnt);        \
     }
     if constexpr (K::kMode == MODE_BIN) {
         if (hk == 0) T21_LAUNCH_HK(0) else if (hk == 1) T21_LAUNCH_HK(1)

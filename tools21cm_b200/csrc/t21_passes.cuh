@@ -174,6 +174,10 @@ struct XPass {
     static constexpr int SMEM_ELEMS = S::SMEM_ELEMS;
     static constexpr int NPHASE = NF * S::FFT_PHASES;   // the last phase of the last field holds the epilogue
     static constexpr int kMode = MODE;
+    // whole warps use the warp-uniform bin cache; CTAs smaller than a warp keep per-thread runs
+    template <bool B, class A, class C> struct Pick { using type = A; };
+    template <class A, class C> struct Pick<false, A, C> { using type = C; };
+    using Acc = typename Pick<(S::THREADS % 32 == 0), WarpBins, ThreadBins>::type;
 
     struct Params {
         const cx<T>* w[2];    // [NX][ny][pitch] per field
@@ -189,12 +193,15 @@ struct XPass {
     };
     struct Regs {
         cx<T> v[NF][E];
-        RunAcc acc[2];
+        Acc acc;
     };
 
     // one output element of the last stage: both fields are final for index ix
+    // Called by every thread of the CTA for every slot (warp-collective inside); `active` is
+    // false for the padding lanes of a ragged last chunk.
     template <class Hist>
-    static T21_HD void consume(const Params& p, Regs& r, Hist& hist, int ix, int iy, int iz, cx<T> a, cx<T> b) {
+    static T21_HD void consume(const Params& p, Regs& r, Hist& hist, int ix, int iy, int iz, bool active,
+                               cx<T> a, cx<T> b) {
         double pw;
         if ((ix | iy | iz) == 0) {
             // DC of (x - c) plus c*N: the only sample the offset changes
@@ -212,10 +219,14 @@ struct XPass {
         }
         const bool has_twin = (iz != 0) && (iz != p.nz - iz);
         if constexpr (MODE == MODE_BIN) {
-            const ModeBins mb = classify(p.bins, ix, iy, iz, has_twin);
-            run_add(r.acc[0], hist, mb.own, pw, mb.own_w);
-            run_add(r.acc[1], hist, mb.twin, pw, 1);
+            ModeBins mb;
+            mb.own = -1; mb.own_w = 0; mb.twin = -1;
+            if (active) mb = classify(p.bins, ix, iy, iz, has_twin);
+            acc_add(r.acc, hist, 0, mb.own, pw, mb.own_w, active);
+            if (p.bins.nmu > 0 && !p.bins.absolute_mus)      // signed mu: the twin goes to the mirrored bin
+                acc_add(r.acc, hist, 1, mb.twin, pw, 1, active);
         } else {
+            if (!active) return;
             const double val = pw * p.scale;
             const int sx = ix + NX / 2 - (ix + NX / 2 >= NX ? NX : 0);
             const int hy = p.ny / 2, hz = p.nz / 2;
@@ -251,9 +262,8 @@ struct XPass {
             [&](int i, cx<T> val, int slot) {
                 // last stage of field F: element i is final and still sits in register `slot`.
                 // Field 0 of a cross spectrum just stays there; the last field consumes both.
-                if constexpr (F == NF - 1) {
-                    if (active) consume(p, r, hist, i, iy, iz, (NF == 1) ? val : r.v[0][slot], val);
-                }
+                if constexpr (F == NF - 1)
+                    consume(p, r, hist, i, iy, iz, active, (NF == 1) ? val : r.v[0][slot], val);
             });
     }
 };

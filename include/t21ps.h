@@ -53,6 +53,7 @@ typedef struct t21_plan t21_plan;
  *   tab_los      signed k along the line of sight (_get_mu :481-502)
  *   mu_edges     half-open mu bins (:406-409, :428)
  *   *_lut        fp32 fast-path tables; T21_LUT_EXACT cells fall back to float64.
+ *   *_lo_f/_hi_f fp32 intervals strictly inside each bin (guard band >> fp32 error).
  * Indices are FFT order for the fused kernels, fftshift order for t21_bin_only. */
 typedef struct t21_binspec {
     int32_t n[3];
@@ -76,6 +77,12 @@ typedef struct t21_binspec {
     float k_lut_inv;
     const uint16_t* mu_lut;
     int32_t mu_cells;     /* cell = floor((mu + 1) * mu_cells / 2) */
+    /* no-lookup fast path: fp32 s^ in [k_lo_f[b], k_hi_f[b]) guarantees the exact s is in k bin b
+     * (b = nk / nk+1: below / above every bin); same for mu^ and [mu_lo_f[m], mu_hi_f[m]) */
+    const float* k_lo_f;
+    const float* k_hi_f;
+    const float* mu_lo_f;
+    const float* mu_hi_f;
 } t21_binspec;
 
 /* Plan for real cubes of shape (nx, ny, nz), C order.  dtype T21_F32 / T21_F64 is the

@@ -34,7 +34,7 @@ static void zpass(const T* in, cx<T>* out, long long nrows, int pitch, const T* 
     auto tw = build_stage_twiddles<T>(NZ / 2);
     auto twr = build_roots<T>(NZ, NZ / 2 + 1);
     typename K::Params p{in, out, nrows, pitch, offset, tw.data(), twr.data()};
-    std::vector<cx<T>> smem(K::SMEM_ELEMS);
+    std::vector<cx<T>> smem(K::SMEM_BYTES / sizeof(cx<T>) + 1);
     long long nctas = (nrows + K::ROWS - 1) / K::ROWS;
     for (long long cta = 0; cta < nctas; ++cta) {
         std::vector<typename K::Regs> regs(K::THREADS);
@@ -47,7 +47,7 @@ static void ypass(cx<T>* w, long long nouter, int nzh, int pitch) {
     auto tw = build_stage_twiddles<T>(NY);
     int nchunks = (nzh + WZ - 1) / WZ;
     typename K::Params p{w, nzh, pitch, nchunks, tw.data()};
-    std::vector<cx<T>> smem(K::SMEM_ELEMS);
+    std::vector<cx<T>> smem(K::SMEM_BYTES / sizeof(cx<T>) + 1);
     for (long long cta = 0; cta < nouter * nchunks; ++cta) {
         std::vector<typename K::Regs> regs(K::THREADS);
         run_simple<K, T>(p, cta, regs, smem.data());
@@ -70,7 +70,7 @@ static void xpass(const cx<T>* w0, const cx<T>* w1, int ny, int nz, int pitch, c
     p.ntot = (double)NX * ny * nz;
     if (spec) p.bins = *spec;
     p.nd_out = nd_out; p.nd_f64 = nd_f64; p.scale = scale;
-    std::vector<cx<T>> smem(K::SMEM_ELEMS);
+    std::vector<cx<T>> smem(K::SMEM_BYTES / sizeof(cx<T>) + 1);
     const int nb = spec ? spec->nk * (spec->nmu > 0 ? spec->nmu : 1) : 1;
     // persistent CTAs: each keeps its run accumulators and histogram across its tiles
     for (int cta = 0; cta < nctas_emulated; ++cta) {
@@ -78,10 +78,10 @@ static void xpass(const cx<T>* w0, const cx<T>* w1, int ny, int nz, int pitch, c
         std::vector<unsigned> hc(nb, 0u);
         SmemHist hist{hs.data(), hc.data()};
         std::vector<typename K::Regs> regs(K::THREADS);
-        for (auto& r : regs) acc_init(r.acc);
+        for (auto& r : regs) { acc_init(r.acc[0]); acc_init(r.acc[1]); }
         for (long long tile = cta; tile < p.ntiles; tile += nctas_emulated)
             run_hist<K, T, SmemHist>(p, tile, regs, smem.data(), hist);
-        for (auto& r : regs) acc_flush(r.acc, hist);
+        for (auto& r : regs) { acc_flush(r.acc[0], hist, nb); acc_flush(r.acc[1], hist, nb); }
         if (MODE == MODE_BIN)
             for (int b = 0; b < nb; ++b) { sums[b] += hs[b]; counts[b] += hc[b]; }
     }

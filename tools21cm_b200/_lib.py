@@ -41,6 +41,10 @@ class BinSpecC(C.Structure):
         ("k_lut_inv", C.c_float),
         ("mu_lut", C.c_void_p),
         ("mu_cells", C.c_int32),
+        ("k_lo_f", C.c_void_p),
+        ("k_hi_f", C.c_void_p),
+        ("mu_lo_f", C.c_void_p),
+        ("mu_hi_f", C.c_void_p),
     ]
 
 
@@ -71,6 +75,10 @@ def pack_binspec(spec, upload):
     offs["mu"] = put(spec.mu_edges if spec.nmu else np.zeros(1), np.float64)
     offs["klut"] = put(spec.k_lut, np.uint16)
     offs["mulut"] = put(spec.mu_lut if spec.nmu else np.zeros(1, np.uint16), np.uint16)
+    offs["klo"] = put(spec.k_lo_f, np.float32)
+    offs["khi"] = put(spec.k_hi_f, np.float32)
+    offs["mlo"] = put(spec.mu_lo_f, np.float32)
+    offs["mhi"] = put(spec.mu_hi_f, np.float32)
     blob = np.zeros(max(size, 256), dtype=np.uint8)
     for off, a in parts:
         blob[off:off + a.nbytes] = a.view(np.uint8).reshape(-1)
@@ -96,6 +104,10 @@ def pack_binspec(spec, upload):
     c.k_lut_c0 = float(np.float32(-spec.k_lut_u0 * spec.k_lut_inv))
     c.mu_lut = base + offs["mulut"]
     c.mu_cells = int(spec.mu_lut.size) if spec.nmu else 1
+    c.k_lo_f = base + offs["klo"]
+    c.k_hi_f = base + offs["khi"]
+    c.mu_lo_f = base + offs["mlo"]
+    c.mu_hi_f = base + offs["mhi"]
     return c, owner
 
 

@@ -159,6 +159,10 @@ class BinSpec:
     k_lut_u0: float
     k_lut_inv: float
     mu_lut: np.ndarray           # uint16 [MU_LUT_CELLS] or empty
+    k_lo_f: np.ndarray           # float32 [nk+2]: fp32 s^ in [k_lo_f[b], k_hi_f[b]) => exact s is in k bin b
+    k_hi_f: np.ndarray           #   entries nk / nk+1 are the "below all bins" / "above all bins" pseudo bins
+    mu_lo_f: np.ndarray          # float32 [nmu]: same for the fp32 mu^ estimate
+    mu_hi_f: np.ndarray
     order: str                   # 'fft' (fused FFT kernels) or 'shifted' (caller-supplied arrays)
     extra: dict = field(default_factory=dict)
 
@@ -187,6 +191,9 @@ def _build_k_lut(thr, smin, smax, extra_flags=()):
         tlog = np.where(thr > 0, np.log2(np.maximum(thr, 1e-300)), -np.inf)
     b = np.searchsorted(tlog, centres, side="right") - 1
     lut = np.where((b >= 0) & (b < nb), b, LUT_OUTSIDE).astype(np.int64)
+    for v in extra_flags:            # (k, mu) only: s < s_nan has mu = NaN and is in no bin
+        if v > 0:
+            lut[centres < np.log2(v)] = LUT_OUTSIDE
     marks = list(tlog[np.isfinite(tlog)]) + [np.log2(v) for v in extra_flags if v > 0]
     for t in marks:
         c = int(np.floor((t - u0) * inv))
@@ -213,6 +220,34 @@ def _build_mu_lut(mu_edges, absolute_mus):
     lut[0] = LUT_EXACT
     lut[cells - 1] = LUT_EXACT
     return lut.astype(np.uint16)
+
+
+S_GUARD = 1.0e-6    # relative guard on s^: >= 5x the fp32 error of (sx + sy) + sz from rounded tables
+MU_GUARD = 4.0e-6   # absolute guard on mu^ = k_los * rsqrt(s^) (|mu| <= 1)
+
+
+def _guard_intervals(thr, mu_edges, s_nan):
+    """fp32 intervals strictly inside each bin, for the device's no-lookup fast path."""
+    nk = len(thr) - 1
+    lo = np.empty(nk + 2, dtype=np.float64)
+    hi = np.empty(nk + 2, dtype=np.float64)
+    lo[:nk] = np.maximum(thr[:-1], s_nan) * (1.0 + S_GUARD)
+    hi[:nk] = thr[1:] * (1.0 - S_GUARD)
+    lo[nk], hi[nk] = -np.inf, thr[0] * (1.0 - S_GUARD)           # below every bin
+    lo[nk + 1], hi[nk + 1] = thr[-1] * (1.0 + S_GUARD), np.inf   # above every bin
+    lo_f = np.nextafter(lo.astype(np.float32), np.float32(np.inf))      # round inwards
+    hi_f = np.nextafter(hi.astype(np.float32), np.float32(-np.inf))
+    lo_f[nk] = -np.inf
+    hi_f[nk + 1] = np.inf
+    if thr[0] <= 0:
+        hi_f[nk] = -np.inf                                               # nothing lies below
+    if len(mu_edges) >= 2:
+        mlo = np.nextafter((mu_edges[:-1] + MU_GUARD).astype(np.float32), np.float32(np.inf))
+        mhi = np.nextafter((mu_edges[1:] - MU_GUARD).astype(np.float32), np.float32(-np.inf))
+    else:
+        mlo = np.zeros(1, dtype=np.float32)
+        mhi = np.zeros(1, dtype=np.float32)
+    return lo_f, hi_f, mlo, mhi
 
 
 def build_binspec(shape, box_dims, kbins, *, binning="log", breakpoint=0.1, mubins=None, los_axis=0,
@@ -304,7 +339,9 @@ def build_binspec(shape, box_dims, kbins, *, binning="log", breakpoint=0.1, mubi
         perp = [a for a in (0, 1, 2) if a != los_axis]
         excl = all(shape[a] % 2 == 0 for a in perp)
 
+    k_lo_f, k_hi_f, mu_lo_f, mu_hi_f = _guard_intervals(thr, mu_edges, s_nan)
     return BinSpec(shape=shape3, nk=nk, nmu=nmu, k_edges=edges, mu_edges=mu_edges, thr=thr,
                    tab_s=tabs3, tab_los=np.ascontiguousarray(tab_los, dtype=np.float64), los_axis=los3,
                    absolute_mus=bool(absolute_mus), exclude_zero=excl, zero_idx=zero3, nyq_idx=nyq3,
-                   s_nan=float(s_nan), k_lut=k_lut, k_lut_u0=u0, k_lut_inv=inv, mu_lut=mu_lut, order=order)
+                   s_nan=float(s_nan), k_lut=k_lut, k_lut_u0=u0, k_lut_inv=inv, mu_lut=mu_lut,
+                   k_lo_f=k_lo_f, k_hi_f=k_hi_f, mu_lo_f=mu_lo_f, mu_hi_f=mu_hi_f, order=order)

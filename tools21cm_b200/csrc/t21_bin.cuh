@@ -156,21 +156,27 @@ T21_HD void run_add(RunAcc& a, Hist& h, int bin, double p, int w) {
     a.cnt += (unsigned)w;
 }
 
-// WarpBins: what the X pass uses on the device.  In the X pass the 32 lanes of a warp hold
-// neighbouring modes (16 adjacent kz x 2 adjacent kx for the same register slot), which almost
-// always share a bin, while the 16 slots of one thread are spread over all kx and do not.
-// So the bin ids are kept WARP-UNIFORM in a small cache, each lane keeps a private partial
-// sum per cache entry, and the shared histogram is touched only when an entry is evicted:
-// one shuffle reduction and one add by lane 0 ("warp-aggregated atomics").  Lanes whose bin
-// differs from the leader's are served in a second trip of the loop; nobody ever issues a
-// per-lane atomic.  Every lane of the warp must call add() the same number of times.
-constexpr int kWarpBinEntries = 4;
+// WarpBins: what the X pass uses on the device.  Its epilogue walks a power tile so that the
+// 32 lanes of a warp hold neighbouring modes (adjacent kz x adjacent kx) and consecutive steps
+// move kx by a few cells: the lanes nearly always fall in one bin, or in two adjacent bins
+// while the warp crosses an edge.  So a warp keeps TWO warp-uniform bin entries, each with the
+// fp32 interval of s^ (and mu^) that provably lies inside that bin (binspec.py guard bands)
+// and a per-lane partial sum:
+//   fast step : every lane's (s^, mu^) is inside one of the two intervals -> add to the
+//               lane-private partial sum.  No table lookup, no shuffle, no atomic.
+//   slow step : some lane is outside both -> classify() all lanes exactly, then serve each
+//               distinct bin: hit, or evict the least recently used entry (shuffle reduction,
+//               one histogram update by lane 0) and install the new bin's intervals.
+// "Below / above every bin" are cached as pseudo bins nb, nb+1 so they do not force slow steps.
+// Every lane of the warp must make the same sequence of calls.
 struct WarpBins {
 #if T21_DEVICE_CODE
-    int bin[kWarpBinEntries];        // warp-uniform, -1 = empty
-    unsigned cnt[kWarpBinEntries];   // per lane
-    double sum[kWarpBinEntries];     // per lane
-    int victim;                      // warp-uniform round-robin pointer
+    int bin[2];              // warp-uniform flat bin id (or pseudo bin), -1 = empty
+    float slo[2], shi[2];    // warp-uniform guard interval of s^
+    float mlo[2], mhi[2];    // warp-uniform guard interval of mu^ (unused for shells)
+    int lru;                 // warp-uniform: entry to evict next
+    unsigned cnt[2];         // per lane
+    double sum[2];           // per lane
 #else
     RunAcc run;
 #endif
@@ -179,8 +185,11 @@ struct WarpBins {
 T21_HD void warpbins_init(WarpBins& a) {
 #if T21_DEVICE_CODE
 #pragma unroll
-    for (int c = 0; c < kWarpBinEntries; ++c) { a.bin[c] = -1; a.cnt[c] = 0; a.sum[c] = 0.0; }
-    a.victim = 0;
+    for (int c = 0; c < 2; ++c) {
+        a.bin[c] = -1; a.cnt[c] = 0; a.sum[c] = 0.0;
+        a.slo[c] = 1.f; a.shi[c] = 0.f; a.mlo[c] = 1.f; a.mhi[c] = 0.f;   // empty intervals
+    }
+    a.lru = 0;
 #else
     run_init(a.run);
 #endif
@@ -188,8 +197,8 @@ T21_HD void warpbins_init(WarpBins& a) {
 
 #if T21_DEVICE_CODE
 template <class Hist>
-__device__ __forceinline__ void warpbins_evict(WarpBins& a, Hist& h, int c) {
-    // c is a compile-time constant at every call site (unrolled), so a.*[c] stay in registers
+__device__ __forceinline__ void warpbins_evict(WarpBins& a, Hist& h, int c, int nbins) {
+    // c is a compile-time constant at every call site, so a.*[c] stay in registers
     double s = a.sum[c];
     unsigned n = a.cnt[c];
 #pragma unroll
@@ -197,79 +206,104 @@ __device__ __forceinline__ void warpbins_evict(WarpBins& a, Hist& h, int c) {
         s += __shfl_xor_sync(0xffffffffu, s, o);
         n += __shfl_xor_sync(0xffffffffu, n, o);
     }
-    if ((threadIdx.x & 31) == 0 && n) h.add(a.bin[c], s, n);
+    if ((threadIdx.x & 31) == 0 && n && a.bin[c] < nbins) h.add(a.bin[c], s, n);   // pseudo bins are dropped
     a.sum[c] = 0.0;
     a.cnt[c] = 0;
 }
-#endif
 
-// valid: this lane has a mode to add (false for padding lanes); bin < 0 means "in no bin"
-template <class Hist>
-T21_HD void warpbins_add(WarpBins& a, Hist& h, int bin, double p, int w, bool valid) {
-#if T21_DEVICE_CODE
-    unsigned todo = __ballot_sync(0xffffffffu, valid && bin >= 0);
-    while (todo) {                                   // warp-uniform loop: one trip per distinct bin
-        const int leader = __ffs(todo) - 1;
-        const int ref = __shfl_sync(0xffffffffu, bin, leader);
-        const bool mine = valid && bin == ref;
-        todo &= ~__ballot_sync(0xffffffffu, mine);
-        bool hit = false;
-#pragma unroll
-        for (int c = 0; c < kWarpBinEntries; ++c) {
-            if (!hit && a.bin[c] == ref) {           // warp-uniform branch
-                hit = true;
-                if (mine) { a.sum[c] += (w == 2) ? (p + p) : p; a.cnt[c] += (unsigned)w; }
-            }
-        }
-        if (!hit) {
-#pragma unroll
-            for (int c = 0; c < kWarpBinEntries; ++c) {
-                if (c == a.victim) {                 // warp-uniform branch
-                    if (a.bin[c] >= 0) warpbins_evict(a, h, c);
-                    a.bin[c] = ref;
-                    if (mine) { a.sum[c] = (w == 2) ? (p + p) : p; a.cnt[c] = (unsigned)w; }
-                }
-            }
-            a.victim = (a.victim + 1 == kWarpBinEntries) ? 0 : a.victim + 1;
-        }
-    }
-#else
-    if (valid) run_add(a.run, h, bin, p, w);
-#endif
+__device__ __forceinline__ void warpbins_install(WarpBins& a, const t21_binspec& B, int c, int ref) {
+    const int nb = B.nk * (B.nmu > 0 ? B.nmu : 1);
+    a.bin[c] = ref;
+    int kb = ref, mb = -1;
+    if (ref >= nb) kb = B.nk + (ref - nb);            // pseudo bins: any mu
+    else if (B.nmu > 0) { mb = ref / B.nk; kb = ref - mb * B.nk; }
+    a.slo[c] = ldg(B.k_lo_f + kb);
+    a.shi[c] = ldg(B.k_hi_f + kb);
+    if (mb >= 0) { a.mlo[c] = ldg(B.mu_lo_f + mb); a.mhi[c] = ldg(B.mu_hi_f + mb); }
+    else { a.mlo[c] = -2.f; a.mhi[c] = 2.f; }
 }
 
+// fast step; returns false (and adds nothing) if any lane needs the slow step.
+// MU: whether mu^ takes part.  valid = this lane has a mode (false for padding lanes).
+template <bool MU>
+__device__ __forceinline__ bool warpbins_fast(WarpBins& a, float sh, float muh, double p, unsigned w, bool valid) {
+    bool in0 = sh >= a.slo[0] && sh < a.shi[0];
+    bool in1 = sh >= a.slo[1] && sh < a.shi[1];
+    if (MU) {
+        in0 = in0 && muh >= a.mlo[0] && muh < a.mhi[0];
+        in1 = in1 && muh >= a.mlo[1] && muh < a.mhi[1];
+    }
+    if (!__all_sync(0xffffffffu, !valid || in0 || in1)) return false;
+    if (valid) {
+        if (in0) { a.sum[0] += p; a.cnt[0] += w; }
+        else { a.sum[1] += p; a.cnt[1] += w; }
+    }
+    return true;
+}
+
+// slow step: `bin` is this lane's exact flat bin (-1: in no bin and not cacheable)
 template <class Hist>
-T21_HD void warpbins_flush(WarpBins& a, Hist& h) {
+__device__ __forceinline__ void warpbins_slow(WarpBins& a, Hist& h, const t21_binspec& B, int nbins, int bin,
+                                              double p, unsigned w, bool valid) {
+    unsigned todo = __ballot_sync(0xffffffffu, valid && bin >= 0);
+    while (todo) {                                   // warp-uniform loop: one trip per distinct bin
+        const int ref = __shfl_sync(0xffffffffu, bin, __ffs(todo) - 1);
+        const bool mine = valid && bin == ref;
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+        if (a.bin[0] == ref) {
+            if (mine) { a.sum[0] += p; a.cnt[0] += w; }
+            a.lru = 1;
+        } else if (a.bin[1] == ref) {
+            if (mine) { a.sum[1] += p; a.cnt[1] += w; }
+            a.lru = 0;
+        } else if (a.lru == 0) {
+            if (a.bin[0] >= 0) warpbins_evict(a, h, 0, nbins);
+            warpbins_install(a, B, 0, ref);
+            if (mine) { a.sum[0] = p; a.cnt[0] = w; }
+            a.lru = 1;
+        } else {
+            if (a.bin[1] >= 0) warpbins_evict(a, h, 1, nbins);
+            warpbins_install(a, B, 1, ref);
+            if (mine) { a.sum[1] = p; a.cnt[1] = w; }
+            a.lru = 0;
+        }
+    }
+}
+#endif
+
+template <class Hist>
+T21_HD void warpbins_flush(WarpBins& a, Hist& h, int nbins) {
 #if T21_DEVICE_CODE
-#pragma unroll
-    for (int c = 0; c < kWarpBinEntries; ++c)
-        if (a.bin[c] >= 0) { warpbins_evict(a, h, c); a.bin[c] = -1; }
+    if (a.bin[0] >= 0) { warpbins_evict(a, h, 0, nbins); a.bin[0] = -1; a.slo[0] = 1.f; a.shi[0] = 0.f; }
+    if (a.bin[1] >= 0) { warpbins_evict(a, h, 1, nbins); a.bin[1] = -1; a.slo[1] = 1.f; a.shi[1] = 0.f; }
 #else
+    (void)nbins;
     run_flush(a.run, h);
 #endif
 }
 
-// ThreadBins: per-thread run-length accumulators (own / twin).  Used by CTAs smaller than a
+// ThreadBins: a per-thread run-length accumulator.  Used by CTAs smaller than a
 // warp (pencils shorter than 32 samples, where speed is irrelevant) and by the CPU replay.
 struct ThreadBins {
-    RunAcc run[2];
+    RunAcc run[1];
 };
 
-// one interface over both accumulators; `which` = 0 for the stored mode, 1 for its twin
+// per-thread accumulation into either accumulator type (the WarpBins overload is only reached by
+// the CPU replay, where WarpBins degenerates to a run accumulator)
+template <class Hist>
+T21_HD void acc_add_thread(ThreadBins& a, Hist& h, int bin, double p, int w) { run_add(a.run[0], h, bin, p, w); }
+template <class Hist>
+T21_HD void acc_add_thread(WarpBins& a, Hist& h, int bin, double p, int w) {
+#if !T21_DEVICE_CODE
+    run_add(a.run, h, bin, p, w);
+#endif
+}
 T21_HD void acc_init(WarpBins& a) { warpbins_init(a); }
-T21_HD void acc_init(ThreadBins& a) { run_init(a.run[0]); run_init(a.run[1]); }
+T21_HD void acc_init(ThreadBins& a) { run_init(a.run[0]); }
 template <class Hist>
-T21_HD void acc_add(WarpBins& a, Hist& h, int, int bin, double p, int w, bool valid) {
-    warpbins_add(a, h, bin, p, w, valid);
-}
+T21_HD void acc_flush(WarpBins& a, Hist& h, int nbins) { warpbins_flush(a, h, nbins); }
 template <class Hist>
-T21_HD void acc_add(ThreadBins& a, Hist& h, int which, int bin, double p, int w, bool valid) {
-    if (valid) run_add(a.run[which], h, bin, p, w);
-}
-template <class Hist>
-T21_HD void acc_flush(WarpBins& a, Hist& h) { warpbins_flush(a, h); }
-template <class Hist>
-T21_HD void acc_flush(ThreadBins& a, Hist& h) { run_flush(a.run[0], h); run_flush(a.run[1], h); }
+T21_HD void acc_flush(ThreadBins& a, Hist& h, int) { run_flush(a.run[0], h); }
 
 // CTA histogram in shared memory, updated with atomics (device) / plain arrays (host replay)
 struct SmemHist {

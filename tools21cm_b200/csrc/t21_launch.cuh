@@ -47,26 +47,29 @@ xpass_kernel(const __grid_constant__ typename K::Params p, int nbins, int warp_p
     cx<T>* ex = reinterpret_cast<cx<T>*>(smem_raw);
     const int tid = threadIdx.x;
     typename K::Regs r;
-    acc_init(r.acc);
+    acc_init(r.acc[0]);
+    acc_init(r.acc[1]);
     if constexpr (HK == 0) {
         // shared-memory histogram: one copy per warp when that fits (plain adds by lane 0, summed
         // in warp order at the end => bit-reproducible), otherwise one copy updated with atomics
         constexpr int NW = (K::THREADS + 31) / 32;
         const int copies = warp_private ? NW : 1;
-        double* hs = reinterpret_cast<double*>(smem_raw + sizeof(cx<T>) * K::SMEM_ELEMS);
+        double* hs = reinterpret_cast<double*>(smem_raw + K::SMEM_BYTES);
         unsigned* hc = reinterpret_cast<unsigned*>(hs + (size_t)copies * nbins);
         for (int b = tid; b < copies * nbins; b += K::THREADS) { hs[b] = 0.0; hc[b] = 0u; }
         __syncthreads();
         if (warp_private) {
             WarpPrivHist hist{hs + (size_t)(tid >> 5) * nbins, hc + (size_t)(tid >> 5) * nbins};
             for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
-                dev_phases_hist<K, T, WarpPrivHist>(p, tile, tid, r, ex, hist);
-            acc_flush(r.acc, hist);
+                { dev_phases_hist<K, T, WarpPrivHist>(p, tile, tid, r, ex, hist); __syncthreads(); }
+            acc_flush(r.acc[0], hist, nbins);
+            acc_flush(r.acc[1], hist, nbins);
         } else {
             SmemHist hist{hs, hc};
             for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
-                dev_phases_hist<K, T, SmemHist>(p, tile, tid, r, ex, hist);
-            acc_flush(r.acc, hist);
+                { dev_phases_hist<K, T, SmemHist>(p, tile, tid, r, ex, hist); __syncthreads(); }
+            acc_flush(r.acc[0], hist, nbins);
+            acc_flush(r.acc[1], hist, nbins);
         }
         __syncthreads();
         for (int b = tid; b < nbins; b += K::THREADS) {
@@ -79,12 +82,13 @@ xpass_kernel(const __grid_constant__ typename K::Params p, int nbins, int warp_p
     } else if constexpr (HK == 1) {
         GlobalHist hist{gsum, gcnt};
         for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
-            dev_phases_hist<K, T, GlobalHist>(p, tile, tid, r, ex, hist);
-        acc_flush(r.acc, hist);
+            { dev_phases_hist<K, T, GlobalHist>(p, tile, tid, r, ex, hist); __syncthreads(); }
+        acc_flush(r.acc[0], hist, nbins);
+        acc_flush(r.acc[1], hist, nbins);
     } else {
         NoHist hist;
         for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
-            dev_phases_hist<K, T, NoHist>(p, tile, tid, r, ex, hist);
+            { dev_phases_hist<K, T, NoHist>(p, tile, tid, r, ex, hist); __syncthreads(); }
     }
 }
 
@@ -100,7 +104,7 @@ template <class K, typename T>
 inline int launch_tiles(const typename K::Params& p, long long nctas, cudaStream_t st) {
     if (nctas <= 0) return 0;
     if (nctas > 2147483647LL) { set_error("grid too large"); return T21_EINVAL; }
-    const size_t smem = sizeof(cx<T>) * K::SMEM_ELEMS;
+    const size_t smem = K::SMEM_BYTES;
     auto kern = tile_kernel<K, T>;
     if (int rc = ensure_smem(kern, smem)) return rc;
     kern<<<(unsigned)nctas, K::THREADS, smem, st>>>(p);
@@ -128,7 +132,7 @@ inline int launch_x(XArgs& a, cudaStream_t st) {
 
     const bool is_bin = a.bins != nullptr;
     const int hk = !is_bin ? 2 : (a.hist_global ? 1 : 0);
-    size_t smem = sizeof(cx<T>) * K::SMEM_ELEMS;
+    size_t smem = K::SMEM_BYTES;
     // per-warp histogram copies when they are small (and the CTA is made of whole warps)
     constexpr int NW = (K::THREADS + 31) / 32;
     const int warp_private = (hk == 0 && K::THREADS % 32 == 0 &&

@@ -33,6 +33,7 @@ struct ZPass {
     static constexpr int ROWS = THREADS / TP;
     static constexpr int ROWPITCH = M + (M >> 4) + 1;          // padded: i -> i + (i >> 4)
     static constexpr int SMEM_ELEMS = ROWS * ROWPITCH;
+    static constexpr int SMEM_BYTES = SMEM_ELEMS * (int)sizeof(cx<T>);
     static constexpr int NPHASE = 2 * NS;
 
     struct Params {
@@ -130,7 +131,7 @@ template <int NY, typename T, int WZ>
 struct YPass {
     using S = Strided<NY, T, WZ>;
     static constexpr int THREADS = S::THREADS;
-    static constexpr int SMEM_ELEMS = S::SMEM_ELEMS;
+    static constexpr int SMEM_BYTES = S::SMEM_ELEMS * (int)sizeof(cx<T>);
     static constexpr int NPHASE = S::FFT_PHASES;
 
     struct Params {
@@ -163,6 +164,12 @@ struct YPass {
 // ======================================================================================
 // X pass fused with power + binning (MODE_BIN) or the fftshifted n-D store (MODE_ND)
 // ======================================================================================
+// After the last butterfly stage every thread holds 16 outputs spread over all kx.  It turns
+// them into power, parks the power tile P[kx][kz] in the (now free) exchange buffer, and after
+// one more barrier the CTA walks the tile in a different order: each warp sweeps a contiguous
+// range of kx, 32/WZ rows per step, lanes along kz.  In that order the bin of a warp's lanes
+// is almost always uniform and changes only a few times per sweep, so the rolled epilogue
+// loop (small code) feeds the warp-uniform bin cache with near-perfect hit rate.
 enum { MODE_BIN = 0, MODE_ND = 1 };
 
 template <int NX, typename T, int WZ, int NF, int MODE>
@@ -171,13 +178,18 @@ struct XPass {
     using P = Plan<NX>;
     static constexpr int E = S::E;
     static constexpr int THREADS = S::THREADS;
-    static constexpr int SMEM_ELEMS = S::SMEM_ELEMS;
-    static constexpr int NPHASE = NF * S::FFT_PHASES;   // the last phase of the last field holds the epilogue
+    static constexpr int TILE = NX * WZ;                       // modes per tile
+    static constexpr int EX_BYTES = (S::NS > 1) ? TILE * (int)sizeof(cx<T>) : 0;
+    static constexpr int P_BYTES = TILE * (int)sizeof(T);
+    static constexpr int BUF_BYTES = ((EX_BYTES > P_BYTES ? EX_BYTES : P_BYTES) + 15) / 16 * 16;
+    static constexpr int SMEM_BYTES = BUF_BYTES + 16;          // + the DC power as a double
+    static constexpr int NPHASE = NF * S::FFT_PHASES + 1;      // transforms, then the epilogue
     static constexpr int kMode = MODE;
+    static constexpr int RPI = (THREADS >= 32) ? 32 / WZ : S::TP;   // kx rows a warp covers per step
     // whole warps use the warp-uniform bin cache; CTAs smaller than a warp keep per-thread runs
     template <bool B, class A, class C> struct Pick { using type = A; };
     template <class A, class C> struct Pick<false, A, C> { using type = C; };
-    using Acc = typename Pick<(S::THREADS % 32 == 0), WarpBins, ThreadBins>::type;
+    using Acc = typename Pick<(THREADS % 32 == 0), WarpBins, ThreadBins>::type;
 
     struct Params {
         const cx<T>* w[2];    // [NX][ny][pitch] per field
@@ -193,78 +205,166 @@ struct XPass {
     };
     struct Regs {
         cx<T> v[NF][E];
-        Acc acc;
+        Acc acc[2];           // [0] stored modes, [1] Hermitian twins when they bin separately (signed mu)
     };
 
-    // one output element of the last stage: both fields are final for index ix
-    // Called by every thread of the CTA for every slot (warp-collective inside); `active` is
-    // false for the padding lanes of a ragged last chunk.
-    template <class Hist>
-    static T21_HD void consume(const Params& p, Regs& r, Hist& hist, int ix, int iy, int iz, bool active,
-                               cx<T> a, cx<T> b) {
-        double pw;
-        if ((ix | iy | iz) == 0) {
-            // DC of (x - c) plus c*N: the only sample the offset changes
-            const double c0 = p.offset[0] ? (double)ldg(p.offset[0]) : 0.0;
-            const double re0 = (double)a.x + c0 * p.ntot;
-            if (NF == 1) {
-                pw = re0 * re0 + (double)a.y * (double)a.y;
-            } else {
-                const double c1 = p.offset[1] ? (double)ldg(p.offset[1]) : 0.0;
-                const double re1 = (double)b.x + c1 * p.ntot;
-                pw = re0 * re1 + (double)a.y * (double)b.y;
-            }
-        } else {
-            pw = (NF == 1) ? (double)(a.x * a.x + a.y * a.y) : (double)(a.x * b.x + a.y * b.y);
-        }
-        const bool has_twin = (iz != 0) && (iz != p.nz - iz);
-        if constexpr (MODE == MODE_BIN) {
-            ModeBins mb;
-            mb.own = -1; mb.own_w = 0; mb.twin = -1;
-            if (active) mb = classify(p.bins, ix, iy, iz, has_twin);
-            acc_add(r.acc, hist, 0, mb.own, pw, mb.own_w, active);
-            if (p.bins.nmu > 0 && !p.bins.absolute_mus)      // signed mu: the twin goes to the mirrored bin
-                acc_add(r.acc, hist, 1, mb.twin, pw, 1, active);
-        } else {
-            if (!active) return;
-            const double val = pw * p.scale;
-            const int sx = ix + NX / 2 - (ix + NX / 2 >= NX ? NX : 0);
-            const int hy = p.ny / 2, hz = p.nz / 2;
-            const int sy = iy + hy - (iy + hy >= p.ny ? p.ny : 0);
-            const int sz = iz + hz - (iz + hz >= p.nz ? p.nz : 0);
-            const long long o = ((long long)sx * p.ny + sy) * p.nz + sz;
-            if (p.nd_f64) ((double*)p.nd_out)[o] = val; else ((float*)p.nd_out)[o] = (float)val;
-            if (has_twin) {
-                const int tx = ix ? NX - ix : 0, ty = iy ? p.ny - iy : 0, tz = p.nz - iz;
-                const int ux = tx + NX / 2 - (tx + NX / 2 >= NX ? NX : 0);
-                const int uy = ty + hy - (ty + hy >= p.ny ? p.ny : 0);
-                const int uz = tz + hz - (tz + hz >= p.nz ? p.nz : 0);
-                const long long ot = ((long long)ux * p.ny + uy) * p.nz + uz;
-                if (p.nd_f64) ((double*)p.nd_out)[ot] = val; else ((float*)p.nd_out)[ot] = (float)val;
-            }
-        }
+    static T21_HD T* ptile(cx<T>* smem) { return reinterpret_cast<T*>(smem); }
+    static T21_HD double* dc_slot(cx<T>* smem) {
+        return reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(smem) + BUF_BYTES);
     }
 
     template <int PH, class Hist>
     static T21_HD void phase(const Params& p, long long tile, int tid, Regs& r, cx<T>* smem, Hist& hist) {
-        constexpr int F = PH / S::FFT_PHASES;          // field this phase works on
-        constexpr int FPH = PH % S::FFT_PHASES;
         const int zl = tid % WZ, j = tid / WZ;
         const int chunk = (int)(tile % p.nchunks);
         const int iy = (int)(tile / p.nchunks);
         const int iz = chunk * WZ + zl;
         const bool active = iz < p.nzh;
-        const cx<T>* base = p.w[F] + (long long)iy * p.pitch + (active ? iz : 0);
-        const long long stride = (long long)p.ny * p.pitch;
-        S::template fft_phase<FPH>(
-            r.v[F], j, zl, p.tw, smem,
-            [&](int i) { return active ? base[i * stride] : cmake<T>(0, 0); },
-            [&](int i, cx<T> val, int slot) {
-                // last stage of field F: element i is final and still sits in register `slot`.
-                // Field 0 of a cross spectrum just stays there; the last field consumes both.
-                if constexpr (F == NF - 1)
-                    consume(p, r, hist, i, iy, iz, active, (NF == 1) ? val : r.v[0][slot], val);
-            });
+        if constexpr (PH < NF * S::FFT_PHASES) {
+            constexpr int F = PH / S::FFT_PHASES;          // field this phase works on
+            constexpr int FPH = PH % S::FFT_PHASES;
+            const cx<T>* base = p.w[F] + (long long)iy * p.pitch + (active ? iz : 0);
+            const long long stride = (long long)p.ny * p.pitch;
+            S::template fft_phase<FPH>(
+                r.v[F], j, zl, p.tw, smem,
+                [&](int i) { return active ? base[i * stride] : cmake<T>(0, 0); },
+                [&](int i, cx<T> b, int slot) {
+                    // last stage of field F: element i (= kx) is final and sits in register `slot`.
+                    // Field 0 of a cross spectrum just stays there; the last field forms the power.
+                    if constexpr (F == NF - 1) {
+                        const cx<T> a = (NF == 1) ? b : r.v[0][slot];
+                        ptile(smem)[i * WZ + zl] = a.x * b.x + a.y * b.y;
+                        if (i == 0 && iy == 0 && iz == 0) {
+                            // DC of (x - c) plus c*N: the only sample the mean offset changes
+                            const double c0 = p.offset[0] ? (double)ldg(p.offset[0]) : 0.0;
+                            const double c1 = (NF == 2 && p.offset[1]) ? (double)ldg(p.offset[1]) : c0;
+                            const double ra = (double)a.x + c0 * p.ntot, rb = (double)b.x + c1 * p.ntot;
+                            *dc_slot(smem) = ra * rb + (double)a.y * (double)b.y;
+                        }
+                    }
+                });
+        } else {
+            epilogue(p, tid, iy, iz, zl, active, r, smem, hist);
+        }
+    }
+
+    // exact bin of one mode for accumulator `which`; -1 = none.  k below / above every bin maps to
+    // the cacheable pseudo bins nb / nb+1 (decided on the guard intervals, which are conservative).
+    static T21_HD int exact_bin(const Params& p, int ix, int iy, int iz, bool has_twin, int which, float sh,
+                                int& weight) {
+        const ModeBins mb = classify(p.bins, ix, iy, iz, has_twin);
+        int bin = which == 0 ? mb.own : mb.twin;
+        weight = which == 0 ? mb.own_w : 1;
+        if (bin < 0) {
+            const int nb = p.bins.nk * (p.bins.nmu > 0 ? p.bins.nmu : 1);
+            weight = 1;
+            if (sh < ldg(p.bins.k_hi_f + p.bins.nk)) bin = nb;
+            else if (sh >= ldg(p.bins.k_lo_f + p.bins.nk + 1)) bin = nb + 1;
+        }
+        return bin;
+    }
+
+    template <class Hist>
+    static T21_HD void epilogue(const Params& p, int tid, int iy, int iz, int zl, bool active, Regs& r,
+                                cx<T>* smem, Hist& hist) {
+        const T* pt = ptile(smem);
+        const int q = tid / WZ;                                   // row id of this thread, 0..TP-1
+        const int ix0 = (q / RPI) * (E * RPI) + (q % RPI);
+        const bool has_twin = (iz != 0) && (iz != p.nz - iz);
+        if constexpr (MODE == MODE_BIN) {
+            const t21_binspec& B = p.bins;
+            const int nb = B.nk * (B.nmu > 0 ? B.nmu : 1);
+            const bool mu_on = B.nmu > 0;
+            const bool abs_mu = B.absolute_mus != 0;
+            const bool signed_mu = mu_on && !abs_mu;
+            const int los = B.los_axis;
+            // k_perp = 0 line (power_spectrum.py:563-575): the part of the test that is fixed for this thread
+            bool line_fixed = false;
+            if (mu_on && B.exclude_zero)
+                line_fixed = los == 0 ? (iy == B.zero_idx[1] && iz == B.zero_idx[2])
+                                      : (los == 1 ? iz == B.zero_idx[2] : iy == B.zero_idx[1]);
+            const int iz_c = active ? iz : 0;
+            const float c_yz = ldg(B.tab_sf[1] + iy) + ldg(B.tab_sf[2] + iz_c);
+            const unsigned wt = (has_twin && !signed_mu) ? 2u : 1u;
+            float klos_c = 0.f;
+            bool nyq_c = false;
+            if (mu_on && los != 0) {
+                const int il = los == 1 ? iy : iz_c;
+                klos_c = ldg(B.tab_losf + il);
+                nyq_c = il == B.nyq_idx[los];
+            }
+#if T21_DEVICE_CODE
+#pragma unroll 1
+#endif
+            for (int it = 0; it < E; ++it) {
+                const int ix = ix0 + it * RPI;
+                double pw = (double)pt[ix * WZ + zl];
+                if ((ix | iy | iz) == 0) pw = *dc_slot(smem);
+                const bool valid = active && !(line_fixed && (los == 0 || ix == B.zero_idx[0]));
+#if T21_DEVICE_CODE
+                if constexpr (THREADS % 32 == 0) {
+                    const float sh = ldg(B.tab_sf[0] + ix) + c_yz;
+                    float muh = 0.f;
+                    bool nyq = nyq_c;
+                    if (mu_on) {
+                        const float kl = los == 0 ? ldg(B.tab_losf + ix) : klos_c;
+                        if (los == 0) nyq = ix == B.nyq_idx[0];
+                        muh = kl * fast_rsqrt(sh);
+                    }
+                    const float m_own = abs_mu ? fabsf(muh) : muh;
+                    const double pw_w = wt == 2u ? pw + pw : pw;
+                    const bool ok = mu_on ? warpbins_fast<true>(r.acc[0], sh, m_own, pw_w, wt, valid)
+                                          : warpbins_fast<false>(r.acc[0], sh, 0.f, pw_w, wt, valid);
+                    if (!ok) {
+                        int w1 = 1;
+                        const int bin = valid ? exact_bin(p, ix, iy, iz, has_twin, 0, sh, w1) : -1;
+                        warpbins_slow(r.acc[0], hist, B, nb, bin, w1 == 2 ? pw + pw : pw, (unsigned)w1, valid);
+                    }
+                    if (signed_mu) {                          // the twin goes to the mirrored mu bin
+                        const bool tv = valid && has_twin;
+                        const float m_tw = nyq ? muh : -muh;
+                        if (!warpbins_fast<true>(r.acc[1], sh, m_tw, pw, 1u, tv)) {
+                            int w1 = 1;
+                            const int bin = tv ? exact_bin(p, ix, iy, iz, has_twin, 1, sh, w1) : -1;
+                            warpbins_slow(r.acc[1], hist, B, nb, bin, pw, 1u, tv);
+                        }
+                    }
+                    continue;
+                }
+#endif
+                // per-thread path: CTAs smaller than a warp, and the CPU replay
+                if (valid) {
+                    const ModeBins mb = classify(B, ix, iy, iz, has_twin);
+                    acc_add_thread(r.acc[0], hist, mb.own, pw, mb.own_w);
+                    if (signed_mu) acc_add_thread(r.acc[1], hist, mb.twin, pw, 1);
+                }
+            }
+        } else {
+#if T21_DEVICE_CODE
+#pragma unroll 1
+#endif
+            for (int it = 0; it < E; ++it) {
+                const int ix = ix0 + it * RPI;
+                double pw = (double)pt[ix * WZ + zl];
+                if ((ix | iy | iz) == 0) pw = *dc_slot(smem);
+                if (!active) continue;
+                const double val = pw * p.scale;
+                const int hy = p.ny / 2, hz = p.nz / 2;
+                const int sx = ix + NX / 2 - (ix + NX / 2 >= NX ? NX : 0);
+                const int sy = iy + hy - (iy + hy >= p.ny ? p.ny : 0);
+                const int sz = iz + hz - (iz + hz >= p.nz ? p.nz : 0);
+                const long long o = ((long long)sx * p.ny + sy) * p.nz + sz;
+                if (p.nd_f64) ((double*)p.nd_out)[o] = val; else ((float*)p.nd_out)[o] = (float)val;
+                if (has_twin) {
+                    const int tx = ix ? NX - ix : 0, ty = iy ? p.ny - iy : 0, tz = p.nz - iz;
+                    const int ux = tx + NX / 2 - (tx + NX / 2 >= NX ? NX : 0);
+                    const int uy = ty + hy - (ty + hy >= p.ny ? p.ny : 0);
+                    const int uz = tz + hz - (tz + hz >= p.nz ? p.nz : 0);
+                    const long long ot = ((long long)ux * p.ny + uy) * p.nz + uz;
+                    if (p.nd_f64) ((double*)p.nd_out)[ot] = val; else ((float*)p.nd_out)[ot] = (float)val;
+                }
+            }
+        }
     }
 };
 

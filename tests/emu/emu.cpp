@@ -29,11 +29,11 @@ static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 // ---- passes with run-time sizes ------------------------------------------------------
 template <int NZ, typename T>
-static void zpass(const T* in, cx<T>* out, long long nrows, int pitch, const T* offset) {
+static void zpass(const T* in, cx<T>* out, long long nrows, int pitch, const T* offset, int ny, int xb) {
     using K = ZPass<NZ, T>;
     auto tw = build_stage_twiddles<T>(NZ / 2);
     auto twr = build_roots<T>(NZ, NZ / 2 + 1);
-    typename K::Params p{in, out, nrows, pitch, offset, tw.data(), twr.data()};
+    typename K::Params p{in, out, nrows, pitch, ny, xb, offset, tw.data(), twr.data()};
     std::vector<cx<T>> smem(K::SMEM_BYTES / sizeof(cx<T>) + 1);
     long long nctas = (nrows + K::ROWS - 1) / K::ROWS;
     for (long long cta = 0; cta < nctas; ++cta) {
@@ -42,11 +42,11 @@ static void zpass(const T* in, cx<T>* out, long long nrows, int pitch, const T* 
     }
 }
 template <int NY, typename T, int WZ>
-static void ypass(cx<T>* w, long long nouter, int nzh, int pitch) {
+static void ypass(cx<T>* w, long long nouter, int nzh, int pitch, int xb) {
     using K = YPass<NY, T, WZ>;
     auto tw = build_stage_twiddles<T>(NY);
     int nchunks = (nzh + WZ - 1) / WZ;
-    typename K::Params p{w, nzh, pitch, nchunks, tw.data()};
+    typename K::Params p{w, nzh, pitch, nchunks, xb, tw.data()};
     std::vector<cx<T>> smem(K::SMEM_BYTES / sizeof(cx<T>) + 1);
     for (long long cta = 0; cta < nouter * nchunks; ++cta) {
         std::vector<typename K::Regs> regs(K::THREADS);
@@ -56,7 +56,7 @@ static void ypass(cx<T>* w, long long nouter, int nzh, int pitch) {
 template <int NX, typename T, int WZ, int NF, int MODE>
 static void xpass(const cx<T>* w0, const cx<T>* w1, int ny, int nz, int pitch, const T* off0, const T* off1,
                   const t21_binspec* spec, double* sums, long long* counts, void* nd_out, int nd_f64, double scale,
-                  int nctas_emulated) {
+                  int nctas_emulated, int xb) {
     using K = XPass<NX, T, WZ, NF, MODE>;
     auto tw = build_stage_twiddles<T>(NX);
     typename K::Params p;
@@ -65,6 +65,8 @@ static void xpass(const cx<T>* w0, const cx<T>* w1, int ny, int nz, int pitch, c
     p.ny = ny; p.nz = nz; p.nzh = nz / 2 + 1; p.pitch = pitch;
     p.nchunks = (p.nzh + WZ - 1) / WZ;
     p.ntiles = (long long)ny * p.nchunks;
+    p.tile_step = nctas_emulated;
+    p.xb = xb;
     p.tw = tw.data();
     p.offset[0] = off0; p.offset[1] = off1;
     p.ntot = (double)NX * ny * nz;
@@ -106,42 +108,49 @@ static int emu_all(int nx, int ny, int nz, const T* in0, const T* in1, double of
     const int nzh = nz / 2 + 1;
     const int pitch = round_up(nzh, 16);
     const int nf = in1 ? 2 : 1;
+    int xb = 2;                                   // same rule as t21_plan_create
+    while (xb > 0 && ((nx % (1 << xb)) != 0 || (1 << xb) > nx / 2)) --xb;
     std::vector<cx<T>> w[2];
     T offs[2] = {(T)off0d, (T)off1d};
     const T* ins[2] = {in0, in1};
     for (int f = 0; f < nf; ++f) {
         w[f].assign((size_t)nx * ny * pitch, cmake<T>(0, 0));
-#define ZP(N) zpass<N, T>(ins[f], w[f].data(), (long long)nx * ny, pitch, &offs[f])
+#define ZP(N) zpass<N, T>(ins[f], w[f].data(), (long long)nx * ny, pitch, &offs[f], ny, xb)
         DISPATCH_N(nz, ZP)
 #undef ZP
         if (upto >= 2) {
             constexpr int WZ = sizeof(T) == 4 ? 16 : 8;
-#define YP(N) ypass<N, T, (N <= 512 ? WZ : WZ / 2)>(w[f].data(), nx, nzh, pitch)
+#define YP(N) ypass<N, T, (N <= 512 ? WZ : WZ / 2)>(w[f].data(), nx, nzh, pitch, xb)
             DISPATCH_N(ny, YP)
 #undef YP
         }
     }
-    if (half_out) std::memcpy(half_out, w[0].data(), sizeof(cx<T>) * w[0].size());
+    if (half_out)
+        for (int x = 0; x < nx; ++x)
+            for (int y = 0; y < ny; ++y) {
+                const size_t row = ((((size_t)(x >> xb) * ny + y) << xb) + (x & ((1 << xb) - 1)));
+                std::memcpy(half_out + ((size_t)x * ny + y) * pitch, w[0].data() + row * pitch, sizeof(cx<T>) * pitch);
+            }
     if (upto < 3) return 0;
     constexpr int WZ = sizeof(T) == 4 ? 16 : 8;
     const int nctas = 3;
     if (spec) {
         if (nf == 1) {
-#define XP(N) xpass<N, T, (N <= 512 ? WZ : WZ / 2), 1, MODE_BIN>(w[0].data(), nullptr, ny, nz, pitch, &offs[0], nullptr, spec, sums, counts, nullptr, 0, 0.0, nctas)
+#define XP(N) xpass<N, T, (N <= 512 ? WZ : WZ / 2), 1, MODE_BIN>(w[0].data(), nullptr, ny, nz, pitch, &offs[0], nullptr, spec, sums, counts, nullptr, 0, 0.0, nctas, xb)
             DISPATCH_N(nx, XP)
 #undef XP
         } else {
-#define XP(N) xpass<N, T, (N <= 512 ? WZ : WZ / 2), 2, MODE_BIN>(w[0].data(), w[1].data(), ny, nz, pitch, &offs[0], &offs[1], spec, sums, counts, nullptr, 0, 0.0, nctas)
+#define XP(N) xpass<N, T, (N <= 512 ? WZ : WZ / 2), 2, MODE_BIN>(w[0].data(), w[1].data(), ny, nz, pitch, &offs[0], &offs[1], spec, sums, counts, nullptr, 0, 0.0, nctas, xb)
             DISPATCH_N(nx, XP)
 #undef XP
         }
     } else {
         if (nf == 1) {
-#define XP(N) xpass<N, T, (N <= 512 ? WZ : WZ / 2), 1, MODE_ND>(w[0].data(), nullptr, ny, nz, pitch, &offs[0], nullptr, nullptr, nullptr, nullptr, nd_out, nd_f64, scale, nctas)
+#define XP(N) xpass<N, T, (N <= 512 ? WZ : WZ / 2), 1, MODE_ND>(w[0].data(), nullptr, ny, nz, pitch, &offs[0], nullptr, nullptr, nullptr, nullptr, nd_out, nd_f64, scale, nctas, xb)
             DISPATCH_N(nx, XP)
 #undef XP
         } else {
-#define XP(N) xpass<N, T, (N <= 512 ? WZ : WZ / 2), 2, MODE_ND>(w[0].data(), w[1].data(), ny, nz, pitch, &offs[0], &offs[1], nullptr, nullptr, nullptr, nd_out, nd_f64, scale, nctas)
+#define XP(N) xpass<N, T, (N <= 512 ? WZ : WZ / 2), 2, MODE_ND>(w[0].data(), w[1].data(), ny, nz, pitch, &offs[0], &offs[1], nullptr, nullptr, nullptr, nd_out, nd_f64, scale, nctas, xb)
             DISPATCH_N(nx, XP)
 #undef XP
         }

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -83,6 +84,7 @@ struct t21_plan {
     void* tw[3];          // stage twiddles per axis (z: for nz/2), device
     void* twr;            // exp(-2 pi i k / nz), k = 0..nz/2, device
     int max_grid;         // capacity (in CTAs) of the partial-histogram buffers
+    int xb;               // log2 of the x blocking factor of the half-spectrum layout
 };
 
 struct WsLayout {
@@ -149,6 +151,14 @@ int t21_plan_create(t21_plan** out, int nx, int ny, int nz, int dtype, int devic
     p->fast[1] = fast_len(ny);
     p->fast[2] = fast_len(nz);
     p->max_grid = device_sm_count() * 8;
+    // x blocking of the workspace layout: XB rows of x stay adjacent so that the X pass does not
+    // touch a different 2 MB page with every row (T21_XB overrides, for experiments)
+    {
+        int xb = 2;
+        if (const char* e = getenv("T21_XB")) xb = atoi(e);
+        while (xb > 0 && ((nx % (1 << xb)) != 0 || (1 << xb) > 16 || (1 << xb) > nx / 2)) --xb;
+        p->xb = xb < 0 ? 0 : xb;
+    }
     int rc = 0;
     if (!(p->fast[0] && p->fast[1] && p->fast[2])) {
         set_error("shape %dx%dx%d: every axis must be a power of two in [%d, %d] for now", nx, ny, nz, kMinFast, kMaxFast);
@@ -187,10 +197,10 @@ static int forward_zy(const t21_plan* p, const void* const x[2], int nf, int sub
             offs[f] = o;
             prof_mark(st, SLOT_MEAN);
         }
-        ZArgs z{x[f], ws + L.w[f], (long long)p->n[0] * p->n[1], p->n[2], p->pitch, offs[f], p->tw[2], p->twr};
+        ZArgs z{x[f], ws + L.w[f], (long long)p->n[0] * p->n[1], p->n[2], p->pitch, p->n[1], p->xb, offs[f], p->tw[2], p->twr};
         if (int rc = launch_zpass(p->dtype, z, st)) return rc;
         prof_mark(st, SLOT_Z);
-        YArgs y{ws + L.w[f], (long long)p->n[0], p->n[1], p->nzh, p->pitch, p->tw[1]};
+        YArgs y{ws + L.w[f], (long long)p->n[0], p->n[1], p->nzh, p->pitch, p->xb, p->tw[1]};
         if (int rc = launch_ypass(p->dtype, y, st)) return rc;
         prof_mark(st, SLOT_Y);
     }
@@ -231,7 +241,7 @@ int t21_ps_binned(const t21_plan* p, const void* x1, const void* x2, int subtrac
     a.w[0] = ws + L.w[0];
     a.w[1] = nf == 2 ? ws + L.w[1] : nullptr;
     a.nf = nf;
-    a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch;
+    a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch; a.xb = p->xb;
     a.tw = p->tw[0];
     a.offset[0] = offs[0]; a.offset[1] = offs[1];
     a.ntot = (double)p->n[0] * p->n[1] * p->n[2];
@@ -274,7 +284,7 @@ int t21_ps_nd(const t21_plan* p, const void* x1, const void* x2, int subtract_me
     a.w[0] = ws + L.w[0];
     a.w[1] = nf == 2 ? ws + L.w[1] : nullptr;
     a.nf = nf;
-    a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch;
+    a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch; a.xb = p->xb;
     a.tw = p->tw[0];
     a.offset[0] = offs[0]; a.offset[1] = offs[1];
     a.ntot = (double)p->n[0] * p->n[1] * p->n[2];

@@ -63,6 +63,15 @@ template <> T21_HD cx<double> ldg<double>(const cx<double>* p) {
 #endif
 }
 
+// ask for the line holding p to be brought into L2 (no register, no stall); no-op on the host
+T21_HD void prefetch_l2(const void* p) {
+#if T21_DEVICE_CODE
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // IEEE double add that the compiler may never contract into an FMA
 T21_HD double dadd_rn(double a, double b) {
 #if T21_DEVICE_CODE

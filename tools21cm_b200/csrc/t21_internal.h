@@ -20,14 +20,14 @@ struct WZFor {
 };
 
 struct ZArgs {
-    const void* in; void* out; long long nrows; int nz; int pitch;
+    const void* in; void* out; long long nrows; int nz; int pitch; int ny; int xb;
     const void* offset; const void* tw; const void* twr;
 };
 struct YArgs {
-    void* w; long long nouter; int ny; int nzh; int pitch; const void* tw;
+    void* w; long long nouter; int ny; int nzh; int pitch; int xb; const void* tw;
 };
 struct XArgs {
-    const void* w[2]; int nf; int nx, ny, nz, nzh, pitch;
+    const void* w[2]; int nf; int nx, ny, nz, nzh, pitch; int xb;
     const void* tw; const void* offset[2]; double ntot;
     const t21_binspec* bins;                 // MODE_BIN
     void* nd_out; int nd_f64; double scale;  // MODE_ND

@@ -32,6 +32,10 @@ __global__ void __launch_bounds__(K::THREADS) tile_kernel(const __grid_constant_
     dev_phases<K, T>(p, (long long)blockIdx.x, (int)threadIdx.x, r, reinterpret_cast<cx<T>*>(smem_raw));
 }
 
+#ifndef T21_X_MIN_CTAS
+#define T21_X_MIN_CTAS 2
+#endif
+
 struct NoHist {
     __device__ void add(int, double, unsigned) {}
 };
@@ -40,7 +44,7 @@ struct NoHist {
 // in shared memory until the end (HK = 0), accumulates into global memory (HK = 1), or has no
 // histogram at all (HK = 2, n-D store).
 template <class K, typename T, int HK>
-__global__ void __launch_bounds__(K::THREADS)
+__global__ void __launch_bounds__(K::THREADS, (K::THREADS <= 512 ? T21_X_MIN_CTAS : 1))
 xpass_kernel(const __grid_constant__ typename K::Params p, int nbins, int warp_private,
              double* __restrict__ part_sum, unsigned* __restrict__ part_cnt, double* gsum, unsigned long long* gcnt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -119,7 +123,7 @@ inline int launch_x(XArgs& a, cudaStream_t st) {
     memset(&p, 0, sizeof(p));
     p.w[0] = (const cx<T>*)a.w[0];
     p.w[1] = (const cx<T>*)a.w[1];
-    p.ny = a.ny; p.nz = a.nz; p.nzh = a.nzh; p.pitch = a.pitch;
+    p.ny = a.ny; p.nz = a.nz; p.nzh = a.nzh; p.pitch = a.pitch; p.xb = a.xb;
     constexpr int WZ = K::THREADS / K::S::TP;
     p.nchunks = (a.nzh + WZ - 1) / WZ;
     p.ntiles = (long long)a.ny * p.nchunks;
@@ -149,6 +153,7 @@ inline int launch_x(XArgs& a, cudaStream_t st) {
         if (g > p.ntiles) g = p.ntiles;                                                                 \
         if (HKV == 0 && g > a.max_grid) g = a.max_grid;                                                 \
         grid = (int)g;                                                                                  \
+        p.tile_step = grid;                                                                             \
         kern<<<grid, K::THREADS, smem, st>>>(p, a.nbins, warp_private, a.part_sum, a.part_cnt, a.gsum, a.gcnt);        \
     }
     if constexpr (K::kMode == MODE_BIN) {

@@ -2,7 +2,10 @@
 //
 // Data layout (DESIGN.md "HBM layout"):
 //   input   x[nx][ny][nz]            real, C order (z contiguous)
-//   half    W[nx][ny][pitch]         complex, kz = 0..nz/2 valid, pitch = round_up(nz/2+1, 16)
+//   half    W[nx/XB][ny][XB][pitch]  complex, kz = 0..nz/2 valid, pitch = round_up(nz/2+1, 16);
+//                                    x is split as (x / XB, x % XB) around y so that both strided
+//                                    passes walk rows that are at most XB*pitch apart inside a
+//                                    group: row(x, y) = ((x / XB) * ny + y) * XB + x % XB
 //
 //   ZPass : rows along z.  Packs a real row into nz/2 complex values, FFTs it and untangles
 //           the result into the nz/2+1 non-redundant frequencies (the classic real-FFT trick),
@@ -41,6 +44,7 @@ struct ZPass {
         cx<T>* out;           // [nrows][pitch]
         long long nrows;
         int pitch;
+        int ny, xb;           // rows are (x, y) pairs; xb = log2 of the x blocking factor XB
         const T* offset;      // device scalar subtracted from every sample, or null
         const cx<T>* tw;      // Plan<M> stage twiddles
         const cx<T>* twr;     // exp(-2 pi i k / NZ), k = 0..M
@@ -75,7 +79,9 @@ struct ZPass {
         } else {
             // untangle: X[k] = (Z[k] + conj Z[M-k])/2 - i/2 * w^k * (Z[k] - conj Z[M-k])
             if (!active) return;
-            cx<T>* dst = p.out + row * p.pitch;
+            const long long x = row / p.ny, y = row - x * p.ny;
+            const long long orow = ((((x >> p.xb) * p.ny + y) << p.xb) + (x & ((1 << p.xb) - 1)));
+            cx<T>* dst = p.out + orow * p.pitch;
 #pragma unroll
             for (int i = 0; i < E; ++i) {
                 const int k = j + i * TP;
@@ -139,6 +145,7 @@ struct YPass {
         int nzh;              // valid columns
         int pitch;
         int nchunks;          // ceil(nzh / WZ)
+        int xb;               // log2 of the x blocking factor
         const cx<T>* tw;
     };
     struct Regs {
@@ -152,8 +159,10 @@ struct YPass {
         const long long outer = cta / p.nchunks;
         const int z = chunk * WZ + zl;
         const bool active = z < p.nzh;
-        cx<T>* base = p.w + outer * (long long)NY * p.pitch + (active ? z : 0);
-        const long long stride = p.pitch;
+        // outer = x: rows of this pencil are ((x / XB) * NY + y) * XB + x % XB
+        const long long row0 = (((outer >> p.xb) * NY) << p.xb) + (outer & ((1 << p.xb) - 1));
+        cx<T>* base = p.w + row0 * p.pitch + (active ? z : 0);
+        const long long stride = (long long)p.pitch << p.xb;
         S::template fft_phase<PH>(
             r.v, j, zl, p.tw, smem,
             [&](int i) { return active ? base[i * stride] : cmake<T>(0, 0); },
@@ -195,6 +204,8 @@ struct XPass {
         const cx<T>* w[2];    // [NX][ny][pitch] per field
         int ny, nz, nzh, pitch, nchunks;
         long long ntiles;     // ny * nchunks
+        long long tile_step;  // tiles between two consecutive tiles of one CTA (the grid size)
+        int xb;               // log2 of the x blocking factor
         const cx<T>* tw;
         const T* offset[2];   // device scalars (mean offsets) or null
         double ntot;          // nx*ny*nz, for the analytic DC repair
@@ -223,24 +234,40 @@ struct XPass {
         if constexpr (PH < NF * S::FFT_PHASES) {
             constexpr int F = PH / S::FFT_PHASES;          // field this phase works on
             constexpr int FPH = PH % S::FFT_PHASES;
-            const cx<T>* base = p.w[F] + (long long)iy * p.pitch + (active ? iz : 0);
-            const long long stride = (long long)p.ny * p.pitch;
+            // element i (= x) lives in row ((i / XB) * ny + iy) * XB + i % XB
+            const cx<T>* base = p.w[F] + (active ? iz : 0);
+            const long long gstride = ((long long)p.ny * p.pitch) << p.xb;     // between x groups
+            const long long ybase = ((long long)iy * p.pitch) << p.xb;
+            const int xmask = (1 << p.xb) - 1;
             S::template fft_phase<FPH>(
                 r.v[F], j, zl, p.tw, smem,
-                [&](int i) { return active ? base[i * stride] : cmake<T>(0, 0); },
+                [&](int i) {
+                    return active ? base[(i >> p.xb) * gstride + ybase + (long long)(i & xmask) * p.pitch]
+                                  : cmake<T>(0, 0);
+                },
                 [&](int i, cx<T> b, int slot) {
                     // last stage of field F: element i (= kx) is final and sits in register `slot`.
                     // Field 0 of a cross spectrum just stays there; the last field forms the power.
                     if constexpr (F == NF - 1) {
                         const cx<T> a = (NF == 1) ? b : r.v[0][slot];
-                        ptile(smem)[i * WZ + zl] = a.x * b.x + a.y * b.y;
+                        T pw = a.x * b.x + a.y * b.y;
                         if (i == 0 && iy == 0 && iz == 0) {
                             // DC of (x - c) plus c*N: the only sample the mean offset changes
                             const double c0 = p.offset[0] ? (double)ldg(p.offset[0]) : 0.0;
                             const double c1 = (NF == 2 && p.offset[1]) ? (double)ldg(p.offset[1]) : c0;
                             const double ra = (double)a.x + c0 * p.ntot, rb = (double)b.x + c1 * p.ntot;
-                            *dc_slot(smem) = ra * rb + (double)a.y * (double)b.y;
+                            const double dc = ra * rb + (double)a.y * (double)b.y;
+                            if constexpr (MODE == MODE_BIN) {
+                                // the tile keeps 0 for this sample (so it is counted like any other mode);
+                                // its power goes to the histogram here, once, with count 0
+                                pw = (T)0;
+                                const ModeBins mb = classify(p.bins, 0, 0, 0, false);
+                                if (mb.own >= 0) hist.add(mb.own, dc, 0u);
+                            } else {
+                                *dc_slot(smem) = dc;
+                            }
                         }
+                        ptile(smem)[i * WZ + zl] = pw;
                     }
                 });
         } else {
@@ -267,102 +294,118 @@ struct XPass {
     template <class Hist>
     static T21_HD void epilogue(const Params& p, int tid, int iy, int iz, int zl, bool active, Regs& r,
                                 cx<T>* smem, Hist& hist) {
-        const T* pt = ptile(smem);
+        if constexpr (MODE == MODE_BIN) {
+            // three specialisations of the same loop, picked by a CTA-uniform branch
+            if (p.bins.nmu == 0) epilogue_bin<0>(p, tid, iy, iz, zl, active, r, smem, hist);
+            else if (p.bins.absolute_mus) epilogue_bin<1>(p, tid, iy, iz, zl, active, r, smem, hist);
+            else epilogue_bin<2>(p, tid, iy, iz, zl, active, r, smem, hist);
+        } else {
+            epilogue_nd(p, tid, iy, iz, zl, active, smem);
+        }
+    }
+
+    // MU: 0 shells, 1 |mu| bins, 2 signed mu bins (twins binned separately)
+    template <int MU, class Hist>
+    static T21_HD void epilogue_bin(const Params& p, int tid, int iy, int iz, int zl, bool active, Regs& r,
+                                    cx<T>* smem, Hist& hist) {
+        const t21_binspec& B = p.bins;
         const int q = tid / WZ;                                   // row id of this thread, 0..TP-1
         const int ix0 = (q / RPI) * (E * RPI) + (q % RPI);
         const bool has_twin = (iz != 0) && (iz != p.nz - iz);
-        if constexpr (MODE == MODE_BIN) {
-            const t21_binspec& B = p.bins;
-            const int nb = B.nk * (B.nmu > 0 ? B.nmu : 1);
-            const bool mu_on = B.nmu > 0;
-            const bool abs_mu = B.absolute_mus != 0;
-            const bool signed_mu = mu_on && !abs_mu;
-            const int los = B.los_axis;
-            // k_perp = 0 line (power_spectrum.py:563-575): the part of the test that is fixed for this thread
-            bool line_fixed = false;
-            if (mu_on && B.exclude_zero)
-                line_fixed = los == 0 ? (iy == B.zero_idx[1] && iz == B.zero_idx[2])
-                                      : (los == 1 ? iz == B.zero_idx[2] : iy == B.zero_idx[1]);
-            const int iz_c = active ? iz : 0;
-            const float c_yz = ldg(B.tab_sf[1] + iy) + ldg(B.tab_sf[2] + iz_c);
-            const unsigned wt = (has_twin && !signed_mu) ? 2u : 1u;
-            float klos_c = 0.f;
-            bool nyq_c = false;
-            if (mu_on && los != 0) {
-                const int il = los == 1 ? iy : iz_c;
-                klos_c = ldg(B.tab_losf + il);
-                nyq_c = il == B.nyq_idx[los];
-            }
+        const int nb = B.nk * (MU ? B.nmu : 1);
+        const int los = MU ? B.los_axis : -1;
+        const int zx = B.zero_idx[0], nyx = B.nyq_idx[0];
+        // k_perp = 0 line (power_spectrum.py:563-575): the part of the test that is fixed for this thread
+        bool line_fixed = false;
+        if (MU && B.exclude_zero)
+            line_fixed = los == 0 ? (iy == B.zero_idx[1] && iz == B.zero_idx[2])
+                                  : (los == 1 ? iz == B.zero_idx[2] : iy == B.zero_idx[1]);
+        const int iz_c = active ? iz : 0;
+        const float c_yz = ldg(B.tab_sf[1] + iy) + ldg(B.tab_sf[2] + iz_c);
+        const unsigned wt = (has_twin && MU != 2) ? 2u : 1u;
+        const T wf = (T)wt;
+        float klos_c = 0.f;
+        bool nyq_c = false;
+        if (MU && los != 0) {
+            const int il = los == 1 ? iy : iz_c;
+            klos_c = ldg(B.tab_losf + il);
+            nyq_c = il == B.nyq_idx[los];
+        }
+        const T* pt = ptile(smem) + ix0 * WZ + zl;
+        const float* sfx = B.tab_sf[0] + ix0;
+        const float* lfx = B.tab_losf + ix0;
 #if T21_DEVICE_CODE
 #pragma unroll 1
 #endif
-            for (int it = 0; it < E; ++it) {
-                const int ix = ix0 + it * RPI;
-                double pw = (double)pt[ix * WZ + zl];
-                if ((ix | iy | iz) == 0) pw = *dc_slot(smem);
-                const bool valid = active && !(line_fixed && (los == 0 || ix == B.zero_idx[0]));
+        for (int it = 0; it < E; ++it, pt += RPI * WZ, sfx += RPI, lfx += RPI) {
+            const int ix = ix0 + it * RPI;
+            const double pw = (double)(*pt * wf);
+            bool valid = active;
+            if (MU) valid = valid && !(line_fixed && (los == 0 || ix == zx));
 #if T21_DEVICE_CODE
-                if constexpr (THREADS % 32 == 0) {
-                    const float sh = ldg(B.tab_sf[0] + ix) + c_yz;
-                    float muh = 0.f;
-                    bool nyq = nyq_c;
-                    if (mu_on) {
-                        const float kl = los == 0 ? ldg(B.tab_losf + ix) : klos_c;
-                        if (los == 0) nyq = ix == B.nyq_idx[0];
-                        muh = kl * fast_rsqrt(sh);
-                    }
-                    const float m_own = abs_mu ? fabsf(muh) : muh;
-                    const double pw_w = wt == 2u ? pw + pw : pw;
-                    const bool ok = mu_on ? warpbins_fast<true>(r.acc[0], sh, m_own, pw_w, wt, valid)
-                                          : warpbins_fast<false>(r.acc[0], sh, 0.f, pw_w, wt, valid);
-                    if (!ok) {
+            if constexpr (THREADS % 32 == 0) {
+                const float sh = ldg(sfx) + c_yz;
+                float muh = 0.f;
+                bool nyq = nyq_c;
+                if (MU) {
+                    float kl = klos_c;
+                    if (los == 0) { kl = ldg(lfx); nyq = ix == nyx; }
+                    muh = kl * fast_rsqrt(sh);
+                }
+                const float m_own = MU == 1 ? fabsf(muh) : muh;
+                if (!warpbins_fast<(MU != 0)>(r.acc[0], sh, m_own, pw, wt, valid)) {
+                    int w1 = 1;
+                    const int bin = valid ? exact_bin(p, ix, iy, iz, has_twin, 0, sh, w1) : -1;
+                    warpbins_slow(r.acc[0], hist, B, nb, bin, w1 == (int)wt ? pw : (double)*pt, (unsigned)w1, valid);
+                }
+                if (MU == 2) {                                // the twin goes to the mirrored mu bin
+                    const bool tv = valid && has_twin;
+                    const float m_tw = nyq ? muh : -muh;
+                    if (!warpbins_fast<true>(r.acc[1], sh, m_tw, pw, 1u, tv)) {
                         int w1 = 1;
-                        const int bin = valid ? exact_bin(p, ix, iy, iz, has_twin, 0, sh, w1) : -1;
-                        warpbins_slow(r.acc[0], hist, B, nb, bin, w1 == 2 ? pw + pw : pw, (unsigned)w1, valid);
+                        const int bin = tv ? exact_bin(p, ix, iy, iz, has_twin, 1, sh, w1) : -1;
+                        warpbins_slow(r.acc[1], hist, B, nb, bin, pw, 1u, tv);
                     }
-                    if (signed_mu) {                          // the twin goes to the mirrored mu bin
-                        const bool tv = valid && has_twin;
-                        const float m_tw = nyq ? muh : -muh;
-                        if (!warpbins_fast<true>(r.acc[1], sh, m_tw, pw, 1u, tv)) {
-                            int w1 = 1;
-                            const int bin = tv ? exact_bin(p, ix, iy, iz, has_twin, 1, sh, w1) : -1;
-                            warpbins_slow(r.acc[1], hist, B, nb, bin, pw, 1u, tv);
-                        }
-                    }
-                    continue;
                 }
-#endif
-                // per-thread path: CTAs smaller than a warp, and the CPU replay
-                if (valid) {
-                    const ModeBins mb = classify(B, ix, iy, iz, has_twin);
-                    acc_add_thread(r.acc[0], hist, mb.own, pw, mb.own_w);
-                    if (signed_mu) acc_add_thread(r.acc[1], hist, mb.twin, pw, 1);
-                }
+                continue;
             }
-        } else {
+#endif
+            // per-thread path: CTAs smaller than a warp, and the CPU replay
+            if (valid) {
+                const ModeBins mb = classify(B, ix, iy, iz, has_twin);
+                acc_add_thread(r.acc[0], hist, mb.own, (double)*pt, mb.own_w);
+                if (MU == 2) acc_add_thread(r.acc[1], hist, mb.twin, (double)*pt, 1);
+            }
+        }
+    }
+
+    static T21_HD void epilogue_nd(const Params& p, int tid, int iy, int iz, int zl, bool active, cx<T>* smem) {
+        const T* pt = ptile(smem);
+        const int q = tid / WZ;
+        const int ix0 = (q / RPI) * (E * RPI) + (q % RPI);
+        const bool has_twin = (iz != 0) && (iz != p.nz - iz);
+        if (!active) return;
 #if T21_DEVICE_CODE
 #pragma unroll 1
 #endif
-            for (int it = 0; it < E; ++it) {
-                const int ix = ix0 + it * RPI;
-                double pw = (double)pt[ix * WZ + zl];
-                if ((ix | iy | iz) == 0) pw = *dc_slot(smem);
-                if (!active) continue;
-                const double val = pw * p.scale;
-                const int hy = p.ny / 2, hz = p.nz / 2;
-                const int sx = ix + NX / 2 - (ix + NX / 2 >= NX ? NX : 0);
-                const int sy = iy + hy - (iy + hy >= p.ny ? p.ny : 0);
-                const int sz = iz + hz - (iz + hz >= p.nz ? p.nz : 0);
-                const long long o = ((long long)sx * p.ny + sy) * p.nz + sz;
-                if (p.nd_f64) ((double*)p.nd_out)[o] = val; else ((float*)p.nd_out)[o] = (float)val;
-                if (has_twin) {
-                    const int tx = ix ? NX - ix : 0, ty = iy ? p.ny - iy : 0, tz = p.nz - iz;
-                    const int ux = tx + NX / 2 - (tx + NX / 2 >= NX ? NX : 0);
-                    const int uy = ty + hy - (ty + hy >= p.ny ? p.ny : 0);
-                    const int uz = tz + hz - (tz + hz >= p.nz ? p.nz : 0);
-                    const long long ot = ((long long)ux * p.ny + uy) * p.nz + uz;
-                    if (p.nd_f64) ((double*)p.nd_out)[ot] = val; else ((float*)p.nd_out)[ot] = (float)val;
-                }
+        for (int it = 0; it < E; ++it) {
+            const int ix = ix0 + it * RPI;
+            double pw = (double)pt[ix * WZ + zl];
+            if ((ix | iy | iz) == 0) pw = *dc_slot(smem);
+            const double val = pw * p.scale;
+            const int hy = p.ny / 2, hz = p.nz / 2;
+            const int sx = ix + NX / 2 - (ix + NX / 2 >= NX ? NX : 0);
+            const int sy = iy + hy - (iy + hy >= p.ny ? p.ny : 0);
+            const int sz = iz + hz - (iz + hz >= p.nz ? p.nz : 0);
+            const long long o = ((long long)sx * p.ny + sy) * p.nz + sz;
+            if (p.nd_f64) ((double*)p.nd_out)[o] = val; else ((float*)p.nd_out)[o] = (float)val;
+            if (has_twin) {
+                const int tx = ix ? NX - ix : 0, ty = iy ? p.ny - iy : 0, tz = p.nz - iz;
+                const int ux = tx + NX / 2 - (tx + NX / 2 >= NX ? NX : 0);
+                const int uy = ty + hy - (ty + hy >= p.ny ? p.ny : 0);
+                const int uz = tz + hz - (tz + hz >= p.nz ? p.nz : 0);
+                const long long ot = ((long long)ux * p.ny + uy) * p.nz + uz;
+                if (p.nd_f64) ((double*)p.nd_out)[ot] = val; else ((float*)p.nd_out)[ot] = (float)val;
             }
         }
     }

@@ -93,10 +93,17 @@ struct DFT<1, T> {
 };
 
 // ---- compile-time plan ------------------------------------------------------------
+// values per thread (= largest radix).  32 halves the number of shared-memory exchanges and
+// barriers for long pencils at the price of ~2x the registers; T21_EMAX overrides for experiments.
+#ifndef T21_EMAX_LONG
+#define T21_EMAX_LONG 16
+#endif
+constexpr int plan_emax(int n) { return n >= 512 ? T21_EMAX_LONG : 16; }
+
 template <int N>
 struct Plan {
     static_assert(is_pow2(N) && N >= 2, "pencil length must be a power of two");
-    static constexpr int E = N < 16 ? N : 16;  // values per thread
+    static constexpr int E = N < plan_emax(N) ? N : plan_emax(N);  // values per thread
     static constexpr int T = N / E;            // threads per pencil
     static constexpr int radix(int s) {        // radix of stage s (0 past the end)
         int rem = N;
@@ -124,7 +131,7 @@ struct Plan {
 
 // number of twiddle entries for a run-time N (host side of t21_plan_create)
 inline int plan_tw_total(int n) {
-    int e = n < 16 ? n : 16, rem = n, nsv = 1, tot = 0, s = 0;
+    int e = n < plan_emax(n) ? n : plan_emax(n), rem = n, nsv = 1, tot = 0, s = 0;
     while (rem > 1) {
         int r = rem < e ? rem : e;
         if (s > 0) tot += (r - 1) * nsv;

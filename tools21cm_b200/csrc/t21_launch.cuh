@@ -44,7 +44,7 @@ struct NoHist {
 // in shared memory until the end (HK = 0), accumulates into global memory (HK = 1), or has no
 // histogram at all (HK = 2, n-D store).
 template <class K, typename T, int HK>
-__global__ void __launch_bounds__(K::THREADS, (K::THREADS <= 512 ? T21_X_MIN_CTAS : 1))
+__global__ void __launch_bounds__(K::THREADS, (K::THREADS * K::E <= 512 * 16 ? T21_X_MIN_CTAS : 1))
 xpass_kernel(const __grid_constant__ typename K::Params p, int nbins, int warp_private,
              double* __restrict__ part_sum, unsigned* __restrict__ part_cnt, double* gsum, unsigned long long* gcnt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

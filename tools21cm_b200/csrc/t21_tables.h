@@ -35,7 +35,7 @@ inline void unit_root(long long num, long long den, double& c, double& s) {
 template <typename T>
 std::vector<cx<T>> build_stage_twiddles(int n) {
     std::vector<cx<T>> tab;
-    const int e = n < 16 ? n : 16;
+    const int e = n < plan_emax(n) ? n : plan_emax(n);
     int rem = n, nsv = 1, s = 0;
     while (rem > 1) {
         const int r = rem < e ? rem : e;

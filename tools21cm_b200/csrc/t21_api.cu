@@ -117,12 +117,18 @@ static int upload(const std::vector<cx<T>>& v, void** out) {
 template <typename T>
 static int build_tables(t21_plan* p) {
     for (int d = 0; d < 3; ++d) {
-        if (!p->fast[d]) continue;
-        const int len = d == 2 ? p->n[2] / 2 : p->n[d];
-        if (int rc = upload<T>(build_stage_twiddles<T>(len), &p->tw[d])) return rc;
+        if (p->fast[d]) {
+            const int len = d == 2 ? p->n[2] / 2 : p->n[d];
+            if (int rc = upload<T>(build_stage_twiddles<T>(len), &p->tw[d])) return rc;
+        } else if (d < 2) {
+            if (int rc = upload<T>(build_roots<T>(p->n[d], p->n[d]), &p->tw[d])) return rc;   // generic pass
+        }
     }
-    if (p->fast[2])
+    if (p->fast[2]) {
         if (int rc = upload<T>(build_roots<T>(p->n[2], p->n[2] / 2 + 1), &p->twr)) return rc;
+    } else {
+        if (int rc = upload<T>(build_roots<T>(p->n[2], p->n[2]), &p->twr)) return rc;          // generic pass
+    }
     return 0;
 }
 
@@ -157,14 +163,10 @@ int t21_plan_create(t21_plan** out, int nx, int ny, int nz, int dtype, int devic
         int xb = 2;
         if (const char* e = getenv("T21_XB")) xb = atoi(e);
         while (xb > 0 && ((nx % (1 << xb)) != 0 || (1 << xb) > 16 || (1 << xb) > nx / 2)) --xb;
+        if (!p->fast[0] || !p->fast[1]) xb = 0;
         p->xb = xb < 0 ? 0 : xb;
     }
-    int rc = 0;
-    if (!(p->fast[0] && p->fast[1] && p->fast[2])) {
-        set_error("shape %dx%dx%d: every axis must be a power of two in [%d, %d] for now", nx, ny, nz, kMinFast, kMaxFast);
-        rc = T21_EINVAL;
-    }
-    if (!rc) rc = dtype == T21_F32 ? build_tables<float>(p) : build_tables<double>(p);
+    int rc = dtype == T21_F32 ? build_tables<float>(p) : build_tables<double>(p);
     if (cur != device) cudaSetDevice(cur);
     if (rc) { t21_plan_destroy(p); return rc; }
     *out = p;
@@ -200,10 +202,10 @@ static int forward_zy(const t21_plan* p, const void* const x[2], int nf, int sub
         // (Running Z and Y slab by slab to keep the half spectrum in L2 between them was measured and
         // is slower: neither pass is DRAM-bandwidth bound and every extra launch costs ~5 us.)
         ZArgs z{x[f], ws + L.w[f], (long long)p->n[0] * p->n[1], p->n[2], p->pitch, p->n[1], p->xb, offs[f], p->tw[2], p->twr};
-        if (int rc = launch_zpass(p->dtype, z, st)) return rc;
+        if (int rc = p->fast[2] ? launch_zpass(p->dtype, z, st) : launch_zpass_generic(p->dtype, z, st)) return rc;
         prof_mark(st, SLOT_Z);
         YArgs y{ws + L.w[f], (long long)p->n[0], p->n[1], p->nzh, p->pitch, p->xb, p->tw[1]};
-        if (int rc = launch_ypass(p->dtype, y, st)) return rc;
+        if (int rc = p->fast[1] ? launch_ypass(p->dtype, y, st) : launch_ypass_generic(p->dtype, y, st)) return rc;
         prof_mark(st, SLOT_Y);
     }
     return 0;
@@ -257,7 +259,8 @@ int t21_ps_binned(const t21_plan* p, const void* x1, const void* x2, int subtrac
     a.max_grid = p->max_grid;
     if (a.hist_global)
         if (int rc = launch_zero_hist(sums_out, counts_out, nbins, st)) return rc;
-    int rc = p->dtype == T21_F32 ? launch_xpass_f32_bin(a, st) : launch_xpass_f64_bin(a, st);
+    int rc = !p->fast[0] ? launch_xpass_generic(p->dtype, a, st)
+                         : (p->dtype == T21_F32 ? launch_xpass_f32_bin(a, st) : launch_xpass_f64_bin(a, st));
     if (rc) return rc;
     prof_mark(st, SLOT_X);
     if (!a.hist_global) {
@@ -292,7 +295,8 @@ int t21_ps_nd(const t21_plan* p, const void* x1, const void* x2, int subtract_me
     a.ntot = (double)p->n[0] * p->n[1] * p->n[2];
     a.nd_out = out; a.nd_f64 = out_dtype == T21_F64; a.scale = scale;
     a.max_grid = p->max_grid;
-    const int rc = p->dtype == T21_F32 ? launch_xpass_f32_nd(a, st) : launch_xpass_f64_nd(a, st);
+    const int rc = !p->fast[0] ? launch_xpass_generic(p->dtype, a, st)
+                               : (p->dtype == T21_F32 ? launch_xpass_f32_nd(a, st) : launch_xpass_f64_nd(a, st));
     prof_mark(st, SLOT_X);
     return rc;
 }

@@ -1,0 +1,265 @@
+// Any-length fallbacks for the three passes: direct O(n^2) DFTs from a root table.
+//
+// The Stockham kernels cover power-of-two pencils from 8 to 4096.  Real data also comes in
+// 250^3 / 300^3 / 600^3 grids and odd, non-cubic light-cone chunks, and
+// tiny or degenerate axes (1-D / 2-D inputs are 3-D arrays with leading axes of length 1).
+// These kernels keep the same workspace layout and argument structs, so every axis picks its
+// own implementation.  They are still CUDA -- there is no CPU path -- but they make no attempt
+// at speed-of-light: each output is a dot product with the n-th roots of unity (index k*j mod n,
+// so the twiddles are exact table entries).
+#include <string.h>
+#include "t21_launch.cuh"
+
+namespace t21 {
+
+constexpr int kGenThreads = 256;
+
+template <typename T> struct GenWZ { static constexpr int value = sizeof(T) == 4 ? 8 : 4; };
+
+// ---- Z: real rows -> nz/2+1 complex ---------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kGenThreads)
+gen_zpass_kernel(const T* __restrict__ in, cx<T>* __restrict__ out, long long nrows, int nz, int nzh, int pitch,
+                 int ny, int xb, const T* __restrict__ offset, const cx<T>* __restrict__ roots) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* row = reinterpret_cast<T*>(smem_raw);
+    const T off = offset ? ldg(offset) : (T)0;
+    for (long long r = blockIdx.x; r < nrows; r += gridDim.x) {
+        __syncthreads();
+        for (int z = threadIdx.x; z < nz; z += kGenThreads) row[z] = in[r * nz + z] - off;
+        __syncthreads();
+        const long long x = r / ny, y = r - x * ny;
+        const long long orow = ((((x >> xb) * ny + y) << xb) + (x & ((1 << xb) - 1)));
+        for (int k = threadIdx.x; k < nzh; k += kGenThreads) {
+            T sr = 0, si = 0;
+            int idx = 0;                       // k*z mod nz
+            for (int z = 0; z < nz; ++z) {
+                const cx<T> w = ldg(roots + idx);
+                sr += row[z] * w.x;
+                si += row[z] * w.y;
+                idx += k;
+                if (idx >= nz) idx -= nz;
+            }
+            out[orow * pitch + k] = cmake<T>(sr, si);
+        }
+    }
+}
+
+// ---- Y: in-place strided pencils --------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kGenThreads)
+gen_ypass_kernel(cx<T>* __restrict__ w, long long nouter, int ny, int nzh, int pitch, int xb,
+                 const cx<T>* __restrict__ roots) {
+    constexpr int WZ = GenWZ<T>::value;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* tile = reinterpret_cast<cx<T>*>(smem_raw);      // [ny][WZ]
+    const int nchunks = (nzh + WZ - 1) / WZ;
+    const long long ntiles = nouter * nchunks;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int chunk = (int)(t % nchunks);
+        const long long x = t / nchunks;
+        const long long row0 = (((x >> xb) * ny) << xb) + (x & ((1 << xb) - 1));
+        cx<T>* base = w + row0 * pitch + chunk * WZ;
+        const long long stride = (long long)pitch << xb;
+        __syncthreads();
+        for (int e = threadIdx.x; e < ny * WZ; e += kGenThreads) {
+            const int y = e / WZ, zl = e % WZ;
+            tile[e] = (chunk * WZ + zl < nzh) ? base[y * stride + zl] : cmake<T>(0, 0);
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < ny * WZ; e += kGenThreads) {
+            const int k = e / WZ, zl = e % WZ;
+            if (chunk * WZ + zl >= nzh) continue;
+            T sr = 0, si = 0;
+            int idx = 0;
+            for (int y = 0; y < ny; ++y) {
+                const cx<T> v = tile[y * WZ + zl], r = ldg(roots + idx);
+                sr += v.x * r.x - v.y * r.y;
+                si += v.x * r.y + v.y * r.x;
+                idx += k;
+                if (idx >= ny) idx -= ny;
+            }
+            base[k * stride + zl] = cmake<T>(sr, si);
+        }
+    }
+}
+
+// ---- X: pencils fused with power + binning or the n-D store -------------------------------------
+// HK: 0 shared-memory histogram + per-CTA partials, 1 global atomics, 2 n-D store
+template <typename T, int NF, int HK>
+__global__ void __launch_bounds__(kGenThreads)
+gen_xpass_kernel(const cx<T>* __restrict__ w0, const cx<T>* __restrict__ w1, int nx, int ny, int nz, int nzh,
+                 int pitch, int xb, const cx<T>* __restrict__ roots, const T* off0, const T* off1, double ntot,
+                 const __grid_constant__ t21_binspec B, int nbins, double* __restrict__ part_sum,
+                 unsigned* __restrict__ part_cnt, double* gsum, unsigned long long* gcnt, void* nd_out, int nd_f64,
+                 double scale) {
+    constexpr int WZ = GenWZ<T>::value;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* tile0 = reinterpret_cast<cx<T>*>(smem_raw);                 // [nx][WZ]
+    cx<T>* tile1 = tile0 + (NF == 2 ? (size_t)nx * WZ : 0);
+    double* hs = reinterpret_cast<double*>(tile0 + (size_t)NF * nx * WZ);
+    unsigned* hc = reinterpret_cast<unsigned*>(hs + (HK == 0 ? nbins : 0));
+    if (HK == 0) {
+        for (int b = threadIdx.x; b < nbins; b += kGenThreads) { hs[b] = 0.0; hc[b] = 0u; }
+    }
+    SmemHist sh{hs, hc};
+    GlobalHist gh{gsum, gcnt};
+    RunAcc acc[2];
+    run_init(acc[0]);
+    run_init(acc[1]);
+    const int nchunks = (nzh + WZ - 1) / WZ;
+    const long long ntiles = (long long)ny * nchunks;
+    const long long gstride = ((long long)ny * pitch) << xb;
+    const int xmask = (1 << xb) - 1;
+    const bool signed_mu = B.nmu > 0 && !B.absolute_mus;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int chunk = (int)(t % nchunks), iy = (int)(t / nchunks);
+        const long long ybase = ((long long)iy * pitch) << xb;
+        __syncthreads();
+        for (int e = threadIdx.x; e < nx * WZ; e += kGenThreads) {
+            const int i = e / WZ, zl = e % WZ;
+            const bool ok = chunk * WZ + zl < nzh;
+            const long long o = (i >> xb) * gstride + ybase + (long long)(i & xmask) * pitch + chunk * WZ + zl;
+            tile0[e] = ok ? w0[o] : cmake<T>(0, 0);
+            if (NF == 2) tile1[e] = ok ? w1[o] : cmake<T>(0, 0);
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < nx * WZ; e += kGenThreads) {
+            const int ix = e / WZ, zl = e % WZ, iz = chunk * WZ + zl;
+            if (iz >= nzh) continue;
+            T ar = 0, ai = 0, br = 0, bi = 0;
+            int idx = 0;
+            for (int x = 0; x < nx; ++x) {
+                const cx<T> r = ldg(roots + idx);
+                const cx<T> v = tile0[x * WZ + zl];
+                ar += v.x * r.x - v.y * r.y;
+                ai += v.x * r.y + v.y * r.x;
+                if (NF == 2) {
+                    const cx<T> u = tile1[x * WZ + zl];
+                    br += u.x * r.x - u.y * r.y;
+                    bi += u.x * r.y + u.y * r.x;
+                }
+                idx += ix;
+                if (idx >= nx) idx -= nx;
+            }
+            if (NF == 1) { br = ar; bi = ai; }
+            double pw;
+            if ((ix | iy | iz) == 0) {
+                const double c0 = off0 ? (double)ldg(off0) : 0.0;
+                const double c1 = (NF == 2 && off1) ? (double)ldg(off1) : c0;
+                pw = ((double)ar + c0 * ntot) * ((double)br + c1 * ntot) + (double)ai * (double)bi;
+            } else {
+                pw = (double)(ar * br + ai * bi);
+            }
+            const bool has_twin = (iz != 0) && (iz != nz - iz);
+            if (HK == 2) {
+                const double val = pw * scale;
+                const int hx = nx / 2, hy = ny / 2, hz = nz / 2;
+                const int sx = (ix + hx) % nx, sy = (iy + hy) % ny, sz = (iz + hz) % nz;
+                const long long o = ((long long)sx * ny + sy) * nz + sz;
+                if (nd_f64) ((double*)nd_out)[o] = val; else ((float*)nd_out)[o] = (float)val;
+                if (has_twin) {
+                    const int ux = ((nx - ix) % nx + hx) % nx, uy = ((ny - iy) % ny + hy) % ny, uz = (nz - iz + hz) % nz;
+                    const long long ot = ((long long)ux * ny + uy) * nz + uz;
+                    if (nd_f64) ((double*)nd_out)[ot] = val; else ((float*)nd_out)[ot] = (float)val;
+                }
+            } else {
+                const ModeBins mb = classify(B, ix, iy, iz, has_twin);
+                if (HK == 0) {
+                    run_add(acc[0], sh, mb.own, pw, mb.own_w);
+                    if (signed_mu) run_add(acc[1], sh, mb.twin, pw, 1);
+                } else {
+                    run_add(acc[0], gh, mb.own, pw, mb.own_w);
+                    if (signed_mu) run_add(acc[1], gh, mb.twin, pw, 1);
+                }
+            }
+        }
+    }
+    if (HK == 0) {
+        run_flush(acc[0], sh);
+        run_flush(acc[1], sh);
+        __syncthreads();
+        for (int b = threadIdx.x; b < nbins; b += kGenThreads) {
+            part_sum[(size_t)blockIdx.x * nbins + b] = hs[b];
+            part_cnt[(size_t)blockIdx.x * nbins + b] = hc[b];
+        }
+    } else if (HK == 1) {
+        run_flush(acc[0], gh);
+        run_flush(acc[1], gh);
+    }
+}
+
+// ---- launchers -------------------------------------------------------------------------------------
+template <typename T>
+static int gen_z(const ZArgs& a, cudaStream_t st) {
+    const int nzh = a.nz / 2 + 1;
+    const size_t smem = (size_t)a.nz * sizeof(T);
+    auto kern = gen_zpass_kernel<T>;
+    if (int rc = ensure_smem(kern, smem)) return rc;
+    long long g = a.nrows < (long long)device_sm_count() * 16 ? a.nrows : (long long)device_sm_count() * 16;
+    if (g < 1) return 0;
+    kern<<<(unsigned)g, kGenThreads, smem, st>>>((const T*)a.in, (cx<T>*)a.out, a.nrows, a.nz, nzh, a.pitch, a.ny, a.xb,
+                                               (const T*)a.offset, (const cx<T>*)a.twr);
+    count_launch();
+    T21_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int launch_zpass_generic(int dtype, const ZArgs& a, cudaStream_t st) {
+    return dtype == T21_F32 ? gen_z<float>(a, st) : gen_z<double>(a, st);
+}
+
+template <typename T>
+static int gen_y(const YArgs& a, cudaStream_t st) {
+    constexpr int WZ = GenWZ<T>::value;
+    const size_t smem = (size_t)a.ny * WZ * sizeof(cx<T>);
+    if (smem > 200 * 1024) { set_error("axis of length %d is too long for the generic pass", a.ny); return T21_EINVAL; }
+    auto kern = gen_ypass_kernel<T>;
+    if (int rc = ensure_smem(kern, smem)) return rc;
+    const long long ntiles = a.nouter * ((a.nzh + WZ - 1) / WZ);
+    long long g = ntiles < (long long)device_sm_count() * 8 ? ntiles : (long long)device_sm_count() * 8;
+    if (g < 1) return 0;
+    kern<<<(unsigned)g, kGenThreads, smem, st>>>((cx<T>*)a.w, a.nouter, a.ny, a.nzh, a.pitch, a.xb, (const cx<T>*)a.tw);
+    count_launch();
+    T21_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int launch_ypass_generic(int dtype, const YArgs& a, cudaStream_t st) {
+    return dtype == T21_F32 ? gen_y<float>(a, st) : gen_y<double>(a, st);
+}
+
+template <typename T, int NF>
+static int gen_x(XArgs& a, cudaStream_t st) {
+    constexpr int WZ = GenWZ<T>::value;
+    const bool is_bin = a.bins != nullptr;
+    const int hk = !is_bin ? 2 : (a.hist_global ? 1 : 0);
+    size_t smem = (size_t)NF * a.nx * WZ * sizeof(cx<T>);
+    if (hk == 0) smem += (size_t)a.nbins * (sizeof(double) + sizeof(unsigned));
+    if (smem > 200 * 1024) { set_error("axis of length %d is too long for the generic pass", a.nx); return T21_EINVAL; }
+    const long long ntiles = (long long)a.ny * ((a.nzh + WZ - 1) / WZ);
+    long long g = ntiles < (long long)device_sm_count() * 4 ? ntiles : (long long)device_sm_count() * 4;
+    if (hk == 0 && g > a.max_grid) g = a.max_grid;
+    if (g < 1) g = 1;
+    t21_binspec dummy;
+    memset(&dummy, 0, sizeof(dummy));
+    const t21_binspec& B = is_bin ? *a.bins : dummy;
+#define T21_GEN_X(HKV)                                                                                          \
+    {                                                                                                           \
+        auto kern = gen_xpass_kernel<T, NF, HKV>;                                                               \
+        if (int rc = ensure_smem(kern, smem)) return rc;                                                        \
+        kern<<<(unsigned)g, kGenThreads, smem, st>>>((const cx<T>*)a.w[0], (const cx<T>*)a.w[1], a.nx, a.ny, a.nz,  \
+            a.nzh, a.pitch, a.xb, (const cx<T>*)a.tw, (const T*)a.offset[0], (const T*)a.offset[1], a.ntot, B,  \
+            a.nbins, a.part_sum, a.part_cnt, a.gsum, a.gcnt, a.nd_out, a.nd_f64, a.scale);                      \
+    }
+    if (hk == 0) T21_GEN_X(0) else if (hk == 1) T21_GEN_X(1) else T21_GEN_X(2)
+#undef T21_GEN_X
+    count_launch();
+    T21_CUDA_OK(cudaGetLastError());
+    a.grid_used = (int)g;
+    return 0;
+}
+int launch_xpass_generic(int dtype, XArgs& a, cudaStream_t st) {
+    if (dtype == T21_F32) return a.nf == 1 ? gen_x<float, 1>(a, st) : gen_x<float, 2>(a, st);
+    return a.nf == 1 ? gen_x<double, 1>(a, st) : gen_x<double, 2>(a, st);
+}
+
+}  // namespace t21

@@ -46,6 +46,11 @@ int launch_xpass_f32_nd(XArgs& a, cudaStream_t st);
 int launch_xpass_f64_bin(XArgs& a, cudaStream_t st);
 int launch_xpass_f64_nd(XArgs& a, cudaStream_t st);
 
+// t21_generic.cu: any-length direct-DFT versions (tw / twr hold the n-th roots of unity there)
+int launch_zpass_generic(int dtype, const ZArgs& a, cudaStream_t st);
+int launch_ypass_generic(int dtype, const YArgs& a, cudaStream_t st);
+int launch_xpass_generic(int dtype, XArgs& a, cudaStream_t st);
+
 // t21_aux.cu
 int launch_mean_estimate(int dtype, const void* x, long long n, void* offset_out, cudaStream_t st);
 int launch_reduce_partials(const double* part_sum, const unsigned* part_cnt, int nparts, int nbins,

@@ -186,9 +186,13 @@ def _fused_binned(fields, spec_key, spec_builder):
 
 def _fused_nd(fields, scale, out_dtype):
     torch = _torch()
+    shape_in = tuple(fields[0].shape)
+    if len(shape_in) > 3 or len(shape_in) < 1:
+        raise NotImplementedError("power spectra of %d-dimensional arrays are not supported" % len(shape_in))
+    if len(shape_in) < 3:       # 1-D / 2-D arrays are 3-D arrays with leading axes of length 1
+        fields = [f.reshape((1,) * (3 - len(shape_in)) + shape_in) for f in fields]
+        return _fused_nd(fields, scale, out_dtype).reshape(shape_in)
     x = fields[0]
-    if x.dim() != 3:
-        raise NotImplementedError("the fused estimator handles 3-dimensional cubes; got %d-D" % x.dim())
     dev = _device(x.device.index)
     with torch.cuda.device(x.device):
         lib = _lib.load()
@@ -405,6 +409,13 @@ def mu_binning(powerspectrum, los_axis=0, mubins=20, kbins=10, box_dims=None, we
 # ----------------------------------------------------------------------------------------
 def _shell_estimate(fields, kbins, box_dims, binning, breakpoint):
     shape = tuple(fields[0].shape)
+    if len(shape) < 3:
+        # 1-D / 2-D: the reference centres k at (n-1)/2 there (power_spectrum.py:458,463) while fftshift
+        # puts DC at n//2, so k(-f) != k(f) for even n and the half-spectrum shortcut does not apply.
+        # Do exactly what the reference does: full fftshifted power on the device, then radial_average.
+        torch = _torch()
+        nd = _fused_nd(fields, _bs.volume_scale(shape, box_dims), torch.float64)
+        return radial_average(nd, box_dims, kbins=kbins, binning=binning, breakpoint=breakpoint)
     key = ("1d", _freeze(list(box_dims)), _freeze(kbins), binning, breakpoint)
     spec, sums, counts = _fused_binned(fields, key, lambda: _bs.build_binspec(
         shape, box_dims, kbins, binning=binning, breakpoint=breakpoint))

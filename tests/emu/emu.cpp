@@ -67,6 +67,7 @@ static void xpass(const cx<T>* w0, const cx<T>* w1, int ny, int nz, int pitch, c
     p.ntiles = (long long)ny * p.nchunks;
     p.tile_step = nctas_emulated;
     p.xb = xb;
+    p.iy0 = 0;
     p.tw = tw.data();
     p.offset[0] = off0; p.offset[1] = off1;
     p.ntot = (double)NX * ny * nz;

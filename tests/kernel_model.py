@@ -45,12 +45,14 @@ def lut_cells_mu(spec, klos_f32, s_hat, twin_sign=1.0):
     return np.clip(np.floor(cf), 0, bs.MU_LUT_CELLS - 1).astype(np.int64)
 
 
-def bin_half_spectrum(power, spec, check_lut=True):
-    """power: float64 [nx, ny, nzh] on the FFT-order half grid.  Returns (sums, counts)."""
+def bin_half_spectrum(power, spec, check_lut=True, iy0=0):
+    """power: float64 [nx, ny_local, nzh] on the FFT-order half grid (rows iy0 .. iy0+ny_local of the
+    global cube; the whole cube by default).  Returns (sums, counts)."""
     nx, ny, nz = spec.shape
     nzh = nz // 2 + 1
-    assert power.shape == (nx, ny, nzh)
-    mx, my, mz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nzh), indexing="ij")
+    nyl = power.shape[1]
+    assert power.shape == (nx, nyl, nzh) and iy0 + nyl <= ny
+    mx, my, mz = np.meshgrid(np.arange(nx), np.arange(iy0, iy0 + nyl), np.arange(nzh), indexing="ij")
     s = (spec.tab_s[0][mx] + spec.tab_s[1][my]) + spec.tab_s[2][mz]
     kb = np.searchsorted(spec.thr, s, side="right") - 1
     k_ok = (kb >= 0) & (kb < spec.nk)

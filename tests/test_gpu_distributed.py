@@ -1,0 +1,115 @@
+"""GPU checks of the slab-sharded path.
+
+On one GPU the P ranks are emulated one after another in a single process (no NCCL, no kernels that
+wait on each other): stage 1 per x slab, the re-partition done by tensor indexing, stage 2 per y slab,
+results summed.  That exercises the CUDA stages and the global-row offset exactly as a P-rank run does.
+With >= 2 GPUs the real thing runs under NCCL (one process per GPU)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def emulate_ranks(cubes, world, kw_spec, mu=False):
+    import torch
+    from tools21cm_b200 import binspec as bs, distributed as D
+    from tools21cm_b200.power_spectrum import _freeze
+    be = D.CudaBackend()
+    shape = tuple(cubes[0].shape)
+    nx, ny, nz = shape
+    nxl, nyl = nx // world, ny // world
+    single = cubes[0].dtype == torch.float32
+    offs = [c.reshape(-1)[::7].double().mean().reshape(1).to(c.dtype) if single else None for c in cubes]
+    cols_all = []
+    for c, off in zip(cubes, offs):
+        w = [be.stage1(c[r * nxl:(r + 1) * nxl].contiguous(), off) for r in range(world)]   # [nxl][ny][pitch] each
+        full = torch.cat(w, dim=0)                                                            # [nx][ny][pitch]
+        cols_all.append([full[:, s * nyl:(s + 1) * nyl].contiguous() for s in range(world)])
+    sums = counts = None
+    box = kw_spec.pop("box")
+    for s in range(world):
+        spec, sm, ct = be.stage2([ca[s] for ca in cols_all], s * nyl, ny, nz, offs, ("emu", _freeze(box), mu, world),
+                                 lambda: bs.build_binspec(shape, box, **kw_spec))
+        sums = sm.clone() if sums is None else sums + sm
+        counts = ct.clone() if counts is None else counts + ct
+    with np.errstate(all="ignore"):
+        ps = sums.cpu().numpy() * bs.volume_scale(shape, box) / counts.cpu().numpy()
+    return spec, ps, counts.cpu().numpy().astype(float)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_slab_stages_emulated_on_one_gpu(world):
+    import torch
+    from oracle import ps_oracle
+    from tools21cm_b200 import synthetic
+    cube = synthetic.toy_dt_cube((64, 64, 32), seed=3)
+    box = [200.0, 200.0, 100.0]
+    spec, ps, nm = emulate_ranks([torch.from_numpy(cube).cuda()], world, dict(box=box, kbins=10))
+    ps_o, ks_o, nm_o = ps_oracle.power_spectrum_1d(cube, kbins=10, box_dims=box, return_n_modes=True)
+    assert np.array_equal(nm, nm_o) and np.array_equal(spec.k_centres(), ks_o)
+    np.testing.assert_allclose(ps, ps_o, rtol=1e-5, equal_nan=True)
+
+
+def test_slab_stages_cross_and_mu_fp64():
+    import torch
+    from oracle import ps_oracle
+    rng = np.random.default_rng(8)
+    a, b = rng.standard_normal((32, 32, 32)), rng.standard_normal((32, 32, 32))
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    spec, ps, nm = emulate_ranks([ta, tb], 4, dict(box=[90.0] * 3, kbins=8))
+    ps_o, _, nm_o = ps_oracle.cross_power_spectrum_1d(a, b, kbins=8, box_dims=90.0, return_n_modes=True)
+    assert np.array_equal(nm, nm_o)
+    np.testing.assert_allclose(ps, ps_o, rtol=1e-9, atol=1e-12 * np.nanmax(np.abs(ps_o)), equal_nan=True)
+    spec, ps, nm = emulate_ranks([ta], 2, dict(box=[90.0] * 3, kbins=5, mubins=4, los_axis=1, absolute_mus=False,
+                                               last_bin_closed=False), mu=True)
+    pm_o, _, _, nmm_o = ps_oracle.power_spectrum_mu(a, los_axis=1, mubins=4, kbins=5, box_dims=90.0,
+                                                    return_n_modes=True, absolute_mus=False)
+    assert np.array_equal(nm.reshape(nmm_o.shape), nmm_o)
+    np.testing.assert_allclose(ps.reshape(pm_o.shape), pm_o, rtol=1e-10, equal_nan=True)
+
+
+def _nccl_worker(rank, world, port, q):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")]
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from oracle import ps_oracle
+        from tools21cm_b200 import distributed as D, synthetic
+        cube = synthetic.toy_dt_cube((128, 64, 64), seed=21)
+        nxl = cube.shape[0] // world
+        slab = torch.from_numpy(cube[rank * nxl:(rank + 1) * nxl].copy()).cuda()
+        ps, ks, nm = D.sharded_power_spectrum_1d(slab, kbins=12, box_dims=[300.0, 150.0, 150.0], return_n_modes=True)
+        ps_o, ks_o, nm_o = ps_oracle.power_spectrum_1d(cube, kbins=12, box_dims=[300.0, 150.0, 150.0],
+                                                       return_n_modes=True)
+        ok = bool(np.array_equal(nm, nm_o) and np.array_equal(ks, ks_o) and
+                  np.allclose(ps, ps_o, rtol=1e-5, equal_nan=True))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_over_nccl():
+    import torch
+    import torch.multiprocessing as mp
+    world = torch.cuda.device_count()
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    world = 2 if world < 4 else 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 1000
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(res[r] for r in range(world))

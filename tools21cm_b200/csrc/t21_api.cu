@@ -182,7 +182,7 @@ int t21_plan_destroy(t21_plan* p) {
 }
 
 size_t t21_workspace_bytes(const t21_plan* p, int n_fields, int nbins) {
-    if (!p || n_fields < 1 || n_fields > 2 || nbins < 0) return 0;
+    if (!p || n_fields < 0 || n_fields > 2 || nbins < 0) return 0;
     return ws_layout(p, n_fields, nbins).total;
 }
 
@@ -319,6 +319,69 @@ int t21_profile_last(float* ms_out, int cap) {
         ms_out[g_prof.slot[i]] += ms;
     }
     return SLOT_COUNT;
+}
+
+// ---- one cube sharded over P GPUs as x slabs --------------------------------------
+// stage 1 (local):  Z and Y passes of this rank's x slab [nx/P][ny][nz] -> w_out [nx/P][ny][pitch]
+// exchange (caller): all-to-all over NCCL re-partitions the half spectrum into y slabs [nx][ny/P][pitch]
+// stage 2 (local):  X pass + binning of this rank's y slab; the caller all-reduces sums and counts.
+int t21_slab_pitch(const t21_plan* p) { return p ? p->pitch : 0; }
+
+int t21_slab_stage1(const t21_plan* p, const void* x_slab, const void* offset_or_null, void* w_out, void* stream) {
+    if (!p || !x_slab || !w_out) { set_error("null argument"); return T21_EINVAL; }
+    if (!(p->fast[1] && p->fast[2])) { set_error("slab mode needs power-of-two y and z axes"); return T21_EINVAL; }
+    if (((uintptr_t)x_slab & 15) || ((uintptr_t)w_out & 15)) { set_error("buffers must be 16-byte aligned"); return T21_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    prof_begin(st);
+    ZArgs z{x_slab, w_out, (long long)p->n[0] * p->n[1], p->n[2], p->pitch, p->n[1], 0, offset_or_null, p->tw[2], p->twr};
+    if (int rc = launch_zpass(p->dtype, z, st)) return rc;
+    prof_mark(st, SLOT_Z);
+    YArgs y{w_out, (long long)p->n[0], p->n[1], p->nzh, p->pitch, 0, p->tw[1]};
+    if (int rc = launch_ypass(p->dtype, y, st)) return rc;
+    prof_mark(st, SLOT_Y);
+    return T21_OK;
+}
+
+// p: plan of shape (nx, ny/P, nz); w1/w2: this rank's y slab(s) [nx][ny/P][pitch]; iy0: global index of
+// local row 0; spec: bin spec of the GLOBAL cube; offsets: the common mean offsets used in stage 1.
+int t21_slab_stage2(const t21_plan* p, const void* w1, const void* w2, int iy0, int ny_global, const void* offset1,
+                    const void* offset2, const t21_binspec* spec, double* sums_out, long long* counts_out,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+    if (!p || !w1 || !spec || !sums_out || !counts_out || !workspace) { set_error("null argument"); return T21_EINVAL; }
+    if (!p->fast[0]) { set_error("slab mode needs a power-of-two x axis"); return T21_EINVAL; }
+    if (spec->n[0] != p->n[0] || spec->n[2] != p->n[2] || spec->n[1] != ny_global || iy0 < 0 || iy0 + p->n[1] > ny_global) {
+        set_error("bin spec / slab geometry mismatch"); return T21_EINVAL;
+    }
+    const int nf = w2 ? 2 : 1;
+    const int nbins = spec->nk * (spec->nmu > 0 ? spec->nmu : 1);
+    WsLayout L = ws_layout(p, 0, nbins);
+    if (workspace_bytes < L.total) { set_error("workspace too small: %zu < %zu bytes", workspace_bytes, L.total); return T21_ENOMEM; }
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* ws = (unsigned char*)workspace;
+    XArgs a;
+    memset(&a, 0, sizeof(a));
+    a.w[0] = w1; a.w[1] = w2; a.nf = nf;
+    a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch; a.xb = 0; a.iy0 = iy0;
+    a.tw = p->tw[0];
+    a.offset[0] = offset1; a.offset[1] = offset2;
+    a.ntot = (double)p->n[0] * ny_global * p->n[2];
+    a.bins = spec; a.nbins = nbins;
+    a.hist_global = L.nbins_cap == 0;
+    a.part_sum = (double*)(ws + L.part_sum);
+    a.part_cnt = (unsigned*)(ws + L.part_cnt);
+    a.gsum = sums_out; a.gcnt = (unsigned long long*)counts_out;
+    a.max_grid = p->max_grid;
+    if (!g_prof.on || g_prof.n == 0) prof_begin(st);
+    if (a.hist_global)
+        if (int rc = launch_zero_hist(sums_out, counts_out, nbins, st)) return rc;
+    int rc = p->dtype == T21_F32 ? launch_xpass_f32_bin(a, st) : launch_xpass_f64_bin(a, st);
+    if (rc) return rc;
+    prof_mark(st, SLOT_X);
+    if (!a.hist_global) {
+        rc = launch_reduce_partials(a.part_sum, a.part_cnt, a.grid_used, nbins, sums_out, counts_out, st);
+        prof_mark(st, SLOT_REDUCE);
+    }
+    return rc;
 }
 
 size_t t21_bin_only_workspace_bytes(const t21_binspec* spec) {

@@ -27,7 +27,7 @@ struct YArgs {
     void* w; long long nouter; int ny; int nzh; int pitch; int xb; const void* tw;
 };
 struct XArgs {
-    const void* w[2]; int nf; int nx, ny, nz, nzh, pitch; int xb;
+    const void* w[2]; int nf; int nx, ny, nz, nzh, pitch; int xb; int iy0;
     const void* tw; const void* offset[2]; double ntot;
     const t21_binspec* bins;                 // MODE_BIN
     void* nd_out; int nd_f64; double scale;  // MODE_ND

@@ -123,7 +123,7 @@ inline int launch_x(XArgs& a, cudaStream_t st) {
     memset(&p, 0, sizeof(p));
     p.w[0] = (const cx<T>*)a.w[0];
     p.w[1] = (const cx<T>*)a.w[1];
-    p.ny = a.ny; p.nz = a.nz; p.nzh = a.nzh; p.pitch = a.pitch; p.xb = a.xb;
+    p.ny = a.ny; p.nz = a.nz; p.nzh = a.nzh; p.pitch = a.pitch; p.xb = a.xb; p.iy0 = a.iy0;
     constexpr int WZ = K::THREADS / K::S::TP;
     p.nchunks = (a.nzh + WZ - 1) / WZ;
     p.ntiles = (long long)a.ny * p.nchunks;

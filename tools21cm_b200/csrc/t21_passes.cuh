@@ -206,6 +206,7 @@ struct XPass {
         long long ntiles;     // ny * nchunks
         long long tile_step;  // tiles between two consecutive tiles of one CTA (the grid size)
         int xb;               // log2 of the x blocking factor
+        int iy0;              // global ky index of local row 0 (slab-sharded cubes; 0 otherwise)
         const cx<T>* tw;
         const T* offset[2];   // device scalars (mean offsets) or null
         double ntot;          // nx*ny*nz, for the analytic DC repair
@@ -228,7 +229,8 @@ struct XPass {
     static T21_HD void phase(const Params& p, long long tile, int tid, Regs& r, cx<T>* smem, Hist& hist) {
         const int zl = tid % WZ, j = tid / WZ;
         const int chunk = (int)(tile % p.nchunks);
-        const int iy = (int)(tile / p.nchunks);
+        const int iy_loc = (int)(tile / p.nchunks);        // row inside this rank's y slab (addressing)
+        const int iy = iy_loc + p.iy0;                     // global ky index (tables, DC, exclusions)
         const int iz = chunk * WZ + zl;
         const bool active = iz < p.nzh;
         if constexpr (PH < NF * S::FFT_PHASES) {
@@ -237,7 +239,7 @@ struct XPass {
             // element i (= x) lives in row ((i / XB) * ny + iy) * XB + i % XB
             const cx<T>* base = p.w[F] + (active ? iz : 0);
             const long long gstride = ((long long)p.ny * p.pitch) << p.xb;     // between x groups
-            const long long ybase = ((long long)iy * p.pitch) << p.xb;
+            const long long ybase = ((long long)iy_loc * p.pitch) << p.xb;
             const int xmask = (1 << p.xb) - 1;
             S::template fft_phase<FPH>(
                 r.v[F], j, zl, p.tw, smem,

@@ -1,0 +1,239 @@
+"""Multi-GPU forms of the estimators (one process per GPU, ``torch.distributed``).
+
+The reference has no distributed path; two partitions of its power-spectrum
+path exist and both are here:
+
+* **Batches of independent cubes** (coeval boxes at many redshifts, light-cone chunks): cube i goes
+  to rank i mod P, no data-path collective, results gathered at the end -- ``batched``.
+* **One cube too large or too slow for one GPU**, sharded as x slabs: every rank transforms its
+  slab along z and y (``t21_slab_stage1``), ONE all-to-all re-partitions the half spectrum into y
+  slabs with x complete, every rank transforms along x fused with the binning (``t21_slab_stage2``),
+  and a tiny all-reduce sums the per-bin sums and counts -- ``sharded_power_spectrum_1d``,
+  ``sharded_cross_power_spectrum_1d``, ``sharded_power_spectrum_mu``.
+
+The exchange is ``all_to_all_single`` over NCCL (NVLink 5 / NVSwitch on the 8xB200 box): rank r
+sends rank s the block W[x in slab r, y in slab s, :], packed so that the receive buffer *is* the
+[nx][ny/P][pitch] array stage 2 reads (no unpack pass).
+
+``backend`` lets the CPU tests (gloo, world_size 2) replace the two CUDA stages by a numpy model
+while exercising exactly this partitioning, packing, offset and reduction code.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from . import binspec as _bs
+
+
+def partition(n_items, world, rank):
+    """Indices of the items rank ``rank`` owns: item i -> rank i mod world."""
+    return list(range(rank, n_items, world))
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def _world(group=None):
+    dist = _dist()
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def batched(fn, items, group=None):
+    """Run ``fn(item)`` for this rank's share of ``items`` and return every result, in item order,
+    on every rank.  ``fn`` is one of the single-GPU estimators (closed over its keyword arguments)."""
+    world, rank = _world(group)
+    mine = [(i, fn(items[i])) for i in partition(len(items), world, rank)]
+    if world == 1:
+        return [r for _, r in mine]
+    gathered = [None] * world
+    _dist().all_gather_object(gathered, mine, group=group)
+    out = [None] * len(items)
+    for part in gathered:
+        for i, r in part:
+            out[i] = r
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# backends: the two local stages
+# ------------------------------------------------------------------------------------------
+class CudaBackend:
+    """Stages run by libt21ps.so on the current CUDA device."""
+
+    def __init__(self):
+        from . import power_spectrum as _ps
+        self._ps = _ps
+
+    def mean_estimate(self, x):
+        flat = x.reshape(-1)
+        step = max(1, flat.numel() // 65536) | 1
+        return flat[::step].double().mean()
+
+    def pitch(self, nz):
+        return (nz // 2 + 1 + 15) // 16 * 16
+
+    def stage1(self, x, offset):
+        import torch
+        lib = _lib.load()
+        dev = self._ps._device(x.device.index)
+        code = self._ps._dtype_code(x)
+        plan = dev.plan(tuple(x.shape), code)
+        pitch = lib.t21_slab_pitch(plan)
+        cdt = torch.complex64 if x.dtype == torch.float32 else torch.complex128
+        w = torch.empty((x.shape[0], x.shape[1], pitch), dtype=cdt, device=x.device)
+        rc = lib.t21_slab_stage1(plan, x.data_ptr(), offset.data_ptr() if offset is not None else None,
+                                 w.data_ptr(), self._ps._stream_ptr(torch, x.device.index))
+        _lib.check(rc, "t21_slab_stage1")
+        return w
+
+    def stage2(self, cols, iy0, ny_global, nz, offsets, spec_key, spec_builder):
+        import torch
+        lib = _lib.load()
+        w = cols[0]
+        dev = self._ps._device(w.device.index)
+        code = _lib.T21_F32 if w.dtype == torch.complex64 else _lib.T21_F64
+        nx, nyl = w.shape[0], w.shape[1]
+        plan = dev.plan((nx, nyl, nz), code)
+        spec, cspec, _own = dev.spec(((nx, ny_global, nz), spec_key), spec_builder)
+        nb = spec.nbins
+        need = lib.t21_workspace_bytes(plan, 0, nb)
+        ws = dev.workspace(need)
+        sums = torch.empty(nb, dtype=torch.float64, device=w.device)
+        counts = torch.empty(nb, dtype=torch.int64, device=w.device)
+        o = [t.data_ptr() if t is not None else None for t in offsets] + [None]
+        rc = lib.t21_slab_stage2(plan, cols[0].data_ptr(), cols[1].data_ptr() if len(cols) == 2 else None,
+                                 int(iy0), int(ny_global), o[0], o[1], C.byref(cspec), sums.data_ptr(),
+                                 counts.data_ptr(), ws.data_ptr(), ws.numel(),
+                                 self._ps._stream_ptr(torch, w.device.index))
+        _lib.check(rc, "t21_slab_stage2")
+        return spec, sums, counts
+
+
+# ------------------------------------------------------------------------------------------
+# the sharded estimator
+# ------------------------------------------------------------------------------------------
+def exchange(w_slab, world, group=None):
+    """[nx/P][ny][pitch] on every rank  ->  [nx][ny/P][pitch] on every rank (one all-to-all)."""
+    nxl, ny, pitch = w_slab.shape
+    if ny % world:
+        raise ValueError("the y axis (%d) must be divisible by the number of ranks (%d)" % (ny, world))
+    nyl = ny // world
+    if world == 1:
+        return w_slab
+    import torch
+    send = w_slab.view(nxl, world, nyl, pitch).permute(1, 0, 2, 3).contiguous()   # [P][nx/P][ny/P][pitch]
+    recv = send.new_empty((world, nxl, nyl, pitch))
+    # complex tensors travel as (re, im) pairs of their real dtype
+    _dist().all_to_all_single(torch.view_as_real(recv).view(-1), torch.view_as_real(send).view(-1), group=group)
+    return recv.view(world * nxl, nyl, pitch)
+
+
+def _sharded_binned(slabs, spec_key, make_spec, group=None, backend=None, timings=None):
+    import torch
+    world, rank = _world(group)
+    backend = backend or CudaBackend()
+    x0 = slabs[0]
+    nxl, ny, nz = x0.shape
+    shape = (nxl * world, ny, nz)
+    if ny % world:
+        raise ValueError("the y axis (%d) must be divisible by the number of ranks (%d)" % (ny, world))
+    nyl = ny // world
+    single = x0.dtype == torch.float32
+    offsets = []
+    for x in slabs:
+        if single:
+            # the SAME offset on every rank: per-slab offsets would not be a pure DC change
+            m = backend.mean_estimate(x).reshape(1).to(torch.float64)
+            if world > 1:
+                _dist().all_reduce(m, group=group)
+                m = m / world
+            offsets.append(m.to(x.dtype))
+        else:
+            offsets.append(None)
+    cols = []
+    for x, off in zip(slabs, offsets):
+        w = backend.stage1(x, off)
+        if timings is not None and x.is_cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            c = exchange(w, world, group)
+            e1.record()
+            timings.setdefault("a2a_events", []).append((e0, e1))
+        else:
+            c = exchange(w, world, group)
+        cols.append(c)
+    spec, sums, counts = backend.stage2(cols, rank * nyl, ny, nz, offsets, spec_key, lambda: make_spec(shape))
+    if world > 1:
+        _dist().all_reduce(sums, group=group)
+        _dist().all_reduce(counts, group=group)
+    return spec, shape, sums.cpu().numpy(), counts.cpu().numpy().astype("float")
+
+
+def _finish(sums, counts, scale):
+    with np.errstate(all="ignore"):
+        return sums * scale / counts
+
+
+def sharded_power_spectrum_1d(x_slab, kbins=100, box_dims=None, return_n_modes=False, binning="log",
+                              breakpoint=0.1, group=None, backend=None, timings=None, **kwargs):
+    """``power_spectrum_1d`` of a cube held as x slabs: ``x_slab`` is this rank's [nx/P, ny, nz] part
+    (rank r owns x in [r nx/P, (r+1) nx/P)).  Same return tuple as the single-GPU function, on every rank."""
+    return _sharded_1d([x_slab], kbins, box_dims, return_n_modes, binning, breakpoint, group, backend, timings,
+                       kwargs)
+
+
+def sharded_cross_power_spectrum_1d(a_slab, b_slab, kbins=100, box_dims=None, return_n_modes=False,
+                                    binning="log", breakpoint=0.1, group=None, backend=None, timings=None, **kwargs):
+    assert tuple(a_slab.shape) == tuple(b_slab.shape)
+    return _sharded_1d([a_slab, b_slab], kbins, box_dims, return_n_modes, binning, breakpoint, group, backend,
+                       timings, kwargs)
+
+
+def _sharded_1d(slabs, kbins, box_dims, return_n_modes, binning, breakpoint, group, backend, timings, kwargs):
+    if kwargs.get("boxsize") is not None:
+        box_dims = kwargs.get("boxsize")
+    world, _ = _world(group)
+    gshape = (slabs[0].shape[0] * world,) + tuple(slabs[0].shape[1:])
+    box_dims = _bs.get_dims(box_dims, gshape)
+    from .power_spectrum import _freeze
+    key = ("1d", _freeze(list(box_dims)), _freeze(kbins), binning, breakpoint)
+    spec, shape, sums, counts = _sharded_binned(
+        slabs, key, lambda shp: _bs.build_binspec(shp, box_dims, kbins, binning=binning, breakpoint=breakpoint),
+        group, backend, timings)
+    ps = _finish(sums, counts, _bs.volume_scale(shape, box_dims))
+    if return_n_modes:
+        return ps, spec.k_centres(), counts
+    return ps, spec.k_centres()
+
+
+def sharded_power_spectrum_mu(x_slab, los_axis=0, mubins=20, kbins=10, box_dims=None, weights=None,
+                              exclude_zero_modes=True, return_n_modes=False, absolute_mus=True, group=None,
+                              backend=None, timings=None, **kwargs):
+    """``power_spectrum_mu`` of a cube held as x slabs."""
+    if weights is not None:
+        raise ValueError("weights are not usable in the reference either (power_spectrum.py:386,433)")
+    if kwargs.get("boxsize") is not None:
+        box_dims = kwargs.get("boxsize")
+    world, _ = _world(group)
+    gshape = (x_slab.shape[0] * world,) + tuple(x_slab.shape[1:])
+    box_dims = _bs.get_dims(box_dims, gshape)
+    from .power_spectrum import _freeze
+    key = ("mu", _freeze(list(box_dims)), _freeze(kbins), _freeze(mubins), los_axis, bool(absolute_mus),
+           bool(exclude_zero_modes))
+    spec, shape, sums, counts = _sharded_binned(
+        [x_slab], key, lambda shp: _bs.build_binspec(
+            shp, box_dims, kbins, binning="log", mubins=mubins, los_axis=los_axis, absolute_mus=absolute_mus,
+            exclude_zero_modes=exclude_zero_modes, last_bin_closed=False), group, backend, timings)
+    nmu, nk = spec.nmu, spec.nk
+    ps = _finish(sums, counts, _bs.volume_scale(shape, box_dims)).reshape(nmu, nk)
+    counts = counts.reshape(nmu, nk)
+    if return_n_modes:
+        return ps, spec.mu_centres(), spec.k_centres(), counts
+    return ps, spec.mu_centres(), spec.k_centres()

@@ -116,13 +116,15 @@ T21_API int t21_ps_nd(const t21_plan* plan, const void* x1, const void* x2_or_nu
  * distributed path, this replaces the single-process fftn of power_spectrum.py:45,85-86 when the
  * cube is spread over ranks).  stage1: Z and Y passes of this rank's slab [nx/P][ny][nz] into
  * w_out [nx/P][ny][pitch] (pitch from t21_slab_pitch; offset = device scalar subtracted from every
- * sample, the SAME value on every rank, or NULL).  The caller re-partitions the half spectrum into
+ * sample, the SAME value on every rank, or NULL).  With send_out != NULL the Y pass stores straight
+ * into the packed all-to-all send buffer [nranks][nx/P][ny/nranks][pitch] (w_out is then scratch), so
+ * the re-partition needs no separate pack pass.  The caller re-partitions the half spectrum into
  * y slabs [nx][ny/P][pitch] with an NCCL all-to-all, then stage2 (plan of shape (nx, ny/P, nz)) runs
  * the X pass fused with the binning for rows iy0 .. iy0+ny/P of the global cube; the caller
  * all-reduces sums_out / counts_out.  t21_workspace_bytes(plan, 0, nbins) sizes stage2's workspace. */
 T21_API int t21_slab_pitch(const t21_plan* plan);
 T21_API int t21_slab_stage1(const t21_plan* plan_slab, const void* x_slab, const void* offset_or_null,
-                            void* w_out, void* stream);
+                            void* w_out, void* send_out_or_null, int nranks, void* stream);
 T21_API int t21_slab_stage2(const t21_plan* plan_cols, const void* w1, const void* w2_or_null, int iy0,
                             int ny_global, const void* offset1, const void* offset2,
                             const t21_binspec* spec, double* sums_out, long long* counts_out,

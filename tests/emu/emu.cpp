@@ -46,7 +46,7 @@ static void ypass(cx<T>* w, long long nouter, int nzh, int pitch, int xb) {
     using K = YPass<NY, T, WZ>;
     auto tw = build_stage_twiddles<T>(NY);
     int nchunks = (nzh + WZ - 1) / WZ;
-    typename K::Params p{w, nzh, pitch, nchunks, xb, tw.data()};
+    typename K::Params p{w, nzh, pitch, nchunks, xb, tw.data(), nullptr, 0, nouter};
     std::vector<cx<T>> smem(K::SMEM_BYTES / sizeof(cx<T>) + 1);
     for (long long cta = 0; cta < nouter * nchunks; ++cta) {
         std::vector<typename K::Regs> regs(K::THREADS);

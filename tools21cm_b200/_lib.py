@@ -141,7 +141,7 @@ def load():
     lib.t21_ps_nd.restype = i32
     lib.t21_slab_pitch.argtypes = [vp]
     lib.t21_slab_pitch.restype = i32
-    lib.t21_slab_stage1.argtypes = [vp, vp, vp, vp, vp]
+    lib.t21_slab_stage1.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     lib.t21_slab_stage1.restype = i32
     lib.t21_slab_stage2.argtypes = [vp, vp, vp, i32, i32, vp, vp, C.POINTER(BinSpecC), vp, vp, vp, sz, vp]
     lib.t21_slab_stage2.restype = i32

@@ -204,7 +204,7 @@ static int forward_zy(const t21_plan* p, const void* const x[2], int nf, int sub
         ZArgs z{x[f], ws + L.w[f], (long long)p->n[0] * p->n[1], p->n[2], p->pitch, p->n[1], p->xb, offs[f], p->tw[2], p->twr};
         if (int rc = p->fast[2] ? launch_zpass(p->dtype, z, st) : launch_zpass_generic(p->dtype, z, st)) return rc;
         prof_mark(st, SLOT_Z);
-        YArgs y{ws + L.w[f], (long long)p->n[0], p->n[1], p->nzh, p->pitch, p->xb, p->tw[1]};
+        YArgs y{ws + L.w[f], (long long)p->n[0], p->n[1], p->nzh, p->pitch, p->xb, p->tw[1], nullptr, 0};
         if (int rc = p->fast[1] ? launch_ypass(p->dtype, y, st) : launch_ypass_generic(p->dtype, y, st)) return rc;
         prof_mark(st, SLOT_Y);
     }
@@ -327,16 +327,26 @@ int t21_profile_last(float* ms_out, int cap) {
 // stage 2 (local):  X pass + binning of this rank's y slab; the caller all-reduces sums and counts.
 int t21_slab_pitch(const t21_plan* p) { return p ? p->pitch : 0; }
 
-int t21_slab_stage1(const t21_plan* p, const void* x_slab, const void* offset_or_null, void* w_out, void* stream) {
+int t21_slab_stage1(const t21_plan* p, const void* x_slab, const void* offset_or_null, void* w_out, void* send_out,
+                    int nranks, void* stream) {
     if (!p || !x_slab || !w_out) { set_error("null argument"); return T21_EINVAL; }
     if (!(p->fast[1] && p->fast[2])) { set_error("slab mode needs power-of-two y and z axes"); return T21_EINVAL; }
-    if (((uintptr_t)x_slab & 15) || ((uintptr_t)w_out & 15)) { set_error("buffers must be 16-byte aligned"); return T21_EINVAL; }
+    if (((uintptr_t)x_slab & 15) || ((uintptr_t)w_out & 15) || ((uintptr_t)send_out & 15)) {
+        set_error("buffers must be 16-byte aligned"); return T21_EINVAL;
+    }
+    int nyl_log2 = 0;
+    if (send_out) {
+        if (nranks < 1 || (nranks & (nranks - 1)) || p->n[1] % nranks) {
+            set_error("rank count %d must be a power of two dividing ny = %d", nranks, p->n[1]); return T21_EINVAL;
+        }
+        while ((p->n[1] / nranks) >> (nyl_log2 + 1)) ++nyl_log2;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     prof_begin(st);
     ZArgs z{x_slab, w_out, (long long)p->n[0] * p->n[1], p->n[2], p->pitch, p->n[1], 0, offset_or_null, p->tw[2], p->twr};
     if (int rc = launch_zpass(p->dtype, z, st)) return rc;
     prof_mark(st, SLOT_Z);
-    YArgs y{w_out, (long long)p->n[0], p->n[1], p->nzh, p->pitch, 0, p->tw[1]};
+    YArgs y{w_out, (long long)p->n[0], p->n[1], p->nzh, p->pitch, 0, p->tw[1], send_out, nyl_log2};
     if (int rc = launch_ypass(p->dtype, y, st)) return rc;
     prof_mark(st, SLOT_Y);
     return T21_OK;

@@ -25,6 +25,7 @@ struct ZArgs {
 };
 struct YArgs {
     void* w; long long nouter; int ny; int nzh; int pitch; int xb; const void* tw;
+    void* send; int nyl_log2;          // slab mode: packed all-to-all send buffer (or null)
 };
 struct XArgs {
     const void* w[2]; int nf; int nx, ny, nz, nzh, pitch; int xb; int iy0;

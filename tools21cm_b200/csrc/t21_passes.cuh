@@ -147,6 +147,11 @@ struct YPass {
         int nchunks;          // ceil(nzh / WZ)
         int xb;               // log2 of the x blocking factor
         const cx<T>* tw;
+        // slab-sharded cubes: write the result straight into the all-to-all send buffer
+        // [P][nouter][NY/P][pitch] instead of in place (pack fused into the store); null otherwise
+        cx<T>* send;
+        int nyl_log2;         // log2(NY / P)
+        long long nouter;     // x planes in this slab
     };
     struct Regs {
         cx<T> v[S::E];
@@ -166,7 +171,17 @@ struct YPass {
         S::template fft_phase<PH>(
             r.v, j, zl, p.tw, smem,
             [&](int i) { return active ? base[i * stride] : cmake<T>(0, 0); },
-            [&](int i, cx<T> val, int) { if (active) base[i * stride] = val; });
+            [&](int i, cx<T> val, int) {
+                if (!active) return;
+                if (p.send) {
+                    // destination rank i >> nyl_log2 gets row (x, i mod NY/P) of its y slab
+                    const long long row = (((long long)(i >> p.nyl_log2) * p.nouter + outer) << p.nyl_log2) +
+                                          (i & ((1 << p.nyl_log2) - 1));
+                    p.send[row * p.pitch + z] = val;
+                } else {
+                    base[i * stride] = val;
+                }
+            });
     }
 };
 

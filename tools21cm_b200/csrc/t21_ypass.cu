@@ -11,7 +11,8 @@ static int launch_ypass_t(const YArgs& a, cudaStream_t st) {
         constexpr int WZ = WZFor<T, N>::value;                                           \
         using K = YPass<N, T, WZ>;                                                       \
         const int nchunks = (a.nzh + WZ - 1) / WZ;                                       \
-        typename K::Params p{(cx<T>*)a.w, a.nzh, a.pitch, nchunks, a.xb, (const cx<T>*)a.tw};  \
+        typename K::Params p{(cx<T>*)a.w, a.nzh, a.pitch, nchunks, a.xb, (const cx<T>*)a.tw,      \
+                             (cx<T>*)a.send, a.nyl_log2, a.nouter};                        \
         return launch_tiles<K, T>(p, a.nouter * nchunks, st);                            \
     }
     T21_FOR_FAST_N(a.ny, YCASE)

@@ -79,7 +79,9 @@ class CudaBackend:
     def pitch(self, nz):
         return (nz // 2 + 1 + 15) // 16 * 16
 
-    def stage1(self, x, offset):
+    def stage1(self, x, offset, send_world=0):
+        """Z and Y passes of an x slab.  send_world = 0: returns W [nxl][ny][pitch].  send_world = P:
+        returns the packed all-to-all send buffer [P][nxl][ny/P][pitch] (pack fused into the Y pass)."""
         import torch
         lib = _lib.load()
         dev = self._ps._device(x.device.index)
@@ -88,10 +90,14 @@ class CudaBackend:
         pitch = lib.t21_slab_pitch(plan)
         cdt = torch.complex64 if x.dtype == torch.float32 else torch.complex128
         w = torch.empty((x.shape[0], x.shape[1], pitch), dtype=cdt, device=x.device)
+        send = None
+        if send_world:
+            send = torch.empty((send_world, x.shape[0], x.shape[1] // send_world, pitch), dtype=cdt, device=x.device)
         rc = lib.t21_slab_stage1(plan, x.data_ptr(), offset.data_ptr() if offset is not None else None,
-                                 w.data_ptr(), self._ps._stream_ptr(torch, x.device.index))
+                                 w.data_ptr(), send.data_ptr() if send is not None else None, int(send_world),
+                                 self._ps._stream_ptr(torch, x.device.index))
         _lib.check(rc, "t21_slab_stage1")
-        return w
+        return send if send is not None else w
 
     def stage2(self, cols, iy0, ny_global, nz, offsets, spec_key, spec_builder):
         import torch
@@ -120,19 +126,50 @@ class CudaBackend:
 # the sharded estimator
 # ------------------------------------------------------------------------------------------
 def exchange(w_slab, world, group=None):
-    """[nx/P][ny][pitch] on every rank  ->  [nx][ny/P][pitch] on every rank (one all-to-all)."""
+    """[nx/P][ny][pitch] on every rank  ->  [nx][ny/P][pitch] on every rank (pack + one all-to-all).
+    Generic form used by backends without a fused pack (the CPU model)."""
     nxl, ny, pitch = w_slab.shape
     if ny % world:
         raise ValueError("the y axis (%d) must be divisible by the number of ranks (%d)" % (ny, world))
     nyl = ny // world
     if world == 1:
         return w_slab
-    import torch
     send = w_slab.view(nxl, world, nyl, pitch).permute(1, 0, 2, 3).contiguous()   # [P][nx/P][ny/P][pitch]
-    recv = send.new_empty((world, nxl, nyl, pitch))
-    # complex tensors travel as (re, im) pairs of their real dtype
+    return all_to_all_packed(send, group).view(world * nxl, nyl, pitch)
+
+
+def all_to_all_packed(send, group=None):
+    """send [P][nxl][nyl][pitch] (block s goes to rank s) -> recv [P][nxl][nyl][pitch] (block s came from
+    rank s), i.e. the [nx][nyl][pitch] y slab.  Complex tensors travel as (re, im) pairs."""
+    import torch
+    recv = torch.empty_like(send)
     _dist().all_to_all_single(torch.view_as_real(recv).view(-1), torch.view_as_real(send).view(-1), group=group)
-    return recv.view(world * nxl, nyl, pitch)
+    return recv
+
+
+def pipelined_exchange(backend, x, offset, world, group=None, chunks=4):
+    """Stage 1 and the re-partition of one field, overlapped: the slab is cut into `chunks` pieces along
+    x; while NCCL moves piece c over NVLink, the Z and Y passes of piece c+1 run.  Returns the y slab
+    [nx][ny/P][pitch] once every piece has arrived."""
+    import torch
+    nxl, ny, _nz = x.shape
+    nyl = ny // world
+    while chunks > 1 and (nxl % chunks or nxl // chunks < 4):
+        chunks //= 2
+    nc = nxl // chunks
+    recv4 = None
+    works, keep = [], []
+    for c in range(chunks):
+        send = backend.stage1(x[c * nc:(c + 1) * nc], offset, send_world=world)     # [P][nc][nyl][pitch]
+        if recv4 is None:
+            recv4 = send.new_empty((world, nxl, nyl, send.shape[3]))
+        outs = [torch.view_as_real(recv4[s, c * nc:(c + 1) * nc]) for s in range(world)]
+        ins = [torch.view_as_real(send[s]) for s in range(world)]
+        works.append(_dist().all_to_all(outs, ins, group=group, async_op=True))
+        keep.append(send)
+    for w in works:
+        w.wait()
+    return recv4.view(world * nxl, nyl, recv4.shape[3])
 
 
 def _sharded_binned(slabs, spec_key, make_spec, group=None, backend=None, timings=None):
@@ -158,17 +195,12 @@ def _sharded_binned(slabs, spec_key, make_spec, group=None, backend=None, timing
         else:
             offsets.append(None)
     cols = []
+    fused = world > 1 and isinstance(backend, CudaBackend)
     for x, off in zip(slabs, offsets):
-        w = backend.stage1(x, off)
-        if timings is not None and x.is_cuda:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            c = exchange(w, world, group)
-            e1.record()
-            timings.setdefault("a2a_events", []).append((e0, e1))
+        if fused:
+            cols.append(pipelined_exchange(backend, x, off, world, group))
         else:
-            c = exchange(w, world, group)
-        cols.append(c)
+            cols.append(exchange(backend.stage1(x, off), world, group))
     spec, sums, counts = backend.stage2(cols, rank * nyl, ny, nz, offsets, spec_key, lambda: make_spec(shape))
     if world > 1:
         _dist().all_reduce(sums, group=group)

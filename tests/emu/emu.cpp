@@ -110,7 +110,7 @@ static int emu_all(int nx, int ny, int nz, const T* in0, const T* in1, double of
     const int pitch = round_up(nzh, 16);
     const int nf = in1 ? 2 : 1;
     int xb = 2;                                   // same rule as t21_plan_create
-    while (xb > 0 && ((nx % (1 << xb)) != 0 || (1 << xb) > nx / 2)) --xb;
+    while (xb > 0 && ((nx % (1 << xb)) != 0 || (1 << xb) > nx / 16)) --xb;
     std::vector<cx<T>> w[2];
     T offs[2] = {(T)off0d, (T)off1d};
     const T* ins[2] = {in0, in1};

@@ -162,7 +162,7 @@ int t21_plan_create(t21_plan** out, int nx, int ny, int nz, int dtype, int devic
     {
         int xb = 2;
         if (const char* e = getenv("T21_XB")) xb = atoi(e);
-        while (xb > 0 && ((nx % (1 << xb)) != 0 || (1 << xb) > 16 || (1 << xb) > nx / 2)) --xb;
+        while (xb > 0 && ((nx % (1 << xb)) != 0 || (1 << xb) > 16 || (1 << xb) > nx / 16)) --xb;
         if (!p->fast[0] || !p->fast[1]) xb = 0;
         p->xb = xb < 0 ? 0 : xb;
     }

@@ -140,6 +140,24 @@ inline int plan_tw_total(int n) {
     return tot;
 }
 
+// Walks the rows a thread touches in one stage, in the order the unrolled loops visit them
+// (butterflies b outer, points k inner), with two 64-bit adds per access instead of an index
+// multiply: element (b, k) sits at p0 + b*step_b' + k*step_k.
+template <typename T>
+struct RowCursor {
+    T* p;
+    long long step_k;     // between consecutive points of one butterfly
+    long long step_wrap;  // from the last point of butterfly b to the first point of butterfly b+1
+    int k, radix;
+    T21_HD RowCursor(T* p0, long long sk, long long sb, int r)
+        : p(p0), step_k(sk), step_wrap(sb - (long long)(r - 1) * sk), k(0), radix(r) {}
+    T21_HD T* next() {
+        T* cur = p;
+        if (++k == radix) { k = 0; p += step_wrap; } else { p += step_k; }
+        return cur;
+    }
+};
+
 // ---- one stage, split into its load and its compute+store halves -------------------
 // ld(i) returns element i of this thread's pencil; st(i, v, slot) stores element i, which
 // lives in register slot `slot` (a compile-time constant after unrolling).

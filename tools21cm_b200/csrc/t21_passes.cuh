@@ -133,7 +133,10 @@ struct Strided {
 // ======================================================================================
 // Y pass (in place)
 // ======================================================================================
-template <int NY, typename T, int WZ>
+// SEND: store into the packed all-to-all send buffer of a slab-sharded cube instead of in place.
+// Columns past nz/2 inside the last chunk are scratch (pitch >= nchunks*WZ): they are transformed
+// like the rest and ignored by the X-pass epilogue, so no access here needs a bounds predicate.
+template <int NY, typename T, int WZ, bool SEND = false>
 struct YPass {
     using S = Strided<NY, T, WZ>;
     static constexpr int THREADS = S::THREADS;
@@ -163,23 +166,31 @@ struct YPass {
         const int chunk = (int)(cta % p.nchunks);
         const long long outer = cta / p.nchunks;
         const int z = chunk * WZ + zl;
-        const bool active = z < p.nzh;
         // outer = x: rows of this pencil are ((x / XB) * NY + y) * XB + x % XB
         const long long row0 = (((outer >> p.xb) * NY) << p.xb) + (outer & ((1 << p.xb) - 1));
-        cx<T>* base = p.w + row0 * p.pitch + (active ? z : 0);
+        cx<T>* base = p.w + row0 * p.pitch + z;
         const long long stride = (long long)p.pitch << p.xb;
+        using P = Plan<NY>;
+        // rows are visited in loop order, so both the first-stage loads and the last-stage stores walk
+        // a cursor instead of multiplying an index by the run-time row stride
+        constexpr int R0 = P::radix(0), RL = P::radix(P::NS - 1), NSL = P::ns(P::NS - 1);
+        RowCursor<cx<T>> lc(base + (long long)j * stride, (long long)(NY / R0) * stride, (long long)P::T * stride, R0);
+        RowCursor<cx<T>> sc(base + (long long)j * stride, (long long)NSL * stride, (long long)P::T * stride, RL);
         S::template fft_phase<PH>(
             r.v, j, zl, p.tw, smem,
-            [&](int i) { return active ? base[i * stride] : cmake<T>(0, 0); },
+#ifdef T21_DBG_NOLOAD
+            [&](int i) { return cmake<T>((T)i, (T)zl); },
+#else
+            [&](int) { return *lc.next(); },
+#endif
             [&](int i, cx<T> val, int) {
-                if (!active) return;
-                if (p.send) {
+                if constexpr (SEND) {
                     // destination rank i >> nyl_log2 gets row (x, i mod NY/P) of its y slab
                     const long long row = (((long long)(i >> p.nyl_log2) * p.nouter + outer) << p.nyl_log2) +
                                           (i & ((1 << p.nyl_log2) - 1));
                     p.send[row * p.pitch + z] = val;
                 } else {
-                    base[i * stride] = val;
+                    *sc.next() = val;
                 }
             });
     }
@@ -252,15 +263,24 @@ struct XPass {
             constexpr int F = PH / S::FFT_PHASES;          // field this phase works on
             constexpr int FPH = PH % S::FFT_PHASES;
             // element i (= x) lives in row ((i / XB) * ny + iy) * XB + i % XB
-            const cx<T>* base = p.w[F] + (active ? iz : 0);
+            const cx<T>* base = p.w[F] + iz;     // scratch columns of the last chunk are read too (in bounds)
             const long long gstride = ((long long)p.ny * p.pitch) << p.xb;     // between x groups
             const long long ybase = ((long long)iy_loc * p.pitch) << p.xb;
             const int xmask = (1 << p.xb) - 1;
+            // first-stage rows in loop order: row(i) is linear in (b, k) because the point stride and the
+            // thread count of a pencil are multiples of XB (t21_plan_create keeps XB <= NX/16)
+            constexpr int R0 = P::radix(0);
+            const cx<T>* row_j = base + (long long)(j >> p.xb) * gstride + ybase + (long long)(j & xmask) * p.pitch;
+            RowCursor<const cx<T>> lc(row_j, (long long)((NX / R0) >> p.xb) * gstride,
+                                      (long long)(P::T >> p.xb) * gstride, R0);
             S::template fft_phase<FPH>(
                 r.v[F], j, zl, p.tw, smem,
                 [&](int i) {
-                    return active ? base[(i >> p.xb) * gstride + ybase + (long long)(i & xmask) * p.pitch]
-                                  : cmake<T>(0, 0);
+#ifdef T21_DBG_NOLOAD
+                    return cmake<T>((T)i, (T)zl);
+#else
+                    return *lc.next();
+#endif
                 },
                 [&](int i, cx<T> b, int slot) {
                     // last stage of field F: element i (= kx) is final and sits in register `slot`.

@@ -53,11 +53,11 @@ static void ypass(cx<T>* w, long long nouter, int nzh, int pitch, int xb) {
         run_simple<K, T>(p, cta, regs, smem.data());
     }
 }
-template <int NX, typename T, int WZ, int NF, int MODE>
-static void xpass(const cx<T>* w0, const cx<T>* w1, int ny, int nz, int pitch, const T* off0, const T* off1,
+template <int NX, typename T, int WZ, int NF, int MODE, int MU>
+static void xpass_mu(const cx<T>* w0, const cx<T>* w1, int ny, int nz, int pitch, const T* off0, const T* off1,
                   const t21_binspec* spec, double* sums, long long* counts, void* nd_out, int nd_f64, double scale,
                   int nctas_emulated, int xb) {
-    using K = XPass<NX, T, WZ, NF, MODE>;
+    using K = XPass<NX, T, WZ, NF, MODE, MU>;
     auto tw = build_stage_twiddles<T>(NX);
     typename K::Params p;
     std::memset(&p, 0, sizeof(p));
@@ -81,13 +81,23 @@ static void xpass(const cx<T>* w0, const cx<T>* w1, int ny, int nz, int pitch, c
         std::vector<unsigned> hc(nb, 0u);
         SmemHist hist{hs.data(), hc.data()};
         std::vector<typename K::Regs> regs(K::THREADS);
-        for (auto& r : regs) { acc_init(r.acc[0]); acc_init(r.acc[1]); }
+        for (auto& r : regs) for (int c = 0; c < K::NACC; ++c) acc_init(r.acc[c]);
         for (long long tile = cta; tile < p.ntiles; tile += nctas_emulated)
             run_hist<K, T, SmemHist>(p, tile, regs, smem.data(), hist);
-        for (auto& r : regs) { acc_flush(r.acc[0], hist, nb); acc_flush(r.acc[1], hist, nb); }
+        for (auto& r : regs) for (int c = 0; c < K::NACC; ++c) acc_flush(r.acc[c], hist, nb);
         if (MODE == MODE_BIN)
             for (int b = 0; b < nb; ++b) { sums[b] += hs[b]; counts[b] += hc[b]; }
     }
+}
+
+template <int NX, typename T, int WZ, int NF, int MODE>
+static void xpass(const cx<T>* w0, const cx<T>* w1, int ny, int nz, int pitch, const T* off0, const T* off1,
+                  const t21_binspec* spec, double* sums, long long* counts, void* nd_out, int nd_f64, double scale,
+                  int nctas_emulated, int xb) {
+    const int mu = (MODE == MODE_BIN && spec && spec->nmu > 0) ? (spec->absolute_mus ? 1 : 2) : 0;
+    if (mu == 0) xpass_mu<NX, T, WZ, NF, MODE, 0>(w0, w1, ny, nz, pitch, off0, off1, spec, sums, counts, nd_out, nd_f64, scale, nctas_emulated, xb);
+    else if (mu == 1) xpass_mu<NX, T, WZ, NF, MODE, 1>(w0, w1, ny, nz, pitch, off0, off1, spec, sums, counts, nd_out, nd_f64, scale, nctas_emulated, xb);
+    else xpass_mu<NX, T, WZ, NF, MODE, 2>(w0, w1, ny, nz, pitch, off0, off1, spec, sums, counts, nd_out, nd_f64, scale, nctas_emulated, xb);
 }
 
 #define DISPATCH_N(n, MACRO)                 \

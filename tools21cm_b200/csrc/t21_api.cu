@@ -260,7 +260,7 @@ int t21_ps_binned(const t21_plan* p, const void* x1, const void* x2, int subtrac
     if (a.hist_global)
         if (int rc = launch_zero_hist(sums_out, counts_out, nbins, st)) return rc;
     int rc = !p->fast[0] ? launch_xpass_generic(p->dtype, a, st)
-                         : (p->dtype == T21_F32 ? launch_xpass_f32_bin(a, st) : launch_xpass_f64_bin(a, st));
+                         : launch_xpass_bin(p->dtype, a, st);
     if (rc) return rc;
     prof_mark(st, SLOT_X);
     if (!a.hist_global) {
@@ -384,7 +384,7 @@ int t21_slab_stage2(const t21_plan* p, const void* w1, const void* w2, int iy0, 
     if (!g_prof.on || g_prof.n == 0) prof_begin(st);
     if (a.hist_global)
         if (int rc = launch_zero_hist(sums_out, counts_out, nbins, st)) return rc;
-    int rc = p->dtype == T21_F32 ? launch_xpass_f32_bin(a, st) : launch_xpass_f64_bin(a, st);
+    int rc = launch_xpass_bin(p->dtype, a, st);
     if (rc) return rc;
     prof_mark(st, SLOT_X);
     if (!a.hist_global) {

@@ -169,11 +169,14 @@ T21_HD void run_add(RunAcc& a, Hist& h, int bin, double p, int w) {
 //               one histogram update by lane 0) and install the new bin's intervals.
 // "Below / above every bin" are cached as pseudo bins nb, nb+1 so they do not force slow steps.
 // Every lane of the warp must make the same sequence of calls.
-struct WarpBins {
+template <bool MU> struct WarpBinsMu { float mlo[2], mhi[2]; };   // warp-uniform guard interval of mu^
+template <> struct WarpBinsMu<false> {};
+
+template <bool MU>
+struct WarpBins : WarpBinsMu<MU> {
 #if T21_DEVICE_CODE
     int bin[2];              // warp-uniform flat bin id (or pseudo bin), -1 = empty
     float slo[2], shi[2];    // warp-uniform guard interval of s^
-    float mlo[2], mhi[2];    // warp-uniform guard interval of mu^ (unused for shells)
     int lru;                 // warp-uniform: entry to evict next
     unsigned cnt[2];         // per lane
     double sum[2];           // per lane
@@ -182,12 +185,14 @@ struct WarpBins {
 #endif
 };
 
-T21_HD void warpbins_init(WarpBins& a) {
+template <bool MU>
+T21_HD void warpbins_init(WarpBins<MU>& a) {
 #if T21_DEVICE_CODE
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
         a.bin[c] = -1; a.cnt[c] = 0; a.sum[c] = 0.0;
-        a.slo[c] = 1.f; a.shi[c] = 0.f; a.mlo[c] = 1.f; a.mhi[c] = 0.f;   // empty intervals
+        a.slo[c] = 1.f; a.shi[c] = 0.f;                                   // empty interval
+        if constexpr (MU) { a.mlo[c] = 1.f; a.mhi[c] = 0.f; }
     }
     a.lru = 0;
 #else
@@ -196,8 +201,8 @@ T21_HD void warpbins_init(WarpBins& a) {
 }
 
 #if T21_DEVICE_CODE
-template <class Hist>
-__device__ __forceinline__ void warpbins_evict(WarpBins& a, Hist& h, int c, int nbins) {
+template <bool MU, class Hist>
+__device__ __forceinline__ void warpbins_evict(WarpBins<MU>& a, Hist& h, int c, int nbins) {
     // c is a compile-time constant at every call site, so a.*[c] stay in registers
     double s = a.sum[c];
     unsigned n = a.cnt[c];
@@ -211,25 +216,28 @@ __device__ __forceinline__ void warpbins_evict(WarpBins& a, Hist& h, int c, int 
     a.cnt[c] = 0;
 }
 
-__device__ __forceinline__ void warpbins_install(WarpBins& a, const t21_binspec& B, int c, int ref) {
-    const int nb = B.nk * (B.nmu > 0 ? B.nmu : 1);
+template <bool MU>
+__device__ __forceinline__ void warpbins_install(WarpBins<MU>& a, const t21_binspec& B, int c, int ref) {
+    const int nb = B.nk * (MU ? B.nmu : 1);
     a.bin[c] = ref;
     int kb = ref, mb = -1;
     if (ref >= nb) kb = B.nk + (ref - nb);            // pseudo bins: any mu
-    else if (B.nmu > 0) { mb = ref / B.nk; kb = ref - mb * B.nk; }
+    else if (MU) { mb = ref / B.nk; kb = ref - mb * B.nk; }
     a.slo[c] = ldg(B.k_lo_f + kb);
     a.shi[c] = ldg(B.k_hi_f + kb);
-    if (mb >= 0) { a.mlo[c] = ldg(B.mu_lo_f + mb); a.mhi[c] = ldg(B.mu_hi_f + mb); }
-    else { a.mlo[c] = -2.f; a.mhi[c] = 2.f; }
+    if constexpr (MU) {
+        if (mb >= 0) { a.mlo[c] = ldg(B.mu_lo_f + mb); a.mhi[c] = ldg(B.mu_hi_f + mb); }
+        else { a.mlo[c] = -2.f; a.mhi[c] = 2.f; }
+    }
 }
 
 // fast step; returns false (and adds nothing) if any lane needs the slow step.
 // MU: whether mu^ takes part.  valid = this lane has a mode (false for padding lanes).
 template <bool MU>
-__device__ __forceinline__ bool warpbins_fast(WarpBins& a, float sh, float muh, double p, unsigned w, bool valid) {
+__device__ __forceinline__ bool warpbins_fast(WarpBins<MU>& a, float sh, float muh, double p, unsigned w, bool valid) {
     bool in0 = sh >= a.slo[0] && sh < a.shi[0];
     bool in1 = sh >= a.slo[1] && sh < a.shi[1];
-    if (MU) {
+    if constexpr (MU) {
         in0 = in0 && muh >= a.mlo[0] && muh < a.mhi[0];
         in1 = in1 && muh >= a.mlo[1] && muh < a.mhi[1];
     }
@@ -242,8 +250,8 @@ __device__ __forceinline__ bool warpbins_fast(WarpBins& a, float sh, float muh, 
 }
 
 // slow step: `bin` is this lane's exact flat bin (-1: in no bin and not cacheable)
-template <class Hist>
-__device__ __forceinline__ void warpbins_slow(WarpBins& a, Hist& h, const t21_binspec& B, int nbins, int bin,
+template <bool MU, class Hist>
+__device__ __forceinline__ void warpbins_slow(WarpBins<MU>& a, Hist& h, const t21_binspec& B, int nbins, int bin,
                                               double p, unsigned w, bool valid) {
     unsigned todo = __ballot_sync(0xffffffffu, valid && bin >= 0);
     while (todo) {                                   // warp-uniform loop: one trip per distinct bin
@@ -271,8 +279,8 @@ __device__ __forceinline__ void warpbins_slow(WarpBins& a, Hist& h, const t21_bi
 }
 #endif
 
-template <class Hist>
-T21_HD void warpbins_flush(WarpBins& a, Hist& h, int nbins) {
+template <bool MU, class Hist>
+T21_HD void warpbins_flush(WarpBins<MU>& a, Hist& h, int nbins) {
 #if T21_DEVICE_CODE
     if (a.bin[0] >= 0) { warpbins_evict(a, h, 0, nbins); a.bin[0] = -1; a.slo[0] = 1.f; a.shi[0] = 0.f; }
     if (a.bin[1] >= 0) { warpbins_evict(a, h, 1, nbins); a.bin[1] = -1; a.slo[1] = 1.f; a.shi[1] = 0.f; }
@@ -292,16 +300,16 @@ struct ThreadBins {
 // the CPU replay, where WarpBins degenerates to a run accumulator)
 template <class Hist>
 T21_HD void acc_add_thread(ThreadBins& a, Hist& h, int bin, double p, int w) { run_add(a.run[0], h, bin, p, w); }
-template <class Hist>
-T21_HD void acc_add_thread(WarpBins& a, Hist& h, int bin, double p, int w) {
+template <bool MU, class Hist>
+T21_HD void acc_add_thread(WarpBins<MU>& a, Hist& h, int bin, double p, int w) {
 #if !T21_DEVICE_CODE
     run_add(a.run, h, bin, p, w);
 #endif
 }
-T21_HD void acc_init(WarpBins& a) { warpbins_init(a); }
+template <bool MU> T21_HD void acc_init(WarpBins<MU>& a) { warpbins_init(a); }
 T21_HD void acc_init(ThreadBins& a) { run_init(a.run[0]); }
-template <class Hist>
-T21_HD void acc_flush(WarpBins& a, Hist& h, int nbins) { warpbins_flush(a, h, nbins); }
+template <bool MU, class Hist>
+T21_HD void acc_flush(WarpBins<MU>& a, Hist& h, int nbins) { warpbins_flush(a, h, nbins); }
 template <class Hist>
 T21_HD void acc_flush(ThreadBins& a, Hist& h, int) { run_flush(a.run[0], h); }
 

@@ -42,10 +42,20 @@ struct XArgs {
 
 int launch_zpass(int dtype, const ZArgs& a, cudaStream_t st);
 int launch_ypass(int dtype, const YArgs& a, cudaStream_t st);
-int launch_xpass_f32_bin(XArgs& a, cudaStream_t st);
+int launch_xpass_f32_bin_mu0(XArgs& a, cudaStream_t st);   // one translation unit per mu mode
+int launch_xpass_f32_bin_mu1(XArgs& a, cudaStream_t st);
+int launch_xpass_f32_bin_mu2(XArgs& a, cudaStream_t st);
+int launch_xpass_f64_bin_mu0(XArgs& a, cudaStream_t st);
+int launch_xpass_f64_bin_mu1(XArgs& a, cudaStream_t st);
+int launch_xpass_f64_bin_mu2(XArgs& a, cudaStream_t st);
 int launch_xpass_f32_nd(XArgs& a, cudaStream_t st);
-int launch_xpass_f64_bin(XArgs& a, cudaStream_t st);
 int launch_xpass_f64_nd(XArgs& a, cudaStream_t st);
+inline int launch_xpass_bin(int dtype, XArgs& a, cudaStream_t st) {
+    const int mu = (a.bins && a.bins->nmu > 0) ? (a.bins->absolute_mus ? 1 : 2) : 0;
+    if (dtype == T21_F32)
+        return mu == 0 ? launch_xpass_f32_bin_mu0(a, st) : (mu == 1 ? launch_xpass_f32_bin_mu1(a, st) : launch_xpass_f32_bin_mu2(a, st));
+    return mu == 0 ? launch_xpass_f64_bin_mu0(a, st) : (mu == 1 ? launch_xpass_f64_bin_mu1(a, st) : launch_xpass_f64_bin_mu2(a, st));
+}
 
 // t21_generic.cu: any-length direct-DFT versions (tw / twr hold the n-th roots of unity there)
 int launch_zpass_generic(int dtype, const ZArgs& a, cudaStream_t st);

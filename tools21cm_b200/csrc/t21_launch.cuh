@@ -52,8 +52,8 @@ xpass_kernel(const __grid_constant__ typename K::Params p, int nbins, int warp_p
     cx<T>* ex = reinterpret_cast<cx<T>*>(smem_raw);
     const int tid = threadIdx.x;
     typename K::Regs r;
-    acc_init(r.acc[0]);
-    acc_init(r.acc[1]);
+#pragma unroll
+    for (int c = 0; c < K::NACC; ++c) acc_init(r.acc[c]);
     if constexpr (HK == 0) {
         // shared-memory histogram: one copy per warp when that fits (plain adds by lane 0, summed
         // in warp order at the end => bit-reproducible), otherwise one copy updated with atomics
@@ -67,14 +67,14 @@ xpass_kernel(const __grid_constant__ typename K::Params p, int nbins, int warp_p
             WarpPrivHist hist{hs + (size_t)(tid >> 5) * nbins, hc + (size_t)(tid >> 5) * nbins};
             for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
                 { dev_phases_hist<K, T, WarpPrivHist>(p, tile, tid, r, ex, hist); __syncthreads(); }
-            acc_flush(r.acc[0], hist, nbins);
-            acc_flush(r.acc[1], hist, nbins);
+#pragma unroll
+            for (int c = 0; c < K::NACC; ++c) acc_flush(r.acc[c], hist, nbins);
         } else {
             SmemHist hist{hs, hc};
             for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
                 { dev_phases_hist<K, T, SmemHist>(p, tile, tid, r, ex, hist); __syncthreads(); }
-            acc_flush(r.acc[0], hist, nbins);
-            acc_flush(r.acc[1], hist, nbins);
+#pragma unroll
+            for (int c = 0; c < K::NACC; ++c) acc_flush(r.acc[c], hist, nbins);
         }
         __syncthreads();
         for (int b = tid; b < nbins; b += K::THREADS) {
@@ -88,8 +88,8 @@ xpass_kernel(const __grid_constant__ typename K::Params p, int nbins, int warp_p
         GlobalHist hist{gsum, gcnt};
         for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
             { dev_phases_hist<K, T, GlobalHist>(p, tile, tid, r, ex, hist); __syncthreads(); }
-        acc_flush(r.acc[0], hist, nbins);
-        acc_flush(r.acc[1], hist, nbins);
+#pragma unroll
+        for (int c = 0; c < K::NACC; ++c) acc_flush(r.acc[c], hist, nbins);
     } else {
         NoHist hist;
         for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)

@@ -207,7 +207,10 @@ struct YPass {
 // loop (small code) feeds the warp-uniform bin cache with near-perfect hit rate.
 enum { MODE_BIN = 0, MODE_ND = 1 };
 
-template <int NX, typename T, int WZ, int NF, int MODE>
+// MU (MODE_BIN only): 0 shells, 1 |mu| bins, 2 signed mu bins (Hermitian twins binned separately).
+// It is a compile-time parameter so that the accumulator state that lives across tiles is as
+// small as the mode allows (shells: 6 lane registers; signed mu: two accumulators with mu intervals).
+template <int NX, typename T, int WZ, int NF, int MODE, int MU = 0>
 struct XPass {
     using S = Strided<NX, T, WZ>;
     using P = Plan<NX>;
@@ -220,11 +223,13 @@ struct XPass {
     static constexpr int SMEM_BYTES = BUF_BYTES + 16;          // + the DC power as a double
     static constexpr int NPHASE = NF * S::FFT_PHASES + 1;      // transforms, then the epilogue
     static constexpr int kMode = MODE;
+    static constexpr int kMu = MU;
+    static constexpr int NACC = (MU == 2) ? 2 : 1;
     static constexpr int RPI = (THREADS >= 32) ? 32 / WZ : S::TP;   // kx rows a warp covers per step
     // whole warps use the warp-uniform bin cache; CTAs smaller than a warp keep per-thread runs
     template <bool B, class A, class C> struct Pick { using type = A; };
     template <class A, class C> struct Pick<false, A, C> { using type = C; };
-    using Acc = typename Pick<(THREADS % 32 == 0), WarpBins, ThreadBins>::type;
+    using Acc = typename Pick<(THREADS % 32 == 0), WarpBins<(MU != 0)>, ThreadBins>::type;
 
     struct Params {
         const cx<T>* w[2];    // [NX][ny][pitch] per field
@@ -243,7 +248,7 @@ struct XPass {
     };
     struct Regs {
         cx<T> v[NF][E];
-        Acc acc[2];           // [0] stored modes, [1] Hermitian twins when they bin separately (signed mu)
+        Acc acc[NACC];        // [0] stored modes, [1] Hermitian twins when they bin separately (signed mu)
     };
 
     static T21_HD T* ptile(cx<T>* smem) { return reinterpret_cast<T*>(smem); }
@@ -332,17 +337,13 @@ struct XPass {
     static T21_HD void epilogue(const Params& p, int tid, int iy, int iz, int zl, bool active, Regs& r,
                                 cx<T>* smem, Hist& hist) {
         if constexpr (MODE == MODE_BIN) {
-            // three specialisations of the same loop, picked by a CTA-uniform branch
-            if (p.bins.nmu == 0) epilogue_bin<0>(p, tid, iy, iz, zl, active, r, smem, hist);
-            else if (p.bins.absolute_mus) epilogue_bin<1>(p, tid, iy, iz, zl, active, r, smem, hist);
-            else epilogue_bin<2>(p, tid, iy, iz, zl, active, r, smem, hist);
+            epilogue_bin(p, tid, iy, iz, zl, active, r, smem, hist);
         } else {
             epilogue_nd(p, tid, iy, iz, zl, active, smem);
         }
     }
 
-    // MU: 0 shells, 1 |mu| bins, 2 signed mu bins (twins binned separately)
-    template <int MU, class Hist>
+    template <class Hist>
     static T21_HD void epilogue_bin(const Params& p, int tid, int iy, int iz, int zl, bool active, Regs& r,
                                     cx<T>* smem, Hist& hist) {
         const t21_binspec& B = p.bins;
@@ -395,7 +396,7 @@ struct XPass {
                     const int bin = valid ? exact_bin(p, ix, iy, iz, has_twin, 0, sh, w1) : -1;
                     warpbins_slow(r.acc[0], hist, B, nb, bin, w1 == (int)wt ? pw : (double)*pt, (unsigned)w1, valid);
                 }
-                if (MU == 2) {                                // the twin goes to the mirrored mu bin
+                if constexpr (MU == 2) {                      // the twin goes to the mirrored mu bin
                     const bool tv = valid && has_twin;
                     const float m_tw = nyq ? muh : -muh;
                     if (!warpbins_fast<true>(r.acc[1], sh, m_tw, pw, 1u, tv)) {
@@ -411,7 +412,7 @@ struct XPass {
             if (valid) {
                 const ModeBins mb = classify(B, ix, iy, iz, has_twin);
                 acc_add_thread(r.acc[0], hist, mb.own, (double)*pt, mb.own_w);
-                if (MU == 2) acc_add_thread(r.acc[1], hist, mb.twin, (double)*pt, 1);
+                if constexpr (MU == 2) acc_add_thread(r.acc[1], hist, mb.twin, (double)*pt, 1);
             }
         }
     }

@@ -1,0 +1,20 @@
+// X pass instantiations: double, MODE_BIN, mu mode 1 (0 shells, 1 |mu|, 2 signed mu); auto and cross.
+#include <string.h>
+#include "t21_launch.cuh"
+
+namespace t21 {
+
+int launch_xpass_f64_bin_mu1(XArgs& a, cudaStream_t st) {
+    using T = double;
+#define XCASE(N)                                                                          \
+    {                                                                                     \
+        constexpr int WZ = WZFor<T, N>::value;                                            \
+        if (a.nf == 1) return launch_x<XPass<N, T, WZ, 1, MODE_BIN, 1>, T>(a, st);    \
+        return launch_x<XPass<N, T, WZ, 2, MODE_BIN, 1>, T>(a, st);                   \
+    }
+    T21_FOR_FAST_N(a.nx, XCASE)
+#undef XCASE
+    return 0;
+}
+
+}  // namespace t21

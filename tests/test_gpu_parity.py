@@ -159,3 +159,59 @@ def test_large_cube_properties(t2c, n):
     ps3, ks3, nm3 = t2c.radial_average(nd, [L, L, L], kbins=15)
     assert np.array_equal(nm3, nm)
     np.testing.assert_allclose(ps3, ps, rtol=1e-5)
+
+
+def test_window_kbins_rules_and_side_effects(t2c):
+    from oracle import ps_oracle
+    rng = np.random.default_rng(12)
+    cube = rng.standard_normal((32, 32, 32))
+    a, b = cube.copy(), cube.copy()
+    got = t2c.power_spectrum_1d(a, kbins=6, box_dims=80.0, window="tukey", return_n_modes=True)
+    want = ps_oracle.power_spectrum_1d(b, kbins=6, box_dims=80.0, window="tukey", return_n_modes=True)
+    assert np.array_equal(a, b) and not np.array_equal(a, cube)         # the caller's array is tapered in place
+    assert np.array_equal(got[2], want[2])
+    np.testing.assert_allclose(got[0], want[0], rtol=1e-11)
+    with pytest.raises(TypeError):                                         # a list of edges fails in the reference too
+        t2c.power_spectrum_1d(cube, kbins=[0.1, 0.2, 0.4], box_dims=80.0)
+    with pytest.raises(ValueError):
+        t2c.power_spectrum_1d(cube, kbins=np.array([0.4, 0.2, 0.8]), box_dims=80.0)
+    # mu_binning zeroes the centre sample of its input, like the reference (power_spectrum.py:414)
+    p = np.abs(rng.standard_normal((16, 16, 16))) + 1.0
+    t2c.mu_binning(p, los_axis=0, mubins=3, kbins=4, box_dims=[50.0] * 3)
+    assert p[8, 8, 8] == 0.0
+    # many bins: the per-warp / shared / global histogram variants all agree with the oracle
+    for nb in (100, 1000, 3000):
+        g = t2c.power_spectrum_1d(cube, kbins=nb, box_dims=80.0, return_n_modes=True)
+        w = ps_oracle.power_spectrum_1d(cube, kbins=nb, box_dims=80.0, return_n_modes=True)
+        assert np.array_equal(g[2], w[2])
+        np.testing.assert_allclose(g[0], w[0], rtol=1e-11, equal_nan=True)
+    g = t2c.power_spectrum_mu(cube, kbins=60, mubins=50, box_dims=80.0, return_n_modes=True, absolute_mus=False)
+    w = ps_oracle.power_spectrum_mu(cube, kbins=60, mubins=50, box_dims=80.0, return_n_modes=True, absolute_mus=False)
+    assert np.array_equal(g[3], w[3])
+    np.testing.assert_allclose(g[0], w[0], rtol=1e-11, equal_nan=True)
+
+
+def test_set_precision_and_run_to_run_reproducibility(t2c):
+    from tools21cm_b200 import synthetic
+    x = synthetic.toy_dt_cube((64, 64, 64), seed=2)
+    a = t2c.power_spectrum_1d(x, kbins=15, box_dims=100.0)
+    b = t2c.power_spectrum_1d(x, kbins=15, box_dims=100.0)
+    assert np.array_equal(a[0], b[0], equal_nan=True), "small histograms are summed in a fixed order: results must be bit-identical"
+    t2c.set_precision("float64")
+    try:
+        c = t2c.power_spectrum_1d(x, kbins=15, box_dims=100.0)
+    finally:
+        t2c.set_precision(None)
+    np.testing.assert_allclose(a[0], c[0], rtol=1e-5, equal_nan=True)
+    assert not np.array_equal(a[0], c[0], equal_nan=True)
+
+
+def test_cross_of_a_cube_with_itself_is_its_auto_spectrum_512(t2c):
+    from tools21cm_b200 import synthetic
+    x = synthetic.toy_dt_cube_torch((512, 512, 512), seed=5)
+    a = t2c.power_spectrum_1d(x, kbins=15, box_dims=300.0, return_n_modes=True)
+    c = t2c.cross_power_spectrum_1d(x, x.clone(), kbins=15, box_dims=300.0, return_n_modes=True)
+    assert np.array_equal(a[2], c[2])
+    np.testing.assert_allclose(a[0], c[0], rtol=1e-12)
+    m = t2c.power_spectrum_mu(x, kbins=10, mubins=5, box_dims=300.0, return_n_modes=True)
+    assert m[3].sum() == 512 ** 3 - 512 - 1 - 0 or m[3].sum() > 0.99 * 512 ** 3

@@ -6,17 +6,26 @@
 namespace t21 {
 
 // ---- mean offset --------------------------------------------------------------------
-// c ~ mean(x) from a strided sample (<= 65536 values, odd stride so it walks every axis).
+// c ~ mean(x) from a strided sample (<= 16384 values, odd stride so it walks every axis).
 // The FFT of x - c differs from the FFT of x only in the DC sample, which the X pass
 // repairs analytically, so c only needs to be close to the mean: it is there to keep
 // the fp32 partial sums small, not to define the result.
 template <typename T>
 __global__ void __launch_bounds__(1024) mean_estimate_kernel(const T* __restrict__ x, long long n, T* out) {
-    const long long want = n < 65536 ? n : 65536;
+    constexpr int kPer = 16;                               // independent loads in flight per thread
+    const long long want = n < 1024 * kPer ? n : 1024 * kPer;
     const long long stride = (n / want) | 1;
     const long long count = (n - 1) / stride + 1;
+    T v[kPer];
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+        const long long i = threadIdx.x + 1024LL * u;
+        v[u] = i < count ? x[i * stride] : (T)0;
+    }
     double s = 0.0;
-    for (long long i = threadIdx.x; i < count; i += 1024) s += (double)x[i * stride];
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) s += (double)v[u];
+    for (long long i = threadIdx.x + 1024LL * kPer; i < count; i += 1024) s += (double)x[i * stride];
     __shared__ double red[32];
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -37,24 +46,30 @@ int launch_mean_estimate(int dtype, const void* x, long long n, void* offset_out
 }
 
 // ---- deterministic inter-CTA reduction ------------------------------------------------
-// one thread per bin, partials added in CTA order
-__global__ void reduce_partials_kernel(const double* __restrict__ part_sum, const unsigned* __restrict__ part_cnt,
-                                       int nparts, int nbins, double* __restrict__ sums, long long* __restrict__ counts) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per bin: lane l adds partials l, l+32, ... in order, then a fixed shuffle tree joins the 32
+// lane sums -- the order never depends on timing, so the result is reproducible
+__global__ void __launch_bounds__(128)
+reduce_partials_kernel(const double* __restrict__ part_sum, const unsigned* __restrict__ part_cnt,
+                       int nparts, int nbins, double* __restrict__ sums, long long* __restrict__ counts) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (b >= nbins) return;
     double s = 0.0;
     long long c = 0;
-    for (int p = 0; p < nparts; ++p) {
+    for (int p = lane; p < nparts; p += 32) {
         s += part_sum[(size_t)p * nbins + b];
         c += part_cnt[(size_t)p * nbins + b];
     }
-    sums[b] = s;
-    counts[b] = c;
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_down_sync(0xffffffffu, s, o);
+        c += __shfl_down_sync(0xffffffffu, c, o);
+    }
+    if (lane == 0) { sums[b] = s; counts[b] = c; }
 }
 
 int launch_reduce_partials(const double* part_sum, const unsigned* part_cnt, int nparts, int nbins,
                            double* sums_out, long long* counts_out, cudaStream_t st) {
-    reduce_partials_kernel<<<(nbins + 127) / 128, 128, 0, st>>>(part_sum, part_cnt, nparts, nbins, sums_out, counts_out);
+    reduce_partials_kernel<<<(nbins + 3) / 4, 128, 0, st>>>(part_sum, part_cnt, nparts, nbins, sums_out, counts_out);
     count_launch();
     T21_CUDA_OK(cudaGetLastError());
     return 0;

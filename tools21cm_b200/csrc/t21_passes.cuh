@@ -77,22 +77,28 @@ struct ZPass {
             if constexpr (PH % 2 == 1) stage_load<M, S>(r.v, j, ld_smem);
             else stage_compute<M, S>(r.v, j, p.tw, st_smem);
         } else {
-            // untangle: X[k] = (Z[k] + conj Z[M-k])/2 - i/2 * w^k * (Z[k] - conj Z[M-k])
+            // untangle: X[k] = (Z[k] + conj Z[M-k])/2 - i/2 * w^k * (Z[k] - conj Z[M-k]),  w = exp(-2 pi i / NZ).
+            // k and M-k need the same two inputs and w^(M-k) = -conj(w^k), so one thread produces both.
             if (!active) return;
             const long long x = row / p.ny, y = row - x * p.ny;
             const long long orow = ((((x >> p.xb) * p.ny + y) << p.xb) + (x & ((1 << p.xb) - 1)));
             cx<T>* dst = p.out + orow * p.pitch;
-#pragma unroll
-            for (int i = 0; i < E; ++i) {
-                const int k = j + i * TP;
+            auto pair = [&](int k) {
                 const cx<T> zk = ld_smem(k), zm = ld_smem((M - k) & (M - 1));
                 const cx<T> w = ldg(p.twr + k);
-                const cx<T> a = cmake<T>(zk.x + zm.x, zk.y - zm.y);
-                const cx<T> d = cmake<T>(zk.x - zm.x, zk.y + zm.y);
+                const cx<T> a = cmake<T>(zk.x + zm.x, zk.y - zm.y);       // Z[k] + conj Z[M-k]
+                const cx<T> d = cmake<T>(zk.x - zm.x, zk.y + zm.y);       // Z[k] - conj Z[M-k]
                 const cx<T> t = cmul(w, d);
                 dst[k] = cmake<T>((T)0.5 * (a.x + t.y), (T)0.5 * (a.y - t.x));
-                if (k == 0) dst[M] = cmake<T>(zk.x - zk.y, (T)0);
+                // partner: conj(a) - i/2 * (-conj w) * (-conj d) = conj(a)/2 - i/2 * conj(t)
+                dst[M - k] = cmake<T>((T)0.5 * (a.x - t.y), (T)0.5 * (-a.y - t.x));
+            };
+#pragma unroll
+            for (int i = 0; i < (E + 1) / 2; ++i) {
+                const int k = j + i * TP;
+                if (k < M / 2 || (M / 2 == 0)) pair(k);
             }
+            if (j == 0 && M >= 2) pair(M / 2);                            // self-paired middle sample
         }
     }
 };

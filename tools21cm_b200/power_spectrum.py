@@ -381,13 +381,7 @@ def mu_binning(powerspectrum, los_axis=0, mubins=20, kbins=10, box_dims=None, we
                exclude_zero_modes=True, binning="log", absolute_mus=True):
     """(k, mu) averages of an fftshifted 3-D array (reference power_spectrum.py:380-435).
     Like the reference it zeroes the centre sample of its input in place."""
-    if weights is not None:
-        # the reference cannot use weights either: an array fails at `weights != None`
-        # (power_spectrum.py:386), a scalar at `weights[idx]` (:433)
-        if np.ndim(weights) > 0:
-            raise ValueError("The truth value of an array with more than one element is ambiguous. "
-                             "Use a.any() or a.all()")
-        raise TypeError("'%s' object is not subscriptable" % type(weights).__name__)
+    _reject_weights(weights)
     assert (len(powerspectrum.shape) == 3)
     box_dims = _get_dims(box_dims, powerspectrum.shape)
     centre = tuple((np.array(powerspectrum.shape) / 2).astype(int))
@@ -422,12 +416,18 @@ def _shell_estimate(fields, kbins, box_dims, binning, breakpoint):
     return _finish(sums, counts, _bs.volume_scale(shape, box_dims)), spec.k_centres(), counts
 
 
-def _mu_estimate(fields, los_axis, mubins, kbins, box_dims, weights, exclude_zero_modes, absolute_mus):
+def _reject_weights(weights):
+    """The reference cannot use weights either: an array fails at `weights != None`
+    (power_spectrum.py:386), a scalar at `weights[idx]` (:433).  Same exception types here."""
     if weights is not None:
         if np.ndim(weights) > 0:
             raise ValueError("The truth value of an array with more than one element is ambiguous. "
                              "Use a.any() or a.all()")
         raise TypeError("'%s' object is not subscriptable" % type(weights).__name__)
+
+
+def _mu_estimate(fields, los_axis, mubins, kbins, box_dims, weights, exclude_zero_modes, absolute_mus):
+    _reject_weights(weights)
     shape = tuple(fields[0].shape)
     assert (len(shape) == 3)
     key = ("mu", _freeze(list(box_dims)), _freeze(kbins), _freeze(mubins), los_axis, bool(absolute_mus),
@@ -480,6 +480,7 @@ def power_spectrum_mu(input_array, los_axis=0, mubins=20, kbins=10, box_dims=Non
     if kwargs.get("boxsize") is not None:
         box_dims = kwargs.get("boxsize")
     box_dims = _get_dims(box_dims, input_array.shape)
+    _reject_weights(weights)
     x, _ = _stage(input_array)
     ps, mu_bins, k_bins, n_modes = _mu_estimate([x], los_axis, mubins, kbins, box_dims, weights,
                                                 exclude_zero_modes, absolute_mus)
@@ -496,6 +497,7 @@ def cross_power_spectrum_mu(input_array1, input_array2, los_axis=0, mubins=20, k
     if kwargs.get("boxsize") is not None:
         box_dims = kwargs.get("boxsize")
     box_dims = _get_dims(box_dims, input_array1.shape)
+    _reject_weights(weights)
     a, _ = _stage(input_array1)
     b, _ = _stage(input_array2)
     if a.dtype != b.dtype:

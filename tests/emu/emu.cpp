@@ -31,7 +31,7 @@ static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 template <int NZ, typename T>
 static void zpass(const T* in, cx<T>* out, long long nrows, int pitch, const T* offset, int ny, int xb) {
     using K = ZPass<NZ, T>;
-    auto tw = build_stage_twiddles<T>(NZ / 2);
+    auto tw = build_stage_twiddles<T>(NZ / 2, emax_z(NZ / 2));
     auto twr = build_roots<T>(NZ, NZ / 2 + 1);
     typename K::Params p{in, out, nrows, pitch, ny, xb, offset, tw.data(), twr.data()};
     std::vector<cx<T>> smem(K::SMEM_BYTES / sizeof(cx<T>) + 1);
@@ -44,7 +44,7 @@ static void zpass(const T* in, cx<T>* out, long long nrows, int pitch, const T* 
 template <int NY, typename T, int WZ>
 static void ypass(cx<T>* w, long long nouter, int nzh, int pitch, int xb) {
     using K = YPass<NY, T, WZ>;
-    auto tw = build_stage_twiddles<T>(NY);
+    auto tw = build_stage_twiddles<T>(NY, emax_y(NY));
     int nchunks = (nzh + WZ - 1) / WZ;
     typename K::Params p{w, nzh, pitch, nchunks, xb, tw.data(), nullptr, 0, nouter};
     std::vector<cx<T>> smem(K::SMEM_BYTES / sizeof(cx<T>) + 1);
@@ -58,7 +58,7 @@ static void xpass_mu(const cx<T>* w0, const cx<T>* w1, int ny, int nz, int pitch
                   const t21_binspec* spec, double* sums, long long* counts, void* nd_out, int nd_f64, double scale,
                   int nctas_emulated, int xb) {
     using K = XPass<NX, T, WZ, NF, MODE, MU>;
-    auto tw = build_stage_twiddles<T>(NX);
+    auto tw = build_stage_twiddles<T>(NX, emax_x(NX));
     typename K::Params p;
     std::memset(&p, 0, sizeof(p));
     p.w[0] = w0; p.w[1] = w1;

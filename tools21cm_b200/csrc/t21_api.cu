@@ -119,7 +119,8 @@ static int build_tables(t21_plan* p) {
     for (int d = 0; d < 3; ++d) {
         if (p->fast[d]) {
             const int len = d == 2 ? p->n[2] / 2 : p->n[d];
-            if (int rc = upload<T>(build_stage_twiddles<T>(len), &p->tw[d])) return rc;
+            const int emax = d == 2 ? emax_z(len) : (d == 1 ? emax_y(len) : emax_x(len));
+            if (int rc = upload<T>(build_stage_twiddles<T>(len, emax), &p->tw[d])) return rc;
         } else if (d < 2) {
             if (int rc = upload<T>(build_roots<T>(p->n[d], p->n[d]), &p->tw[d])) return rc;   // generic pass
         }

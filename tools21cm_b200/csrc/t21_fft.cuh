@@ -93,17 +93,15 @@ struct DFT<1, T> {
 };
 
 // ---- compile-time plan ------------------------------------------------------------
-// values per thread (= largest radix).  32 halves the number of shared-memory exchanges and
-// barriers for long pencils at the price of ~2x the registers; T21_EMAX overrides for experiments.
-#ifndef T21_EMAX_LONG
-#define T21_EMAX_LONG 16
-#endif
-constexpr int plan_emax(int n) { return n >= 512 ? T21_EMAX_LONG : 16; }
-
-template <int N>
+// EMAX = values per thread (= largest radix), 16 or 32.  32 halves the number of shared-memory
+// exchanges and barriers and lets a CTA be half as many threads (more CTAs per SM for the same
+// shared memory) at the price of ~86 registers per thread; each pass picks its own (t21_internal.h).
+template <int N, int EMAX = 16>
 struct Plan {
     static_assert(is_pow2(N) && N >= 2, "pencil length must be a power of two");
-    static constexpr int E = N < plan_emax(N) ? N : plan_emax(N);  // values per thread
+    static_assert(EMAX == 16 || EMAX == 32, "EMAX");
+    static constexpr int E = N < EMAX ? N : EMAX;  // values per thread
+    static constexpr int LEN = N;
     static constexpr int T = N / E;            // threads per pencil
     static constexpr int radix(int s) {        // radix of stage s (0 past the end)
         int rem = N;
@@ -130,8 +128,8 @@ struct Plan {
 };
 
 // number of twiddle entries for a run-time N (host side of t21_plan_create)
-inline int plan_tw_total(int n) {
-    int e = n < plan_emax(n) ? n : plan_emax(n), rem = n, nsv = 1, tot = 0, s = 0;
+inline int plan_tw_total(int n, int emax) {
+    int e = n < emax ? n : emax, rem = n, nsv = 1, tot = 0, s = 0;
     while (rem > 1) {
         int r = rem < e ? rem : e;
         if (s > 0) tot += (r - 1) * nsv;
@@ -161,10 +159,9 @@ struct RowCursor {
 // ---- one stage, split into its load and its compute+store halves -------------------
 // ld(i) returns element i of this thread's pencil; st(i, v, slot) stores element i, which
 // lives in register slot `slot` (a compile-time constant after unrolling).
-template <int N, int S, typename T, class LoadFn>
+template <class P, int S, typename T, class LoadFn>
 T21_HD void stage_load(cx<T>* v, int j, LoadFn&& ld) {
-    using P = Plan<N>;
-    constexpr int R = P::radix(S), NB = P::E / R, STRIDE = N / R;
+    constexpr int R = P::radix(S), NB = P::E / R, STRIDE = P::LEN / R;
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         const int jj = j + b * P::T;
@@ -173,9 +170,8 @@ T21_HD void stage_load(cx<T>* v, int j, LoadFn&& ld) {
     }
 }
 
-template <int N, int S, typename T, class StoreFn>
+template <class P, int S, typename T, class StoreFn>
 T21_HD void stage_compute(cx<T>* v, int j, const cx<T>* __restrict__ tw, StoreFn&& st) {
-    using P = Plan<N>;
     constexpr int R = P::radix(S), NB = P::E / R, NSV = P::ns(S), OFF = P::tw_off(S);
 #pragma unroll
     for (int b = 0; b < NB; ++b) {

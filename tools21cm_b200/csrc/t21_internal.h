@@ -3,21 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/t21ps.h"
+#include "t21_config.h"
 
 namespace t21 {
-
-// widest pow2 pencil the Stockham kernels are instantiated for; other lengths take the
-// generic DFT kernels (t21_generic.cu)
-constexpr int kMinFast = 8;
-constexpr int kMaxFast = 4096;
-inline bool fast_len(int n) { return n >= kMinFast && n <= kMaxFast && (n & (n - 1)) == 0; }
-
-// columns of the half spectrum a strided CTA owns (WZ * sizeof(complex) contiguous bytes per row)
-template <typename T, int N>
-struct WZFor {
-    static constexpr int value = sizeof(T) == 4 ? (N <= 512 ? 16 : (N <= 2048 ? 8 : 4))
-                                                : (N <= 512 ? 8 : (N <= 2048 ? 4 : 2));
-};
 
 struct ZArgs {
     const void* in; void* out; long long nrows; int nz; int pitch; int ny; int xb;

@@ -27,7 +27,7 @@ __device__ __forceinline__ void dev_phases_hist(const typename K::Params& p, lon
 
 // one CTA per tile (Z and Y passes)
 template <class K, typename T>
-__global__ void __launch_bounds__(K::THREADS) tile_kernel(const __grid_constant__ typename K::Params p) {
+__global__ void __launch_bounds__(K::THREADS, K::MIN_CTAS) tile_kernel(const __grid_constant__ typename K::Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename K::Regs r;
     dev_phases<K, T>(p, (long long)blockIdx.x, (int)threadIdx.x, r, reinterpret_cast<cx<T>*>(smem_raw));

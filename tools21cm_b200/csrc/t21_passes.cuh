@@ -20,6 +20,7 @@
 #pragma once
 #include "t21_fft.cuh"
 #include "t21_bin.cuh"
+#include "t21_config.h"
 
 namespace t21 {
 
@@ -30,13 +31,14 @@ template <int NZ, typename T>
 struct ZPass {
     static_assert(is_pow2(NZ) && NZ >= 4, "nz");
     static constexpr int M = NZ / 2;
-    using P = Plan<M>;
+    using P = Plan<M, emax_z(M)>;
     static constexpr int E = P::E, TP = P::T, NS = P::NS;
     static constexpr int THREADS = TP >= 256 ? TP : 256;
     static constexpr int ROWS = THREADS / TP;
     static constexpr int ROWPITCH = M + (M >> 4) + 1;          // padded: i -> i + (i >> 4)
     static constexpr int SMEM_ELEMS = ROWS * ROWPITCH;
     static constexpr int SMEM_BYTES = SMEM_ELEMS * (int)sizeof(cx<T>);
+    static constexpr int MIN_CTAS = (THREADS <= 256 && sizeof(T) == 4) ? 4 : 1;   // 64 registers: what it needs anyway
     static constexpr int NPHASE = 2 * NS;
 
     struct Params {
@@ -67,15 +69,15 @@ struct ZPass {
         if constexpr (PH == 0) {
             const T off = p.offset ? ldg(p.offset) : (T)0;
             const cx<T>* src = reinterpret_cast<const cx<T>*>(p.in + (active ? row : 0) * NZ);
-            stage_load<M, 0>(r.v, j, [&](int i) {
+            stage_load<P, 0>(r.v, j, [&](int i) {
                 cx<T> v = active ? src[i] : cmake<T>(0, 0);
                 return cmake<T>(v.x - off, v.y - off);
             });
-            stage_compute<M, 0>(r.v, j, p.tw, st_smem);
+            stage_compute<P, 0>(r.v, j, p.tw, st_smem);
         } else if constexpr (PH < NPHASE - 1) {
             constexpr int S = (PH + 1) / 2;
-            if constexpr (PH % 2 == 1) stage_load<M, S>(r.v, j, ld_smem);
-            else stage_compute<M, S>(r.v, j, p.tw, st_smem);
+            if constexpr (PH % 2 == 1) stage_load<P, S>(r.v, j, ld_smem);
+            else stage_compute<P, S>(r.v, j, p.tw, st_smem);
         } else {
             // untangle: X[k] = (Z[k] + conj Z[M-k])/2 - i/2 * w^k * (Z[k] - conj Z[M-k]),  w = exp(-2 pi i / NZ).
             // k and M-k need the same two inputs and w^(M-k) = -conj(w^k), so one thread produces both.
@@ -106,9 +108,9 @@ struct ZPass {
 // ======================================================================================
 // strided pencils: shared pieces of the Y and X passes
 // ======================================================================================
-template <int N, typename T, int WZ>
+template <int N, typename T, int WZ, int EMAX>
 struct Strided {
-    using P = Plan<N>;
+    using P = Plan<N, EMAX>;
     static constexpr int E = P::E, TP = P::T, NS = P::NS;
     static constexpr int THREADS = WZ * TP;
     static constexpr int SMEM_ELEMS = (NS > 1) ? N * WZ : 1;
@@ -121,16 +123,16 @@ struct Strided {
         auto st_smem = [&](int i, cx<T> val, int) { smem[i * WZ + zl] = val; };
         auto ld_smem = [&](int i) { return smem[i * WZ + zl]; };
         if constexpr (PH == 0) {
-            stage_load<N, 0>(v, j, ld_g);
-            if constexpr (NS == 1) stage_compute<N, 0>(v, j, tw, fin);
-            else stage_compute<N, 0>(v, j, tw, st_smem);
+            stage_load<P, 0>(v, j, ld_g);
+            if constexpr (NS == 1) stage_compute<P, 0>(v, j, tw, fin);
+            else stage_compute<P, 0>(v, j, tw, st_smem);
         } else {
             constexpr int S = (PH + 1) / 2;
             if constexpr (PH % 2 == 1) {
-                stage_load<N, S>(v, j, ld_smem);
+                stage_load<P, S>(v, j, ld_smem);
             } else {
-                if constexpr (S == NS - 1) stage_compute<N, S>(v, j, tw, fin);
-                else stage_compute<N, S>(v, j, tw, st_smem);
+                if constexpr (S == NS - 1) stage_compute<P, S>(v, j, tw, fin);
+                else stage_compute<P, S>(v, j, tw, st_smem);
             }
         }
     }
@@ -144,10 +146,15 @@ struct Strided {
 // like the rest and ignored by the X-pass epilogue, so no access here needs a bounds predicate.
 template <int NY, typename T, int WZ, bool SEND = false>
 struct YPass {
-    using S = Strided<NY, T, WZ>;
+    using S = Strided<NY, T, WZ, emax_y(NY)>;
     static constexpr int THREADS = S::THREADS;
     static constexpr int SMEM_BYTES = S::SMEM_ELEMS * (int)sizeof(cx<T>);
     static constexpr int NPHASE = S::FFT_PHASES;
+    // aim at 64 registers per thread (1024 resident threads per SM) as far as shared memory allows: the
+    // pass is latency bound and wants every CTA it can get
+    static constexpr int kByRegs = THREADS >= 1024 ? 1 : (1024 / THREADS > 8 ? 8 : 1024 / THREADS);
+    static constexpr int kBySmem = SMEM_BYTES > 0 ? (200 * 1024) / (SMEM_BYTES + 1024) : 8;
+    static constexpr int MIN_CTAS = S::E > 16 ? 1 : (kByRegs < kBySmem ? kByRegs : (kBySmem < 1 ? 1 : kBySmem));
 
     struct Params {
         cx<T>* w;             // [nouter][NY][pitch]
@@ -176,7 +183,7 @@ struct YPass {
         const long long row0 = (((outer >> p.xb) * NY) << p.xb) + (outer & ((1 << p.xb) - 1));
         cx<T>* base = p.w + row0 * p.pitch + z;
         const long long stride = (long long)p.pitch << p.xb;
-        using P = Plan<NY>;
+        using P = typename S::P;
         // rows are visited in loop order, so both the first-stage loads and the last-stage stores walk
         // a cursor instead of multiplying an index by the run-time row stride
         constexpr int R0 = P::radix(0), RL = P::radix(P::NS - 1), NSL = P::ns(P::NS - 1);
@@ -218,8 +225,8 @@ enum { MODE_BIN = 0, MODE_ND = 1 };
 // small as the mode allows (shells: 6 lane registers; signed mu: two accumulators with mu intervals).
 template <int NX, typename T, int WZ, int NF, int MODE, int MU = 0>
 struct XPass {
-    using S = Strided<NX, T, WZ>;
-    using P = Plan<NX>;
+    using S = Strided<NX, T, WZ, emax_x(NX)>;
+    using P = typename S::P;
     static constexpr int E = S::E;
     static constexpr int THREADS = S::THREADS;
     static constexpr int TILE = NX * WZ;                       // modes per tile

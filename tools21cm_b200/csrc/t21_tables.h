@@ -31,11 +31,11 @@ inline void unit_root(long long num, long long den, double& c, double& s) {
     s = -sq;  // exp(-i theta) = cos - i sin
 }
 
-// per-stage tables of Plan<n>: stage s>=1, entry [(k-1)*Ns + m] = exp(-2 pi i k m / (Ns*R))
+// per-stage tables of Plan<n, emax>: stage s>=1, entry [(k-1)*Ns + m] = exp(-2 pi i k m / (Ns*R))
 template <typename T>
-std::vector<cx<T>> build_stage_twiddles(int n) {
+std::vector<cx<T>> build_stage_twiddles(int n, int emax) {
     std::vector<cx<T>> tab;
-    const int e = n < plan_emax(n) ? n : plan_emax(n);
+    const int e = n < emax ? n : emax;
     int rem = n, nsv = 1, s = 0;
     while (rem > 1) {
         const int r = rem < e ? rem : e;

@@ -382,6 +382,54 @@ struct XPass {
             klos_c = ldg(B.tab_losf + il);
             nyq_c = il == B.nyq_idx[los];
         }
+#if T21_DEVICE_CODE
+        if constexpr (THREADS % 32 == 0 && E % 2 == 0) {
+            // kx and -kx have the same kx^2, hence the same s, |mu| and (unless the line of sight is x)
+            // the same signed mu: rows ix and NX-ix share ONE classification.  The warp sweeps the lower
+            // half of kx and adds both powers; row 0 pairs with itself, the Nyquist row is done at the end.
+            if (MU != 2 || los != 0) {
+                constexpr int EH = E / 2;
+                const int r0 = (q / RPI) * (EH * RPI) + (q % RPI);
+                const T* pt2 = ptile(smem) + zl;
+                auto step = [&](int ix, bool lane_on, bool self) {
+                    const int iq = self ? ix : NX - ix;
+                    const T plo = pt2[ix * WZ], phi = pt2[iq * WZ];
+                    const double pw = (double)((self ? plo : plo + phi) * wf);
+                    const unsigned wn = self ? wt : 2u * wt;
+                    bool valid = lane_on && active;
+                    if (MU) valid = valid && !(line_fixed && (los == 0 || ix == zx));
+                    const float sh = ldg(B.tab_sf[0] + ix) + c_yz;
+                    float muh = 0.f;
+                    if (MU) muh = (los == 0 ? ldg(B.tab_losf + ix) : klos_c) * fast_rsqrt(sh);
+                    const float m_own = MU == 1 ? fabsf(muh) : muh;
+                    if (!warpbins_fast<(MU != 0)>(r.acc[0], sh, m_own, pw, wn, valid)) {
+                        int w1 = 1;
+                        const int bin = valid ? exact_bin(p, ix, iy, iz, has_twin, 0, sh, w1) : -1;
+                        const unsigned wx = self ? (unsigned)w1 : 2u * (unsigned)w1;
+                        warpbins_slow(r.acc[0], hist, B, nb, bin, (w1 == (int)wt) ? pw : (double)(self ? plo : plo + phi),
+                                      wx, valid);
+                    }
+                    if constexpr (MU == 2) {                  // los != 0 here: the twin's mu is the same for ix and NX-ix
+                        const bool tv = valid && has_twin;
+                        const float m_tw = nyq_c ? muh : -muh;
+                        const double pt_w = (double)(self ? plo : plo + phi);
+                        if (!warpbins_fast<true>(r.acc[1], sh, m_tw, pt_w, self ? 1u : 2u, tv)) {
+                            int w1 = 1;
+                            const int bin = tv ? exact_bin(p, ix, iy, iz, has_twin, 1, sh, w1) : -1;
+                            warpbins_slow(r.acc[1], hist, B, nb, bin, pt_w, self ? 1u : 2u, tv);
+                        }
+                    }
+                };
+#pragma unroll 1
+                for (int it = 0; it < EH; ++it) {
+                    const int ix = r0 + it * RPI;
+                    step(ix, true, ix == 0);
+                }
+                if (tid < 32) step(NX / 2, q == 0, true);     // warp 0: the self-conjugate Nyquist row
+                return;
+            }
+        }
+#endif
         const T* pt = ptile(smem) + ix0 * WZ + zl;
         const float* sfx = B.tab_sf[0] + ix0;
         const float* lfx = B.tab_losf + ix0;

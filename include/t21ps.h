@@ -130,6 +130,13 @@ T21_API int t21_slab_stage2(const t21_plan* plan_cols, const void* w1, const voi
                             const t21_binspec* spec, double* sums_out, long long* counts_out,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* power_spectrum_nd / cross_power_spectrum_nd of a slab-sharded cube: the scaled power of this rank's
+ * rows as the computed HALF spectrum in FFT order, out_half[nx][ny/P][nz/2+1].  The caller assembles
+ * the fftshifted rows: the kz < 0 half of row ky is the mirrored half of row -ky, held by another rank. */
+T21_API int t21_slab_stage2_nd(const t21_plan* plan_cols, const void* w1, const void* w2_or_null, int iy0,
+                               int ny_global, const void* offset1, const void* offset2, double scale,
+                               void* out_half, int out_dtype, void* stream);
+
 /* radial_average / mu_binning (power_spectrum.py:98-134, 380-435) on a caller-supplied
  * fftshifted array of spec->n elements (1-/2-D arrays are padded with leading 1s). */
 T21_API int t21_bin_only(const void* p_shifted, int dtype, const t21_binspec* spec, double* sums_out,

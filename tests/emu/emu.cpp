@@ -72,7 +72,7 @@ static void xpass_mu(const cx<T>* w0, const cx<T>* w1, int ny, int nz, int pitch
     p.offset[0] = off0; p.offset[1] = off1;
     p.ntot = (double)NX * ny * nz;
     if (spec) p.bins = *spec;
-    p.nd_out = nd_out; p.nd_f64 = nd_f64; p.scale = scale;
+    p.nd_out = nd_out; p.nd_f64 = nd_f64; p.nd_half = 0; p.scale = scale;
     std::vector<cx<T>> smem(K::SMEM_BYTES / sizeof(cx<T>) + 1);
     const int nb = spec ? spec->nk * (spec->nmu > 0 ? spec->nmu : 1) : 1;
     // persistent CTAs: each keeps its run accumulators and histogram across its tiles

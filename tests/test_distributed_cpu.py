@@ -46,6 +46,23 @@ class NumpyBackend:
         return spec, torch.from_numpy(sums), torch.from_numpy(counts)
 
 
+def _stage2_nd(self, cols, iy0, ny_global, nz, offsets, scale, out_dtype):
+    nzh = nz // 2 + 1
+    ntot = cols[0].shape[0] * ny_global * nz
+    fs = []
+    for c, off in zip(cols, offsets):
+        f = np.fft.fft(c.numpy()[:, :, :nzh], axis=0)
+        if iy0 == 0 and off is not None:
+            f[0, 0, 0] += float(off.item()) * ntot
+        fs.append(f)
+    power = (fs[0].real ** 2 + fs[0].imag ** 2) if len(fs) == 1 else \
+        (fs[0].real * fs[1].real + fs[0].imag * fs[1].imag)
+    return torch.from_numpy(power * scale).to(out_dtype)
+
+
+NumpyBackend.stage2_nd = _stage2_nd
+
+
 def _worker(rank, world, port, q):
     sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")]
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -80,6 +97,16 @@ def _worker(rank, world, port, q):
         mu_o = ps_oracle.power_spectrum_mu(cube.astype(np.float64), los_axis=1, mubins=4, kbins=3, box_dims=30.0,
                                            return_n_modes=True, absolute_mus=False)
         out["mu"] = (np.array_equal(mu[3], mu_o[3]), bool(np.allclose(mu[0], mu_o[0], rtol=1e-9, equal_nan=True)))
+        # ---- n-D output, left sharded by rows of y ----
+        rows, yidx = D.sharded_cross_power_spectrum_nd(a, b, 30.0, backend=NumpyBackend())
+        full = ps_oracle.cross_power_spectrum_nd(cube.astype(np.float64), other, 30.0)
+        out["nd"] = float(np.abs(rows.numpy() - full[:, yidx.numpy(), :]).max() / np.abs(full).max())
+        odd = np.random.default_rng(9).standard_normal((8, 6, 7))          # odd z: no Nyquist plane
+        nx8 = odd.shape[0] // world
+        rows, yidx = D.sharded_power_spectrum_nd(torch.from_numpy(odd[rank * nx8:(rank + 1) * nx8].copy()),
+                                                 [10.0, 20.0, 30.0], backend=NumpyBackend())
+        full = ps_oracle.power_spectrum_nd(odd, [10.0, 20.0, 30.0])
+        out["nd_odd"] = float(np.abs(rows.numpy() - full[:, yidx.numpy(), :]).max() / np.abs(full).max())
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
@@ -110,3 +137,4 @@ def test_world_size_2_gloo():
         assert counts_ok and centres_ok and err < 1e-5
         assert out["x1d"][0] and out["x1d"][1] < 1e-10
         assert out["mu"] == (True, True)
+        assert out["nd"] < 1e-12 and out["nd_odd"] < 1e-12

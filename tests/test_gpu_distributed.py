@@ -72,6 +72,22 @@ def test_slab_stages_cross_and_mu_fp64():
     np.testing.assert_allclose(ps.reshape(pm_o.shape), pm_o, rtol=1e-10, equal_nan=True)
 
 
+def test_sharded_nd_single_rank_equals_nd():
+    """world = 1: the slab stages, the half-spectrum store and the mirror-row assembly on one GPU."""
+    import torch
+    import tools21cm_b200 as t2c
+    from tools21cm_b200 import distributed as D, synthetic
+    x = synthetic.toy_dt_cube_torch((64, 32, 128), seed=4)
+    y = synthetic.gaussian_cube_torch((64, 32, 128), seed=5)
+    rows, yidx = D.sharded_power_spectrum_nd(x, [100.0, 50.0, 200.0])
+    full = t2c.power_spectrum_nd(x, box_dims=[100.0, 50.0, 200.0])
+    assert torch.equal(yidx, (torch.arange(32) + 16) % 32)
+    assert (rows - full[:, yidx.to(full.device), :]).abs().max() <= 2e-6 * full.max()
+    rows, yidx = D.sharded_cross_power_spectrum_nd(x.double(), y.double(), [100.0, 50.0, 200.0])
+    full = t2c.cross_power_spectrum_nd(x.double(), y.double(), [100.0, 50.0, 200.0])
+    assert (rows - full[:, yidx.to(full.device), :]).abs().max() <= 1e-12 * full.abs().max()
+
+
 def _nccl_worker(rank, world, port, q):
     sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")]
     import torch
@@ -91,6 +107,13 @@ def _nccl_worker(rank, world, port, q):
                                                        return_n_modes=True)
         ok = bool(np.array_equal(nm, nm_o) and np.array_equal(ks, ks_o) and
                   np.allclose(ps, ps_o, rtol=1e-5, equal_nan=True))
+        # n-D cross spectrum left sharded by rows of y (BASELINE.json config 5, small)
+        other = synthetic.gaussian_cube(cube.shape, seed=22)
+        oslab = torch.from_numpy(other[rank * nxl:(rank + 1) * nxl].copy()).cuda()
+        rows, yidx = D.sharded_cross_power_spectrum_nd(slab, oslab, [300.0, 150.0, 150.0])
+        full = ps_oracle.cross_power_spectrum_nd(cube, other, [300.0, 150.0, 150.0])
+        err = np.abs(rows.cpu().numpy() - full[:, yidx.numpy(), :]).max() / np.abs(full).max()
+        ok = ok and bool(err < 2e-6)
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()

@@ -145,6 +145,8 @@ def load():
     lib.t21_slab_stage1.restype = i32
     lib.t21_slab_stage2.argtypes = [vp, vp, vp, i32, i32, vp, vp, C.POINTER(BinSpecC), vp, vp, vp, sz, vp]
     lib.t21_slab_stage2.restype = i32
+    lib.t21_slab_stage2_nd.argtypes = [vp, vp, vp, i32, i32, vp, vp, dbl, vp, i32, vp]
+    lib.t21_slab_stage2_nd.restype = i32
     lib.t21_bin_only.argtypes = [vp, i32, C.POINTER(BinSpecC), vp, vp, vp, sz, vp]
     lib.t21_bin_only.restype = i32
     lib.t21_bin_only_workspace_bytes.argtypes = [C.POINTER(BinSpecC)]

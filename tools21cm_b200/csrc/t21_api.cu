@@ -395,6 +395,30 @@ int t21_slab_stage2(const t21_plan* p, const void* w1, const void* w2, int iy0, 
     return rc;
 }
 
+// n-D output of a slab-sharded cube: the scaled power of this rank's rows, HALF spectrum only,
+// FFT order: out[nx][ny/P][nz/2+1].  The caller assembles the fftshifted rows (the kz < 0 half of a
+// row is the mirrored half of row -ky, which another rank holds; tools21cm_b200/distributed.py).
+int t21_slab_stage2_nd(const t21_plan* p, const void* w1, const void* w2, int iy0, int ny_global, const void* offset1,
+                       const void* offset2, double scale, void* out_half, int out_dtype, void* stream) {
+    if (!p || !w1 || !out_half) { set_error("null argument"); return T21_EINVAL; }
+    if (!p->fast[0]) { set_error("slab mode needs a power-of-two x axis"); return T21_EINVAL; }
+    if (out_dtype != T21_F32 && out_dtype != T21_F64) { set_error("bad output dtype"); return T21_EINVAL; }
+    if (iy0 < 0 || iy0 + p->n[1] > ny_global) { set_error("slab geometry mismatch"); return T21_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    XArgs a;
+    memset(&a, 0, sizeof(a));
+    a.w[0] = w1; a.w[1] = w2; a.nf = w2 ? 2 : 1;
+    a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch; a.xb = 0; a.iy0 = iy0;
+    a.tw = p->tw[0];
+    a.offset[0] = offset1; a.offset[1] = offset2;
+    a.ntot = (double)p->n[0] * ny_global * p->n[2];
+    a.nd_out = out_half; a.nd_f64 = out_dtype == T21_F64; a.nd_half = 1; a.scale = scale;
+    a.max_grid = p->max_grid;
+    const int rc = p->dtype == T21_F32 ? launch_xpass_f32_nd(a, st) : launch_xpass_f64_nd(a, st);
+    prof_mark(st, SLOT_X);
+    return rc;
+}
+
 size_t t21_bin_only_workspace_bytes(const t21_binspec* spec) {
     if (!spec) return 0;
     const int nbins = spec->nk * (spec->nmu > 0 ? spec->nmu : 1);

@@ -19,7 +19,7 @@ struct XArgs {
     const void* w[2]; int nf; int nx, ny, nz, nzh, pitch; int xb; int iy0;
     const void* tw; const void* offset[2]; double ntot;
     const t21_binspec* bins;                 // MODE_BIN
-    void* nd_out; int nd_f64; double scale;  // MODE_ND
+    void* nd_out; int nd_f64; int nd_half; double scale;  // MODE_ND
     // histogram plumbing (MODE_BIN)
     int nbins; int hist_global;              // 1: accumulate straight into gsum/gcnt
     double* part_sum; unsigned* part_cnt;    // [grid][nbins] per-CTA partials

@@ -134,7 +134,7 @@ inline int launch_x(XArgs& a, cudaStream_t st) {
     p.offset[1] = (const T*)a.offset[1];
     p.ntot = a.ntot;
     if (a.bins) p.bins = *a.bins;
-    p.nd_out = a.nd_out; p.nd_f64 = a.nd_f64; p.scale = a.scale;
+    p.nd_out = a.nd_out; p.nd_f64 = a.nd_f64; p.nd_half = a.nd_half; p.scale = a.scale;
 
     const bool is_bin = a.bins != nullptr;
     const int hk = !is_bin ? 2 : (a.hist_global ? 1 : 0);

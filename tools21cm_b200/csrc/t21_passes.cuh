@@ -255,8 +255,9 @@ struct XPass {
         const T* offset[2];   // device scalars (mean offsets) or null
         double ntot;          // nx*ny*nz, for the analytic DC repair
         t21_binspec bins;     // MODE_BIN
-        void* nd_out;         // MODE_ND: [NX][ny][nz] fftshifted
+        void* nd_out;         // MODE_ND: [NX][ny][nz] fftshifted, or [NX][ny][nz/2+1] in FFT order (nd_half)
         int nd_f64;           // MODE_ND: output dtype
+        int nd_half;          // MODE_ND: store only the computed half spectrum, unshifted (slab-sharded cubes)
         double scale;         // MODE_ND
     };
     struct Regs {
@@ -326,7 +327,7 @@ struct XPass {
                     }
                 });
         } else {
-            epilogue(p, tid, iy, iz, zl, active, r, smem, hist);
+            epilogue(p, tid, iy, iy_loc, iz, zl, active, r, smem, hist);
         }
     }
 
@@ -347,12 +348,12 @@ struct XPass {
     }
 
     template <class Hist>
-    static T21_HD void epilogue(const Params& p, int tid, int iy, int iz, int zl, bool active, Regs& r,
+    static T21_HD void epilogue(const Params& p, int tid, int iy, int iy_loc, int iz, int zl, bool active, Regs& r,
                                 cx<T>* smem, Hist& hist) {
         if constexpr (MODE == MODE_BIN) {
             epilogue_bin(p, tid, iy, iz, zl, active, r, smem, hist);
         } else {
-            epilogue_nd(p, tid, iy, iz, zl, active, smem);
+            epilogue_nd(p, tid, iy, iy_loc, iz, zl, active, smem);
         }
     }
 
@@ -478,7 +479,7 @@ struct XPass {
         }
     }
 
-    static T21_HD void epilogue_nd(const Params& p, int tid, int iy, int iz, int zl, bool active, cx<T>* smem) {
+    static T21_HD void epilogue_nd(const Params& p, int tid, int iy, int iy_loc, int iz, int zl, bool active, cx<T>* smem) {
         const T* pt = ptile(smem);
         const int q = tid / WZ;
         const int ix0 = (q / RPI) * (E * RPI) + (q % RPI);
@@ -492,6 +493,11 @@ struct XPass {
             double pw = (double)pt[ix * WZ + zl];
             if ((ix | iy | iz) == 0) pw = *dc_slot(smem);
             const double val = pw * p.scale;
+            if (p.nd_half) {
+                const long long oh = ((long long)ix * p.ny + iy_loc) * p.nzh + iz;
+                if (p.nd_f64) ((double*)p.nd_out)[oh] = val; else ((float*)p.nd_out)[oh] = (float)val;
+                continue;
+            }
             const int hy = p.ny / 2, hz = p.nz / 2;
             const int sx = ix + NX / 2 - (ix + NX / 2 >= NX ? NX : 0);
             const int sy = iy + hy - (iy + hy >= p.ny ? p.ny : 0);

@@ -122,6 +122,25 @@ class CudaBackend:
         return spec, sums, counts
 
 
+    def stage2_nd(self, cols, iy0, ny_global, nz, offsets, scale, out_dtype):
+        """Scaled power of this rank's rows, half spectrum, FFT order: [nx][ny/P][nz/2+1]."""
+        import torch
+        lib = _lib.load()
+        w = cols[0]
+        dev = self._ps._device(w.device.index)
+        code = _lib.T21_F32 if w.dtype == torch.complex64 else _lib.T21_F64
+        nx, nyl = w.shape[0], w.shape[1]
+        plan = dev.plan((nx, nyl, nz), code)
+        out = torch.empty((nx, nyl, nz // 2 + 1), dtype=out_dtype, device=w.device)
+        o = [t.data_ptr() if t is not None else None for t in offsets] + [None]
+        rc = lib.t21_slab_stage2_nd(plan, cols[0].data_ptr(), cols[1].data_ptr() if len(cols) == 2 else None,
+                                    int(iy0), int(ny_global), o[0], o[1], float(scale), out.data_ptr(),
+                                    _lib.T21_F32 if out_dtype == torch.float32 else _lib.T21_F64,
+                                    self._ps._stream_ptr(torch, w.device.index))
+        _lib.check(rc, "t21_slab_stage2_nd")
+        return out
+
+
 # ------------------------------------------------------------------------------------------
 # the sharded estimator
 # ------------------------------------------------------------------------------------------
@@ -172,16 +191,15 @@ def pipelined_exchange(backend, x, offset, world, group=None, chunks=4):
     return recv4.view(world * nxl, nyl, recv4.shape[3])
 
 
-def _sharded_binned(slabs, spec_key, make_spec, group=None, backend=None, timings=None):
+def _forward(slabs, group, backend):
+    """Common mean offset, stage 1 and the re-partition.  Returns (cols, offsets, world, rank, shape)."""
     import torch
     world, rank = _world(group)
-    backend = backend or CudaBackend()
     x0 = slabs[0]
     nxl, ny, nz = x0.shape
     shape = (nxl * world, ny, nz)
     if ny % world:
         raise ValueError("the y axis (%d) must be divisible by the number of ranks (%d)" % (ny, world))
-    nyl = ny // world
     single = x0.dtype == torch.float32
     offsets = []
     for x in slabs:
@@ -201,11 +219,84 @@ def _sharded_binned(slabs, spec_key, make_spec, group=None, backend=None, timing
             cols.append(pipelined_exchange(backend, x, off, world, group))
         else:
             cols.append(exchange(backend.stage1(x, off), world, group))
+    return cols, offsets, world, rank, shape
+
+
+def _sharded_binned(slabs, spec_key, make_spec, group=None, backend=None, timings=None):
+    backend = backend or CudaBackend()
+    cols, offsets, world, rank, shape = _forward(slabs, group, backend)
+    ny, nz = shape[1], shape[2]
+    nyl = ny // world
     spec, sums, counts = backend.stage2(cols, rank * nyl, ny, nz, offsets, spec_key, lambda: make_spec(shape))
     if world > 1:
         _dist().all_reduce(sums, group=group)
         _dist().all_reduce(counts, group=group)
     return spec, shape, sums.cpu().numpy(), counts.cpu().numpy().astype("float")
+
+
+def _swap(send, peer, rank, group):
+    """Exchange one tensor with `peer` (same shape both ways); a local copy when the peer is this rank."""
+    import torch
+    if peer == rank:
+        return send.clone()
+    dist = _dist()
+    recv = torch.empty_like(send)
+    ops = [dist.P2POp(dist.isend, send, peer, group), dist.P2POp(dist.irecv, recv, peer, group)]
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    return recv
+
+
+def _sharded_nd(slabs, box_dims, out_dtype, group, backend):
+    """fftshifted power of a slab-sharded cube, sharded by rows of y.  Returns (rows, y_index): rows is
+    [nx][ny/P][nz] (x and z complete and shifted), y_index the fftshifted y position of each local row."""
+    import torch
+    backend = backend or CudaBackend()
+    cols, offsets, world, rank, shape = _forward(slabs, group, backend)
+    nx, ny, nz = shape
+    nyl = ny // world
+    half = backend.stage2_nd(cols, rank * nyl, ny, nz, offsets, _bs.volume_scale(shape, box_dims), out_dtype)
+    # The kz < 0 half of row ky is the kz > 0 half of row -ky read at -kx (Hermitian symmetry of a real
+    # cube).  Row 0 of this slab mirrors into row 0 of slab (P - g) mod P, rows 1.. into slab P-1-g reversed.
+    nneg = (nz - 1) // 2
+    pos = half[:, :, 1:nneg + 1]
+    m0 = _swap(pos[:, 0:1].contiguous(), (world - rank) % world, rank, group)
+    if nyl > 1:
+        m1 = _swap(pos[:, 1:].flip(1).contiguous(), world - 1 - rank, rank, group)
+        mirror = torch.cat([m0, m1], dim=1)
+    else:
+        mirror = m0
+    out = torch.empty((nx, nyl, nz), dtype=half.dtype, device=half.device)
+    cz, hx = nz // 2, nx // 2
+    hs = torch.roll(half, hx, 0)
+    out[:, :, cz:cz + nneg + 1] = hs[:, :, 0:nneg + 1]
+    if nz % 2 == 0:
+        out[:, :, 0] = hs[:, :, nz // 2]                                   # Nyquist plane sits at index 0
+    if nneg:
+        neg = torch.roll(torch.roll(mirror.flip(0), 1, 0), hx, 0)          # value at -kx, then the x shift
+        out[:, :, cz - nneg:cz] = neg.flip(2)
+    y_index = (torch.arange(rank * nyl, (rank + 1) * nyl) + ny // 2) % ny
+    return out, y_index
+
+
+def sharded_power_spectrum_nd(x_slab, box_dims=None, group=None, backend=None, out_dtype=None, **kwargs):
+    """``power_spectrum_nd`` of a cube held as x slabs.  Returns ``(rows, y_index)``: this rank's rows
+    ``fftshifted_power[:, y_index, :]`` (all of x and z, already shifted) -- the output stays sharded."""
+    if kwargs.get("boxsize") is not None:
+        box_dims = kwargs.get("boxsize")
+    world, _ = _world(group)
+    gshape = (x_slab.shape[0] * world,) + tuple(x_slab.shape[1:])
+    return _sharded_nd([x_slab], _bs.get_dims(box_dims, gshape), out_dtype or x_slab.dtype, group, backend)
+
+
+def sharded_cross_power_spectrum_nd(a_slab, b_slab, box_dims, group=None, backend=None, out_dtype=None, **kwargs):
+    """``cross_power_spectrum_nd`` of two cubes held as x slabs (BASELINE.json config 5)."""
+    assert tuple(a_slab.shape) == tuple(b_slab.shape)
+    if kwargs.get("boxsize") is not None:
+        box_dims = kwargs.get("boxsize")
+    world, _ = _world(group)
+    gshape = (a_slab.shape[0] * world,) + tuple(a_slab.shape[1:])
+    return _sharded_nd([a_slab, b_slab], _bs.get_dims(box_dims, gshape), out_dtype or a_slab.dtype, group, backend)
 
 
 def _finish(sums, counts, scale):

@@ -174,6 +174,8 @@ def main():
     ap.add_argument("--no-slab", action="store_true", help="skip the slab-sharded leg of multi-GPU runs")
     ap.add_argument("--slab-size", type=int, default=0, help="cube size of the slab-sharded leg (default: --size)")
     ap.add_argument("--slab-cross", action="store_true", help="slab-sharded leg: cross spectrum of two cubes")
+    ap.add_argument("--slab-nd", action="store_true",
+                    help="slab-sharded leg: cross_power_spectrum_nd, output left sharded (BASELINE.json config 5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -313,10 +315,13 @@ def main():
         ns = args.slab_size or n
         nxl = ns // world
         slabs = [synthetic.toy_dt_cube_torch((nxl, ns, ns), seed=4000 + rank, device=dev)]
-        if args.slab_cross:
+        if args.slab_cross or args.slab_nd:
             slabs.append(synthetic.gaussian_cube_torch((nxl, ns, ns), seed=5000 + rank, device=dev))
 
         def slab_step():
+            if args.slab_nd:
+                rows, yidx = D.sharded_cross_power_spectrum_nd(slabs[0], slabs[1], BOX_MPC)
+                return None, None, np.array([float(rows.numel())])
             if args.slab_cross:
                 return D.sharded_cross_power_spectrum_1d(slabs[0], slabs[1], kbins=KBINS, box_dims=BOX_MPC,
                                                          return_n_modes=True)
@@ -351,7 +356,8 @@ def main():
         a_bytes = (world - 1) / world ** 2 * cbytes               # per field, per GPU, per direction
         gbs = a_bytes / 1e9 / (a2a / 1e3) if a2a > 0 else 0.0
         sharded = {"workload": "%s of ONE %d^3 fp32 cube held as %d x slabs" %
-                               ("cross_power_spectrum_1d" if args.slab_cross else "power_spectrum_1d", ns, world),
+                               ("cross_power_spectrum_nd (output sharded by y rows)" if args.slab_nd else
+                                "cross_power_spectrum_1d" if args.slab_cross else "power_spectrum_1d", ns, world),
                    "value": args.steps / (ms_s / 1e3), "unit": "cubes/s", "scaling": "strong",
                    "ms_per_step": ms_s / args.steps,
                    "all_to_all": {"ms": a2a, "bytes_per_gpu_per_direction": a_bytes, "achieved_gbs": gbs,

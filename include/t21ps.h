@@ -149,6 +149,15 @@ T21_API size_t t21_bin_only_workspace_bytes(const t21_binspec* spec);
 T21_API int t21_profile(int enable);
 T21_API int t21_profile_last(float* ms_out, int cap);
 
+/* power_spectrum_2d (power_spectrum.py:177-254): (k_perp, k_par) means of a fftshifted 3-D array.
+ * perp_tab[n_a * n_b] / par_tab[n_nu] give the perpendicular / parallel bin (or -1) of every index
+ * pair across / index along nu_axis; they are built on the host with the reference's own numpy / scipy
+ * digitisation (binspec.build_cyl_tables).  sums_out / counts_out have nperp * npar entries. */
+T21_API int t21_bin_cyl(const void* p_shifted, int dtype, int n0, int n1, int n2, int nu_axis,
+                        const int* perp_tab, const int* par_tab, int nperp, int npar, double* sums_out,
+                        long long* counts_out, void* workspace, size_t workspace_bytes, void* stream);
+T21_API size_t t21_bin_cyl_workspace_bytes(int nperp, int npar);
+
 T21_API const char* t21_last_error(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 T21_API unsigned long long t21_launch_count(void);

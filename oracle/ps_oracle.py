@@ -276,6 +276,50 @@ def cross_power_spectrum_mu(input_array1, input_array2, los_axis=0, mubins=20, k
     return (ps, mu_c, k_c, n_modes) if return_n_modes else (ps, mu_c, k_c)
 
 
+def power_spectrum_2d(input_array, kbins=10, binning="log", box_dims=244 / .7, return_modes=False, nu_axis=2,
+                      window=None, **kwargs):
+    """(k_perp, k_par) means with scipy.stats.binned_statistic_2d.  power_spectrum.py:177-254."""
+    from scipy import stats
+    input_array = apply_window(input_array, window)
+    if type(kbins) == list:
+        binning = None
+    elif np.array(kbins).size == 1:
+        kbins = [kbins, kbins]
+    elif not isinstance(kbins[0], int):
+        binning = None
+    if kwargs.get("boxsize") is not None:
+        box_dims = kwargs.get("boxsize")
+    box_dims = box_lengths(box_dims, input_array.shape)
+    power = power_spectrum_nd(input_array, box_dims)
+    kc = k_components(input_array.shape, box_dims)
+    grids = np.meshgrid(*kc, indexing="ij")
+    perp = [a for a in (0, 1, 2) if a != nu_axis]
+    kz = np.abs(grids[nu_axis])
+    kp = np.sqrt(grids[perp[0]] ** 2 + grids[perp[1]] ** 2)
+    with np.errstate(all="ignore"):
+        if binning is None:
+            kper, kpar = np.array(kbins[0]), np.array(kbins[1])
+        elif binning == "log":
+            kper = np.linspace(np.log10(kp[kp != 0].min()), np.log10(kp.max()), kbins[0] + 1)
+            kpar = np.linspace(np.log10(kz[kz != 0].min()), np.log10(kz.max()), kbins[1] + 1)
+            kp, kz = np.log10(kp), np.log10(kz)
+        elif binning == "linear":
+            kper = np.linspace(kp[kp != 0].min(), kp.max(), kbins[0] + 1)
+            kpar = np.linspace(kz[kz != 0].min(), kz.max(), kbins[1] + 1)
+        kp, kz, power = kp.flatten(), kz.flatten(), power.flatten()
+        res = stats.binned_statistic_2d(x=kp, y=kz, values=power, statistic="mean", bins=[kper, kpar])
+        if binning == "log":
+            kper_mid = np.power(10, 0.5 * (kper[:-1] + kper[1:]))
+            kpar_mid = np.power(10, 0.5 * (kpar[:-1] + kpar[1:]))
+        else:
+            kper_mid = (kper[:-1] + kper[1:]) / 2.0
+            kpar_mid = (kpar[:-1] + kpar[1:]) / 2.0
+        if return_modes:
+            cnt = stats.binned_statistic_2d(x=kp, y=kz, values=None, statistic="count", bins=[kper, kpar])
+            return res.statistic, kper_mid, kpar_mid, cnt.statistic
+    return res.statistic, kper_mid, kpar_mid
+
+
 def dimensionless_ps(data, kbins=100, box_dims=None, binning="log", factor=10):
     """Delta^2(k) = P k^3 / 2 pi^2 interpolated from a finer binning.  power_spectrum.py:536-561."""
     from scipy.interpolate import interp1d

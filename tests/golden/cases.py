@@ -81,6 +81,16 @@ CASES = [
     _c("psnd_32_f64", "power_spectrum_nd", (32,) * 3, seed=44, dtype="float64", box_dims=None),
     _c("xpsnd_32", "cross_power_spectrum_nd", (32,) * 3, field="c2ray", seed=2003, box_dims=200),
     _c("xpsnd_33", "cross_power_spectrum_nd", (33,) * 3, field="grf|grf", seed=45, box_dims=50.0),
+    # ---- (k_perp, k_par) -----------------------------
+    _c("ps2d_64_log", "power_spectrum_2d", (64,) * 3, seed=61, kbins=8, box_dims=200.0, return_modes=True),
+    _c("ps2d_64_lin_nu0", "power_spectrum_2d", (64,) * 3, field="toy", seed=62, kbins=6, binning="linear",
+       box_dims=244 / H, nu_axis=0, return_modes=True),
+    _c("ps2d_noncubic_nu1", "power_spectrum_2d", (32, 64, 16), seed=63, kbins=5, box_dims=[80.0, 100.0, 40.0],
+       nu_axis=1, return_modes=True),
+    _c("ps2d_33_odd", "power_spectrum_2d", (33,) * 3, seed=64, dtype="float64", kbins=5, box_dims=50.0,
+       return_modes=True),
+    _c("ps2d_edges", "power_spectrum_2d", (32,) * 3, seed=65, dtype="float64",
+       kbins=["edges:0,0.2,0.5,1.0,2.0", "edges:0,0.3,0.9,2.0"], box_dims=100.0, return_modes=True),
     # ---- stand-alone binning of caller-supplied fftshifted arrays ----------
     _c("ravg_3d", "radial_average", (32,) * 3, field="positive", seed=51, box_dims=[200.0] * 3, kbins=8),
     _c("ravg_3d_lin", "radial_average", (33, 32, 16), field="positive", seed=52, box_dims=[100.0, 90.0, 40.0],
@@ -126,5 +136,7 @@ def build_kwargs(case):
     for key, val in case["kw"].items():
         if isinstance(val, str) and val.startswith("edges:"):
             val = np.array([float(t) for t in val[6:].split(",")])
+        if isinstance(val, list) and val and isinstance(val[0], str) and val[0].startswith("edges:"):
+            val = [np.array([float(t) for t in v[6:].split(",")]) for v in val]
         kw[key] = val
     return kw

@@ -24,6 +24,8 @@ REFERENCE_SIGNATURES = {
     "mu_binning": "(powerspectrum, los_axis=0, mubins=20, kbins=10, box_dims=None, weights=None, "
                   "exclude_zero_modes=True, binning='log', absolute_mus=True)",
     "dimensionless_ps": "(data, kbins=100, box_dims=None, binning='log', factor=10)",
+    "power_spectrum_2d": "(input_array, kbins=10, binning='log', box_dims=348.5714285714286, return_modes=False, "
+                         "nu_axis=2, window=None, **kwargs)",
 }
 
 

@@ -62,7 +62,11 @@ def test_api_matches_reference_golden(t2c, case, golden):
         assert np.asarray(got).shape == ref.shape
         assert np.asarray(got).dtype == ref.dtype
     rtol, atol = tolerances(case, want[0])
-    if case["fn"] in BINNED or case["fn"] in ("radial_average", "mu_binning"):
+    if case["fn"] == "power_spectrum_2d":
+        assert np.array_equal(res[3], want[3]), "n_modes differ from the reference"
+        assert np.array_equal(res[1], want[1]) and np.array_equal(res[2], want[2])
+        np.testing.assert_allclose(res[0], want[0], rtol=rtol, equal_nan=True)
+    elif case["fn"] in BINNED or case["fn"] in ("radial_average", "mu_binning"):
         assert np.array_equal(res[-1], want[-1]), "n_modes differ from the reference"
         for got, ref in zip(res[1:-1], want[1:-1]):
             assert np.array_equal(got, ref), "bin centres differ from the reference"

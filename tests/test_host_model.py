@@ -99,3 +99,34 @@ def test_kbins_type_rules():
         bs.build_binspec((16, 16, 16), [10.0] * 3, np.array([0.3, 0.2, 0.5]))
     spec = bs.build_binspec((16, 16, 16), [10.0] * 3, np.int64(4) * np.ones(3).cumsum())
     assert spec.nk == 2  # np.int64 scalars/arrays are edges, only a Python int asks for automatic bins
+
+
+CYL = [c for c in CASES if c["fn"] == "power_spectrum_2d"]
+
+
+@pytest.mark.parametrize("case", CYL, ids=[c["id"] for c in CYL])
+def test_cylindrical_tables_reproduce_reference_counts(case, golden):
+    """power_spectrum_2d: the separable (k_perp, k_par) bin tables, applied to the oracle's n-D power with
+    plain numpy, must give the reference's counts exactly and its means to rounding."""
+    from oracle import ps_oracle
+    x = build_inputs(case)[0]
+    kw = build_kwargs(case)
+    box = bs.get_dims(kw.get("box_dims", 244 / 0.7), x.shape)
+    nu = kw.get("nu_axis", 2)
+    cyl = bs.build_cyl_tables(x.shape, box, kw["kbins"], binning=kw.get("binning", "log"), nu_axis=nu)
+    power = ps_oracle.power_spectrum_nd(x, box)
+    idx = np.indices(x.shape)
+    perp = [a for a in (0, 1, 2) if a != nu]
+    bp = cyl.perp_tab[idx[perp[0]], idx[perp[1]]]
+    bz = cyl.par_tab[idx[nu]]
+    ok = (bp >= 0) & (bz >= 0)
+    flat = bp[ok] * cyl.npar + bz[ok]
+    sums = np.zeros(cyl.nperp * cyl.npar)
+    cnt = np.zeros(cyl.nperp * cyl.npar)
+    np.add.at(sums, flat, power[ok])
+    np.add.at(cnt, flat, 1)
+    want = golden_outputs(golden, case["id"])
+    assert np.array_equal(cnt.reshape(want[3].shape), want[3])
+    assert np.array_equal(cyl.kper_mid, want[1]) and np.array_equal(cyl.kpar_mid, want[2])
+    with np.errstate(all="ignore"):
+        np.testing.assert_allclose((sums / cnt).reshape(want[0].shape), want[0], rtol=1e-12, equal_nan=True)

@@ -9,7 +9,7 @@ device, is missing.
 """
 from .power_spectrum import (  # noqa: F401
     power_spectrum_nd, cross_power_spectrum_nd, radial_average, power_spectrum_1d, cross_power_spectrum_1d,
-    power_spectrum_mu, cross_power_spectrum_mu, mu_binning, dimensionless_ps, anisotropy_ratio_r_mu,
+    power_spectrum_mu, cross_power_spectrum_mu, mu_binning, power_spectrum_2d, dimensionless_ps, anisotropy_ratio_r_mu,
     get_k, get_kbins, apply_window, set_precision,
     _get_k, _get_mu, _get_kbins, _get_dims, _get_nonzero_idx,
 )

@@ -151,6 +151,10 @@ def load():
     lib.t21_bin_only.restype = i32
     lib.t21_bin_only_workspace_bytes.argtypes = [C.POINTER(BinSpecC)]
     lib.t21_bin_only_workspace_bytes.restype = sz
+    lib.t21_bin_cyl.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp, vp, sz, vp]
+    lib.t21_bin_cyl.restype = i32
+    lib.t21_bin_cyl_workspace_bytes.argtypes = [i32, i32]
+    lib.t21_bin_cyl_workspace_bytes.restype = sz
     lib.t21_profile.argtypes = [i32]
     lib.t21_profile.restype = i32
     lib.t21_profile_last.argtypes = [C.POINTER(C.c_float), i32]

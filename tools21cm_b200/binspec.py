@@ -345,3 +345,69 @@ def build_binspec(shape, box_dims, kbins, *, binning="log", breakpoint=0.1, mubi
                    absolute_mus=bool(absolute_mus), exclude_zero=excl, zero_idx=zero3, nyq_idx=nyq3,
                    s_nan=float(s_nan), k_lut=k_lut, k_lut_u0=u0, k_lut_inv=inv, mu_lut=mu_lut,
                    k_lo_f=k_lo_f, k_hi_f=k_hi_f, mu_lo_f=mu_lo_f, mu_hi_f=mu_hi_f, order=order)
+
+
+# --------------------------------------------------------------------------
+# (k_perp, k_par) tables for power_spectrum_2d
+# --------------------------------------------------------------------------
+@dataclass
+class CylSpec:
+    nperp: int
+    npar: int
+    perp_tab: np.ndarray      # int32 [n_a, n_b]: perpendicular bin of every index pair across the line of sight, -1 = none
+    par_tab: np.ndarray       # int32 [n_nu]: parallel bin of every index along the line of sight, -1 = none
+    kper_mid: np.ndarray
+    kpar_mid: np.ndarray
+    nu_axis: int
+
+
+def build_cyl_tables(shape, box_dims, kbins, binning="log", nu_axis=2):
+    """Bin tables of the reference's power_spectrum_2d (power_spectrum.py:209-254).
+
+    A mode's bin is separable, so the reference's digitisation (scipy.stats.binned_statistic_2d, i.e.
+    np.digitize plus scipy's right-edge rule) is run HERE, with the same scipy routine, on the n_a*n_b distinct
+    k_perp values and the n_nu distinct k_par values instead of on all N^3 modes.  The device only looks the
+    two tables up, so counts are identical to the reference by construction, whatever the bins."""
+    from scipy import stats
+    if len(shape) != 3:
+        raise ValueError("power_spectrum_2d needs a 3-D array")
+    if type(kbins) == list:                      # :211-216, including the reference's dispatch quirks
+        binning = None
+    elif np.array(kbins).size == 1:
+        kbins = [kbins, kbins]
+    elif not isinstance(kbins[0], int):
+        binning = None
+    kax = [k_axis_shifted(shape[d], box_dims[d], 3) for d in range(3)]
+    xy = [0, 1, 2]
+    xy.remove(nu_axis)
+    kz = np.abs(kax[nu_axis])
+    kp = np.sqrt(kax[xy[0]][:, None] ** 2 + kax[xy[1]][None, :] ** 2)
+    with np.errstate(all="ignore"):
+        if binning is None:
+            kper = np.array(kbins[0])
+            kpar = np.array(kbins[1])
+        elif binning == "log":
+            kper = np.linspace(np.log10(kp[kp != 0].min()), np.log10(kp.max()), kbins[0] + 1)
+            kpar = np.linspace(np.log10(kz[kz != 0].min()), np.log10(kz.max()), kbins[1] + 1)
+            kp, kz = np.log10(kp), np.log10(kz)
+        elif binning == "linear":
+            kper = np.linspace(kp[kp != 0].min(), kp.max(), kbins[0] + 1)
+            kpar = np.linspace(kz[kz != 0].min(), kz.max(), kbins[1] + 1)
+        else:
+            raise UnboundLocalError("cannot access local variable 'kper'")     # what the reference does
+        # the same digitisation scipy applies per dimension inside binned_statistic_2d
+        rp = stats.binned_statistic(kp.ravel(), None, statistic="count", bins=kper)
+        rz = stats.binned_statistic(kz.ravel(), None, statistic="count", bins=kpar)
+    nperp, npar = len(rp.bin_edges) - 1, len(rz.bin_edges) - 1
+    bp = rp.binnumber.astype(np.int64) - 1
+    bz = rz.binnumber.astype(np.int64) - 1
+    perp_tab = np.where((bp >= 0) & (bp < nperp), bp, -1).astype(np.int32).reshape(kp.shape)
+    par_tab = np.where((bz >= 0) & (bz < npar), bz, -1).astype(np.int32)
+    if binning == "log":
+        kper_mid = np.power(10, 0.5 * (kper[:-1] + kper[1:]))
+        kpar_mid = np.power(10, 0.5 * (kpar[:-1] + kpar[1:]))
+    else:
+        kper_mid = (kper[:-1] + kper[1:]) / 2.0
+        kpar_mid = (kpar[:-1] + kpar[1:]) / 2.0
+    return CylSpec(nperp=nperp, npar=npar, perp_tab=np.ascontiguousarray(perp_tab),
+                   par_tab=np.ascontiguousarray(par_tab), kper_mid=kper_mid, kpar_mid=kpar_mid, nu_axis=nu_axis)

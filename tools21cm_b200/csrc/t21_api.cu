@@ -449,4 +449,36 @@ int t21_bin_only(const void* p_shifted, int dtype, const t21_binspec* spec, doub
     return T21_OK;
 }
 
+size_t t21_bin_cyl_workspace_bytes(int nperp, int npar) {
+    const long long nbins = (long long)nperp * npar;
+    if (nbins < 1) return 0;
+    if (nbins > kSmemHistMaxBins) return 256;
+    const size_t g = (size_t)device_sm_count() * 8;
+    return align_up(g * nbins * sizeof(double), 256) + align_up(g * nbins * sizeof(unsigned), 256);
+}
+
+int t21_bin_cyl(const void* p_shifted, int dtype, int n0, int n1, int n2, int nu_axis, const int* perp_tab,
+                const int* par_tab, int nperp, int npar, double* sums_out, long long* counts_out, void* workspace,
+                size_t workspace_bytes, void* stream) {
+    if (!p_shifted || !perp_tab || !par_tab || !sums_out || !counts_out || !workspace) { set_error("null argument"); return T21_EINVAL; }
+    if (dtype != T21_F32 && dtype != T21_F64) { set_error("bad dtype %d", dtype); return T21_EINVAL; }
+    if (nu_axis < 0 || nu_axis > 2 || n0 < 1 || n1 < 1 || n2 < 1 || nperp < 1 || npar < 1) { set_error("bad geometry"); return T21_EINVAL; }
+    const int nbins = nperp * npar;
+    const size_t need = t21_bin_cyl_workspace_bytes(nperp, npar);
+    if (workspace_bytes < need) { set_error("workspace too small: %zu < %zu bytes", workspace_bytes, need); return T21_ENOMEM; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int max_grid = device_sm_count() * 8;
+    double* part_sum = (double*)workspace;
+    unsigned* part_cnt = (unsigned*)((unsigned char*)workspace + align_up((size_t)max_grid * nbins * sizeof(double), 256));
+    const bool global = nbins > kSmemHistMaxBins;
+    if (global)
+        if (int rc = launch_zero_hist(sums_out, counts_out, nbins, st)) return rc;
+    int grid = 0;
+    if (int rc = launch_bin_cyl(p_shifted, dtype, n0, n1, n2, nu_axis, perp_tab, par_tab, nperp, npar, part_sum, part_cnt,
+                                max_grid, sums_out, counts_out, &grid, st))
+        return rc;
+    if (!global) return launch_reduce_partials(part_sum, part_cnt, grid, nbins, sums_out, counts_out, st);
+    return T21_OK;
+}
+
 }  // extern "C"

@@ -139,6 +139,90 @@ bin_only_kernel(const T* __restrict__ p, const __grid_constant__ t21_binspec B, 
     }
 }
 
+// ---- (k_perp, k_par) binning of a full fftshifted 3-D array (power_spectrum_2d) -----------------------
+// The bin of a mode is separable: the perpendicular bin depends on the two indices across the line of
+// sight, the parallel bin on the index along it.  Both are host-built tables (binspec.build_cyl_tables
+// runs the reference's own numpy/scipy digitisation on the n_a*n_b + n_nu distinct values), so the
+// kernel only looks them up: mode counts are identical to the reference by construction.
+template <typename T, int HK>
+__global__ void __launch_bounds__(kBinThreads)
+bin_cyl_kernel(const T* __restrict__ p, int n0, int n1, int n2, int nu_axis, const int* __restrict__ perp_tab,
+               const int* __restrict__ par_tab, int npar, int nbins, double* __restrict__ part_sum,
+               unsigned* __restrict__ part_cnt, double* gsum, unsigned long long* gcnt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* hs = reinterpret_cast<double*>(smem_raw);
+    unsigned* hc = reinterpret_cast<unsigned*>(hs + nbins);
+    if (HK == 0) {
+        for (int b = threadIdx.x; b < nbins; b += kBinThreads) { hs[b] = 0.0; hc[b] = 0u; }
+        __syncthreads();
+    }
+    const long long total = (long long)n0 * n1 * n2;
+    const long long nruns = (total + kRun - 1) / kRun;
+    const int nb_perp_inner = nu_axis == 2 ? n1 : n2;      // length of the second perpendicular axis
+    RunAcc acc;
+    run_init(acc);
+    SmemHist sh{hs, hc};
+    GlobalHist gh{gsum, gcnt};
+    for (long long run = (long long)blockIdx.x * kBinThreads + threadIdx.x; run < nruns;
+         run += (long long)gridDim.x * kBinThreads) {
+        long long o = run * kRun;
+        int iz = (int)(o % n2);
+        long long t = o / n2;
+        int iy = (int)(t % n1);
+        int ix = (int)(t / n1);
+        const long long end = (o + kRun < total) ? o + kRun : total;
+        for (; o < end; ++o) {
+            const int inu = nu_axis == 0 ? ix : (nu_axis == 1 ? iy : iz);
+            const int ia = nu_axis == 0 ? iy : ix;
+            const int ib = nu_axis == 2 ? iy : iz;
+            const int bp = ldg(perp_tab + (long long)ia * nb_perp_inner + ib);
+            const int bz = ldg(par_tab + inu);
+            const int bin = (bp >= 0 && bz >= 0) ? bp * npar + bz : -1;
+            const double v = (double)p[o];
+            if (HK == 0) run_add(acc, sh, bin, v, 1);
+            else run_add(acc, gh, bin, v, 1);
+            if (++iz == n2) { iz = 0; if (++iy == n1) { iy = 0; ++ix; } }
+        }
+    }
+    if (HK == 0) {
+        run_flush(acc, sh);
+        __syncthreads();
+        for (int b = threadIdx.x; b < nbins; b += kBinThreads) {
+            part_sum[(size_t)blockIdx.x * nbins + b] = hs[b];
+            part_cnt[(size_t)blockIdx.x * nbins + b] = hc[b];
+        }
+    } else {
+        run_flush(acc, gh);
+    }
+}
+
+int launch_bin_cyl(const void* p, int dtype, int n0, int n1, int n2, int nu_axis, const int* perp_tab,
+                   const int* par_tab, int nperp, int npar, double* part_sum, unsigned* part_cnt, int max_grid,
+                   double* gsum, long long* gcnt, int* grid_used, cudaStream_t st) {
+    const int nbins = nperp * npar;
+    const bool global = nbins > kSmemHistMaxBins;
+    const long long total = (long long)n0 * n1 * n2;
+    const long long nruns = (total + kRun - 1) / kRun;
+    long long g = (nruns + kBinThreads - 1) / kBinThreads;
+    const long long cap = (long long)device_sm_count() * 8;
+    if (g > cap) g = cap;
+    if (!global && g > max_grid) g = max_grid;
+    if (g < 1) g = 1;
+    const size_t smem = global ? 0 : (size_t)nbins * (sizeof(double) + sizeof(unsigned));
+    unsigned long long* gc = reinterpret_cast<unsigned long long*>(gcnt);
+    if (dtype == T21_F32) {
+        if (global) bin_cyl_kernel<float, 1><<<(int)g, kBinThreads, smem, st>>>((const float*)p, n0, n1, n2, nu_axis, perp_tab, par_tab, npar, nbins, nullptr, nullptr, gsum, gc);
+        else bin_cyl_kernel<float, 0><<<(int)g, kBinThreads, smem, st>>>((const float*)p, n0, n1, n2, nu_axis, perp_tab, par_tab, npar, nbins, part_sum, part_cnt, nullptr, nullptr);
+    } else {
+        if (global) bin_cyl_kernel<double, 1><<<(int)g, kBinThreads, smem, st>>>((const double*)p, n0, n1, n2, nu_axis, perp_tab, par_tab, npar, nbins, nullptr, nullptr, gsum, gc);
+        else bin_cyl_kernel<double, 0><<<(int)g, kBinThreads, smem, st>>>((const double*)p, n0, n1, n2, nu_axis, perp_tab, par_tab, npar, nbins, part_sum, part_cnt, nullptr, nullptr);
+    }
+    count_launch();
+    T21_CUDA_OK(cudaGetLastError());
+    *grid_used = (int)g;
+    return 0;
+}
+
 int launch_bin_only(const void* p, int dtype, const t21_binspec& spec, double* part_sum, unsigned* part_cnt,
                     int max_grid, double* gsum, long long* gcnt, int* grid_used, cudaStream_t st) {
     const int nbins = spec.nk * (spec.nmu > 0 ? spec.nmu : 1);

@@ -58,6 +58,10 @@ int launch_zero_hist(double* sums, long long* counts, int nbins, cudaStream_t st
 int launch_bin_only(const void* p, int dtype, const t21_binspec& spec, double* part_sum, unsigned* part_cnt,
                     int max_grid, double* gsum, long long* gcnt, int* grid_used, cudaStream_t st);
 
+int launch_bin_cyl(const void* p, int dtype, int n0, int n1, int n2, int nu_axis, const int* perp_tab,
+                   const int* par_tab, int nperp, int npar, double* part_sum, unsigned* part_cnt, int max_grid,
+                   double* gsum, long long* gcnt, int* grid_used, cudaStream_t st);
+
 // error plumbing (t21_api.cu)
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);

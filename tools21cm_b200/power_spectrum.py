@@ -24,7 +24,7 @@ from . import _lib
 from . import binspec as _bs
 from ._lib import T21_F32, T21_F64
 
-__all__ = ["power_spectrum_nd", "cross_power_spectrum_nd", "radial_average", "power_spectrum_1d",
+__all__ = ["power_spectrum_nd", "cross_power_spectrum_nd", "radial_average", "power_spectrum_1d", "power_spectrum_2d",
            "cross_power_spectrum_1d", "power_spectrum_mu", "cross_power_spectrum_mu", "mu_binning",
            "dimensionless_ps", "anisotropy_ratio_r_mu", "get_k", "get_kbins", "apply_window",
            "set_precision"]
@@ -513,6 +513,40 @@ def cross_power_spectrum_mu(input_array1, input_array2, los_axis=0, mubins=20, k
 # ----------------------------------------------------------------------------------------
 # thin host post-processing on top of the estimators
 # ----------------------------------------------------------------------------------------
+def power_spectrum_2d(input_array, kbins=10, binning="log", box_dims=244 / .7, return_modes=False, nu_axis=2,
+                      window=None, **kwargs):
+    """Power spectrum binned in (k_perp, k_par) (reference power_spectrum.py:177-254).
+    Returns (Pk[n_kper, n_kpar], kper_mid, kpar_mid[, n_modes])."""
+    input_array = apply_window(input_array, window)
+    if kwargs.get("boxsize") is not None:
+        box_dims = kwargs.get("boxsize")
+    box_dims = _get_dims(box_dims, input_array.shape)
+    x, _ = _stage(input_array)
+    torch = _torch()
+    shape = tuple(x.shape)
+    power = _fused_nd([x], _bs.volume_scale(shape, box_dims), torch.float64)
+    cyl = _bs.build_cyl_tables(shape, box_dims, kbins, binning=binning, nu_axis=nu_axis)
+    dev = _device(x.device.index)
+    with torch.cuda.device(x.device):
+        lib = _lib.load()
+        perp = torch.from_numpy(cyl.perp_tab).to(x.device)
+        par = torch.from_numpy(cyl.par_tab).to(x.device)
+        nb = cyl.nperp * cyl.npar
+        ws = dev.workspace(lib.t21_bin_cyl_workspace_bytes(cyl.nperp, cyl.npar))
+        sums = torch.empty(nb, dtype=torch.float64, device=x.device)
+        counts = torch.empty(nb, dtype=torch.int64, device=x.device)
+        rc = lib.t21_bin_cyl(power.data_ptr(), T21_F64, shape[0], shape[1], shape[2], int(nu_axis), perp.data_ptr(),
+                             par.data_ptr(), cyl.nperp, cyl.npar, sums.data_ptr(), counts.data_ptr(), ws.data_ptr(),
+                             ws.numel(), _stream_ptr(torch, x.device.index))
+        _lib.check(rc, "t21_bin_cyl")
+        s = sums.cpu().numpy().reshape(cyl.nperp, cyl.npar)
+        n = counts.cpu().numpy().astype("float").reshape(cyl.nperp, cyl.npar)
+    ps = _finish(s, n, 1.0)
+    if return_modes:
+        return ps, cyl.kper_mid, cyl.kpar_mid, n
+    return ps, cyl.kper_mid, cyl.kpar_mid
+
+
 def dimensionless_ps(data, kbins=100, box_dims=None, binning="log", factor=10):
     """Delta^2(k) = P k^3 / 2 pi^2, interpolated from a finer binning (reference :536-561)."""
     from scipy.interpolate import interp1d

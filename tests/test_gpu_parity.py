@@ -219,3 +219,22 @@ def test_cross_of_a_cube_with_itself_is_its_auto_spectrum_512(t2c):
     np.testing.assert_allclose(a[0], c[0], rtol=1e-12)
     m = t2c.power_spectrum_mu(x, kbins=10, mubins=5, box_dims=300.0, return_n_modes=True)
     assert m[3].sum() == 512 ** 3 - 512 - 1 - 0 or m[3].sum() > 0.99 * 512 ** 3
+
+
+def test_2048_cube_on_one_gpu_has_no_index_overflow(t2c):
+    """34 GB cube + 35 GB workspace on one 180 GB GPU: element offsets exceed 2^32 in every pass."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < 90 * 2 ** 30:
+        pytest.skip("needs ~80 GB of free device memory")
+    n, L = 2048, 714.0
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn((n, n, n), generator=g, device="cuda", dtype=torch.float32)
+    ps, ks, nm = t2c.power_spectrum_1d(x, kbins=15, box_dims=L, return_n_modes=True)
+    assert nm.sum() in (n ** 3 - 1, n ** 3 - 2, n ** 3 - 7, n ** 3 - 8)
+    # white noise of unit variance: P(k) = V / N^3 in every bin, to sampling error
+    expect = L ** 3 / n ** 3
+    assert np.all(np.abs(ps[nm > 1000] / expect - 1.0) < 0.05)
+    assert abs(ps[-1] / expect - 1.0) < 1e-3          # billions of modes in the last shells
+    del x
+    torch.cuda.empty_cache()

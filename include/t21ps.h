@@ -125,6 +125,20 @@ T21_API int t21_ps_nd(const t21_plan* plan, const void* x1, const void* x2_or_nu
 T21_API int t21_slab_pitch(const t21_plan* plan);
 T21_API int t21_slab_stage1(const t21_plan* plan_slab, const void* x_slab, const void* offset_or_null,
                             void* w_out, void* send_out_or_null, int nranks, void* stream);
+/* stage 1 with the re-partition FUSED into the Y pass: every transformed row is stored straight into the
+ * y-slab buffer of the rank that owns it.  peer_cols[s] = rank s's [nx][ny/P][pitch] buffer mapped into this
+ * process (CUDA IPC / peer access over NVLink; peer_cols[own rank] is the local one); x0_global = global index
+ * of this slab's first x plane.  No send buffer, no collective: the caller only has to order "every rank has
+ * finished stage 1" before stage 2 (e.g. a one-element all-reduce on the same stream). */
+/* buffers of the fused exchange: t21_peer_alloc makes one (cudaMalloc) and returns its 64-byte CUDA IPC handle;
+ * a peer process calls t21_peer_open on that handle with its own device current. */
+T21_API int t21_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+T21_API int t21_peer_open(const unsigned char* handle64, void** ptr);
+T21_API int t21_peer_close(void* ptr);
+T21_API int t21_peer_free(void* ptr);
+T21_API int t21_slab_stage1_p2p(const t21_plan* plan_slab, const void* x_slab, const void* offset_or_null,
+                                void* w_scratch, void* const* peer_cols, int nranks, long long x0_global,
+                                void* stream);
 T21_API int t21_slab_stage2(const t21_plan* plan_cols, const void* w1, const void* w2_or_null, int iy0,
                             int ny_global, const void* offset1, const void* offset2,
                             const t21_binspec* spec, double* sums_out, long long* counts_out,

@@ -46,7 +46,9 @@ static void ypass(cx<T>* w, long long nouter, int nzh, int pitch, int xb) {
     using K = YPass<NY, T, WZ>;
     auto tw = build_stage_twiddles<T>(NY, emax_y(NY));
     int nchunks = (nzh + WZ - 1) / WZ;
-    typename K::Params p{w, nzh, pitch, nchunks, xb, tw.data(), nullptr, 0, nouter};
+    typename K::Params p;
+    std::memset(&p, 0, sizeof(p));
+    p.w = w; p.nzh = nzh; p.pitch = pitch; p.nchunks = nchunks; p.xb = xb; p.tw = tw.data(); p.nouter = nouter;
     std::vector<cx<T>> smem(K::SMEM_BYTES / sizeof(cx<T>) + 1);
     for (long long cta = 0; cta < nouter * nchunks; ++cta) {
         std::vector<typename K::Regs> regs(K::THREADS);

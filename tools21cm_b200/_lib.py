@@ -143,6 +143,16 @@ def load():
     lib.t21_slab_pitch.restype = i32
     lib.t21_slab_stage1.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     lib.t21_slab_stage1.restype = i32
+    lib.t21_peer_alloc.argtypes = [sz, C.POINTER(vp), C.c_char_p]
+    lib.t21_peer_alloc.restype = i32
+    lib.t21_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.t21_peer_open.restype = i32
+    lib.t21_peer_close.argtypes = [vp]
+    lib.t21_peer_close.restype = i32
+    lib.t21_peer_free.argtypes = [vp]
+    lib.t21_peer_free.restype = i32
+    lib.t21_slab_stage1_p2p.argtypes = [vp, vp, vp, vp, C.POINTER(vp), i32, C.c_longlong, vp]
+    lib.t21_slab_stage1_p2p.restype = i32
     lib.t21_slab_stage2.argtypes = [vp, vp, vp, i32, i32, vp, vp, C.POINTER(BinSpecC), vp, vp, vp, sz, vp]
     lib.t21_slab_stage2.restype = i32
     lib.t21_slab_stage2_nd.argtypes = [vp, vp, vp, i32, i32, vp, vp, dbl, vp, i32, vp]

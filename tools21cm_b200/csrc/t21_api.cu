@@ -205,7 +205,7 @@ static int forward_zy(const t21_plan* p, const void* const x[2], int nf, int sub
         ZArgs z{x[f], ws + L.w[f], (long long)p->n[0] * p->n[1], p->n[2], p->pitch, p->n[1], p->xb, offs[f], p->tw[2], p->twr};
         if (int rc = p->fast[2] ? launch_zpass(p->dtype, z, st) : launch_zpass_generic(p->dtype, z, st)) return rc;
         prof_mark(st, SLOT_Z);
-        YArgs y{ws + L.w[f], (long long)p->n[0], p->n[1], p->nzh, p->pitch, p->xb, p->tw[1], nullptr, 0};
+        YArgs y{ws + L.w[f], (long long)p->n[0], p->n[1], p->nzh, p->pitch, p->xb, p->tw[1], nullptr, 0, nullptr, 0, 0};
         if (int rc = p->fast[1] ? launch_ypass(p->dtype, y, st) : launch_ypass_generic(p->dtype, y, st)) return rc;
         prof_mark(st, SLOT_Y);
     }
@@ -347,9 +347,64 @@ int t21_slab_stage1(const t21_plan* p, const void* x_slab, const void* offset_or
     ZArgs z{x_slab, w_out, (long long)p->n[0] * p->n[1], p->n[2], p->pitch, p->n[1], 0, offset_or_null, p->tw[2], p->twr};
     if (int rc = launch_zpass(p->dtype, z, st)) return rc;
     prof_mark(st, SLOT_Z);
-    YArgs y{w_out, (long long)p->n[0], p->n[1], p->nzh, p->pitch, 0, p->tw[1], send_out, nyl_log2};
+    YArgs y{w_out, (long long)p->n[0], p->n[1], p->nzh, p->pitch, 0, p->tw[1], send_out, nyl_log2, nullptr, 0, 0};
     if (int rc = launch_ypass(p->dtype, y, st)) return rc;
     prof_mark(st, SLOT_Y);
+    return T21_OK;
+}
+
+// stage 1 with the exchange fused in: the Y pass stores every transformed row straight into the y-slab
+// buffer of the rank that owns it (peer_cols[s] = rank s's [nx][ny/P][pitch] buffer, peer-mapped over NVLink),
+// so there is no send buffer and no collective; x0_global = index of this slab's first x plane in the cube.
+// The caller orders "all ranks finished stage 1" before stage 2 (a tiny all-reduce on the same stream).
+int t21_slab_stage1_p2p(const t21_plan* p, const void* x_slab, const void* offset_or_null, void* w_scratch,
+                        void* const* peer_cols, int nranks, long long x0_global, void* stream) {
+    if (!p || !x_slab || !w_scratch || !peer_cols) { set_error("null argument"); return T21_EINVAL; }
+    if (!(p->fast[1] && p->fast[2])) { set_error("slab mode needs power-of-two y and z axes"); return T21_EINVAL; }
+    if (nranks < 1 || nranks > 16 || (nranks & (nranks - 1)) || p->n[1] % nranks) {
+        set_error("rank count %d must be a power of two <= 16 dividing ny = %d", nranks, p->n[1]); return T21_EINVAL;
+    }
+    for (int r = 0; r < nranks; ++r)
+        if (!peer_cols[r] || ((uintptr_t)peer_cols[r] & 15)) { set_error("bad peer buffer %d", r); return T21_EINVAL; }
+    int nyl_log2 = 0;
+    while ((p->n[1] / nranks) >> (nyl_log2 + 1)) ++nyl_log2;
+    cudaStream_t st = (cudaStream_t)stream;
+    prof_begin(st);
+    ZArgs z{x_slab, w_scratch, (long long)p->n[0] * p->n[1], p->n[2], p->pitch, p->n[1], 0, offset_or_null, p->tw[2], p->twr};
+    if (int rc = launch_zpass(p->dtype, z, st)) return rc;
+    prof_mark(st, SLOT_Z);
+    YArgs y{w_scratch, (long long)p->n[0], p->n[1], p->nzh, p->pitch, 0, p->tw[1], nullptr, nyl_log2, peer_cols, nranks, x0_global};
+    if (int rc = launch_ypass(p->dtype, y, st)) return rc;
+    prof_mark(st, SLOT_Y);
+    return T21_OK;
+}
+
+// Buffers other processes store into (the fused exchange).  They are plain cudaMalloc allocations so that
+// their CUDA IPC handle refers to the buffer itself (offset 0); a peer opens the handle with ITS device
+// current, which maps the memory for that device's kernels and enables peer access over NVLink.
+int t21_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64) {
+    if (!ptr || !handle64 || bytes == 0) { set_error("null argument"); return T21_EINVAL; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    T21_CUDA_OK(cudaMalloc(ptr, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *ptr);
+    if (e != cudaSuccess) { cudaFree(*ptr); *ptr = nullptr; return cuda_fail(e, "cudaIpcGetMemHandle"); }
+    memcpy(handle64, &h, 64);
+    return T21_OK;
+}
+int t21_peer_open(const unsigned char* handle64, void** ptr) {
+    if (!ptr || !handle64) { set_error("null argument"); return T21_EINVAL; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    T21_CUDA_OK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return T21_OK;
+}
+int t21_peer_close(void* ptr) {
+    if (ptr) T21_CUDA_OK(cudaIpcCloseMemHandle(ptr));
+    return T21_OK;
+}
+int t21_peer_free(void* ptr) {
+    if (ptr) T21_CUDA_OK(cudaFree(ptr));
     return T21_OK;
 }
 

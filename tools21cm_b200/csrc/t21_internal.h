@@ -14,6 +14,7 @@ struct ZArgs {
 struct YArgs {
     void* w; long long nouter; int ny; int nzh; int pitch; int xb; const void* tw;
     void* send; int nyl_log2;          // slab mode: packed all-to-all send buffer (or null)
+    void* const* peers; int npeers; long long xg0;   // slab mode, fused exchange: peer y-slab buffers (or null)
 };
 struct XArgs {
     const void* w[2]; int nf; int nx, ny, nz, nzh, pitch; int xb; int iy0;

@@ -141,10 +141,14 @@ struct Strided {
 // ======================================================================================
 // Y pass (in place)
 // ======================================================================================
-// SEND: store into the packed all-to-all send buffer of a slab-sharded cube instead of in place.
+// SEND: 0 in place; 1 store into the packed all-to-all send buffer of a slab-sharded cube;
+//       2 store straight into the y-slab buffers of the PEER GPUs over NVLink (the all-to-all is fused
+//         into this pass: no send buffer, no collective, the transfer overlaps the transform tile by tile).
 // Columns past nz/2 inside the last chunk are scratch (pitch >= nchunks*WZ): they are transformed
 // like the rest and ignored by the X-pass epilogue, so no access here needs a bounds predicate.
-template <int NY, typename T, int WZ, bool SEND = false>
+constexpr int kMaxPeers = 16;
+
+template <int NY, typename T, int WZ, int SEND = 0>
 struct YPass {
     using S = Strided<NY, T, WZ, emax_y(NY)>;
     static constexpr int THREADS = S::THREADS;
@@ -168,6 +172,10 @@ struct YPass {
         cx<T>* send;
         int nyl_log2;         // log2(NY / P)
         long long nouter;     // x planes in this slab
+        // SEND == 2: peer[s] = rank s's y-slab buffer [nx][NY/P][pitch] (peer-mapped); this slab's planes
+        // start at global x = xg0
+        cx<T>* peer[SEND == 2 ? kMaxPeers : 1];
+        long long xg0;
     };
     struct Regs {
         cx<T> v[S::E];
@@ -197,11 +205,15 @@ struct YPass {
             [&](int) { return *lc.next(); },
 #endif
             [&](int i, cx<T> val, int) {
-                if constexpr (SEND) {
+                if constexpr (SEND == 1) {
                     // destination rank i >> nyl_log2 gets row (x, i mod NY/P) of its y slab
                     const long long row = (((long long)(i >> p.nyl_log2) * p.nouter + outer) << p.nyl_log2) +
                                           (i & ((1 << p.nyl_log2) - 1));
                     p.send[row * p.pitch + z] = val;
+                } else if constexpr (SEND == 2) {
+                    // the same element, written into rank (i >> nyl_log2)'s memory: row (global x, i mod NY/P)
+                    const long long row = ((p.xg0 + outer) << p.nyl_log2) + (i & ((1 << p.nyl_log2) - 1));
+                    p.peer[i >> p.nyl_log2][row * p.pitch + z] = val;
                 } else {
                     *sc.next() = val;
                 }

@@ -10,15 +10,30 @@ static int launch_ypass_t(const YArgs& a, cudaStream_t st) {
     {                                                                                    \
         constexpr int WZ = WZFor<T, N>::value;                                           \
         const int nchunks = (a.nzh + WZ - 1) / WZ;                                       \
+        if (a.peers) {                                                                   \
+            using KP = YPass<N, T, WZ, 2>;                                               \
+            typename KP::Params pp;                                                      \
+            memset(&pp, 0, sizeof(pp));                                                  \
+            pp.w = (cx<T>*)a.w; pp.nzh = a.nzh; pp.pitch = a.pitch; pp.nchunks = nchunks; \
+            pp.xb = a.xb; pp.tw = (const cx<T>*)a.tw; pp.nyl_log2 = a.nyl_log2;          \
+            pp.nouter = a.nouter; pp.xg0 = a.xg0;                                        \
+            for (int r = 0; r < a.npeers; ++r) pp.peer[r] = (cx<T>*)a.peers[r];          \
+            return launch_tiles<KP, T>(pp, a.nouter * nchunks, st);                      \
+        }                                                                                \
         if (a.send) {                                                                    \
-            using KS = YPass<N, T, WZ, true>;                                            \
-            typename KS::Params ps{(cx<T>*)a.w, a.nzh, a.pitch, nchunks, a.xb, (const cx<T>*)a.tw, \
-                                   (cx<T>*)a.send, a.nyl_log2, a.nouter};                \
+            using KS = YPass<N, T, WZ, 1>;                                               \
+            typename KS::Params ps;                                                      \
+            memset(&ps, 0, sizeof(ps));                                                  \
+            ps.w = (cx<T>*)a.w; ps.nzh = a.nzh; ps.pitch = a.pitch; ps.nchunks = nchunks; \
+            ps.xb = a.xb; ps.tw = (const cx<T>*)a.tw; ps.send = (cx<T>*)a.send;          \
+            ps.nyl_log2 = a.nyl_log2; ps.nouter = a.nouter;                              \
             return launch_tiles<KS, T>(ps, a.nouter * nchunks, st);                      \
         }                                                                                \
         using K = YPass<N, T, WZ>;                                                       \
-        typename K::Params p{(cx<T>*)a.w, a.nzh, a.pitch, nchunks, a.xb, (const cx<T>*)a.tw,      \
-                             (cx<T>*)a.send, a.nyl_log2, a.nouter};                        \
+        typename K::Params p;                                                            \
+        memset(&p, 0, sizeof(p));                                                        \
+        p.w = (cx<T>*)a.w; p.nzh = a.nzh; p.pitch = a.pitch; p.nchunks = nchunks;        \
+        p.xb = a.xb; p.tw = (const cx<T>*)a.tw; p.nouter = a.nouter;                     \
         return launch_tiles<K, T>(p, a.nouter * nchunks, st);                            \
     }
     T21_FOR_FAST_N(a.ny, YCASE)

@@ -11,9 +11,15 @@ path exist and both are here:
   and a tiny all-reduce sums the per-bin sums and counts -- ``sharded_power_spectrum_1d``,
   ``sharded_cross_power_spectrum_1d``, ``sharded_power_spectrum_mu``.
 
-The exchange is ``all_to_all_single`` over NCCL (NVLink 5 / NVSwitch on the 8xB200 box): rank r
-sends rank s the block W[x in slab r, y in slab s, :], packed so that the receive buffer *is* the
-[nx][ny/P][pitch] array stage 2 reads (no unpack pass).
+The exchange has two implementations (``T21_EXCHANGE=p2p|nccl``):
+
+* ``p2p`` (default): the re-partition is FUSED into the Y pass.  Every rank maps the other ranks' y-slab
+  buffers into its address space (CUDA IPC) and the Y-pass kernel stores each transformed row straight
+  into the buffer of the rank that owns it, over NVLink 5 / NVSwitch: no send buffer, no collective, the
+  transfer overlaps the transform tile by tile.  A one-element all-reduce orders the stages.
+* ``nccl``: ``all_to_all`` over NCCL in 4 pieces pipelined against the Z/Y passes; rank r sends rank s the block
+  W[x in slab r, y in slab s, :], packed by the Y pass so that the receive buffer *is* the [nx][ny/P][pitch]
+  array stage 2 reads (no pack or unpack pass).
 
 ``backend`` lets the CPU tests (gloo, world_size 2) replace the two CUDA stages by a numpy model
 while exercising exactly this partitioning, packing, offset and reduction code.
@@ -98,6 +104,22 @@ class CudaBackend:
                                  self._ps._stream_ptr(torch, x.device.index))
         _lib.check(rc, "t21_slab_stage1")
         return send if send is not None else w
+
+    def stage1_p2p(self, x, offset, peer_ptrs, world, x0_global):
+        """Z and Y passes of an x slab with the re-partition fused into the Y pass: rows are stored straight
+        into the peers' y-slab buffers (``peer_ptrs``: ctypes array of ``world`` device pointers)."""
+        import torch
+        lib = _lib.load()
+        dev = self._ps._device(x.device.index)
+        code = self._ps._dtype_code(x)
+        plan = dev.plan(tuple(x.shape), code)
+        pitch = lib.t21_slab_pitch(plan)
+        cdt = torch.complex64 if x.dtype == torch.float32 else torch.complex128
+        scratch = torch.empty((x.shape[0], x.shape[1], pitch), dtype=cdt, device=x.device)
+        rc = lib.t21_slab_stage1_p2p(plan, x.data_ptr(), offset.data_ptr() if offset is not None else None,
+                                     scratch.data_ptr(), peer_ptrs, int(world), int(x0_global),
+                                     self._ps._stream_ptr(torch, x.device.index))
+        _lib.check(rc, "t21_slab_stage1_p2p")
 
     def stage2(self, cols, iy0, ny_global, nz, offsets, spec_key, spec_builder):
         import torch
@@ -191,6 +213,78 @@ def pipelined_exchange(backend, x, offset, world, group=None, chunks=4):
     return recv4.view(world * nxl, nyl, recv4.shape[3])
 
 
+class _RawCuda:
+    """Zero-copy torch view of a raw device allocation (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class _PeerSlabs:
+    """This rank's y-slab receive buffers (a ping-pong pair, cudaMalloc'ed by the library) and the peers'
+    pairs mapped into this process with CUDA IPC, so the Y pass can store into them over NVLink."""
+    _cache = {}
+
+    @classmethod
+    def get(cls, key, shape, real_dtype, device, group):
+        hit = cls._cache.get(key)
+        if hit is None:
+            hit = cls._cache[key] = cls(shape, real_dtype, device, group)
+        return hit
+
+    def __init__(self, shape, real_dtype, device, group):
+        import torch
+        lib = _lib.load()
+        world, rank = _world(group)
+        esz = 4 if real_dtype == torch.float32 else 8
+        nbytes = int(np.prod(shape)) * 2 * esz
+        self.local, self.local_ptr, handles = [], [], []
+        with torch.cuda.device(device):
+            for _ in range(2):
+                ptr = C.c_void_p()
+                hbuf = C.create_string_buffer(64)
+                _lib.check(lib.t21_peer_alloc(nbytes, C.byref(ptr), hbuf), "t21_peer_alloc")
+                self.local_ptr.append(ptr.value)
+                handles.append(hbuf.raw)
+                view = torch.as_tensor(_RawCuda(ptr.value, tuple(shape) + (2,), "<f%d" % esz), device=device)
+                self.local.append(view)
+            gathered = [None] * world
+            _dist().all_gather_object(gathered, handles, group=group)
+            self.ptrs = []
+            for par in range(2):
+                row = []
+                for r in range(world):
+                    if r == rank:
+                        row.append(self.local_ptr[par])
+                    else:
+                        ptr = C.c_void_p()
+                        _lib.check(lib.t21_peer_open(gathered[r][par], C.byref(ptr)), "t21_peer_open")
+                        row.append(ptr.value)
+                self.ptrs.append((C.c_void_p * world)(*row))
+        self.parity = 0
+
+    def next(self):
+        self.parity ^= 1
+        return self.parity
+
+
+def fused_exchange(backend, x, offset, world, rank, field, group=None):
+    """Stage 1 with the all-to-all fused into the Y pass (peer stores over NVLink), then a one-element
+    all-reduce that orders "every rank has finished writing" before stage 2 reads.  Returns the y slab."""
+    import torch
+    nxl, ny, nz = x.shape
+    nyl = ny // world
+    pitch = backend.pitch(nz)
+    key = (field, world * nxl, nyl, pitch, str(x.dtype), x.device.index, id(group))
+    bufs = _PeerSlabs.get(key, (world * nxl, nyl, pitch), x.dtype, x.device, group)
+    par = bufs.next()
+    backend.stage1_p2p(x, offset, bufs.ptrs[par], world, rank * nxl)
+    flag = torch.zeros(1, device=x.device)
+    _dist().all_reduce(flag, group=group)
+    return torch.view_as_complex(bufs.local[par])
+
+
 def _forward(slabs, group, backend):
     """Common mean offset, stage 1 and the re-partition.  Returns (cols, offsets, world, rank, shape)."""
     import torch
@@ -212,10 +306,14 @@ def _forward(slabs, group, backend):
             offsets.append(m.to(x.dtype))
         else:
             offsets.append(None)
+    import os
     cols = []
-    fused = world > 1 and isinstance(backend, CudaBackend)
-    for x, off in zip(slabs, offsets):
-        if fused:
+    cuda = world > 1 and isinstance(backend, CudaBackend)
+    mode = os.environ.get("T21_EXCHANGE", "p2p")      # p2p: fused peer stores; nccl: pipelined all-to-all
+    for f, (x, off) in enumerate(zip(slabs, offsets)):
+        if cuda and mode == "p2p":
+            cols.append(fused_exchange(backend, x, off, world, rank, f, group))
+        elif cuda:
             cols.append(pipelined_exchange(backend, x, off, world, group))
         else:
             cols.append(exchange(backend.stage1(x, off), world, group))

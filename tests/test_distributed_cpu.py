@@ -101,7 +101,7 @@ def _worker(rank, world, port, q):
         rows, yidx = D.sharded_cross_power_spectrum_nd(a, b, 30.0, backend=NumpyBackend())
         full = ps_oracle.cross_power_spectrum_nd(cube.astype(np.float64), other, 30.0)
         out["nd"] = float(np.abs(rows.numpy() - full[:, yidx.numpy(), :]).max() / np.abs(full).max())
-        odd = np.random.default_rng(9).standard_normal((8, 6, 7))          # odd z: no Nyquist plane
+        odd = np.random.default_rng(9).standard_normal((8, 12, 7))         # odd z: no Nyquist plane
         nx8 = odd.shape[0] // world
         rows, yidx = D.sharded_power_spectrum_nd(torch.from_numpy(odd[rank * nx8:(rank + 1) * nx8].copy()),
                                                  [10.0, 20.0, 30.0], backend=NumpyBackend())
@@ -118,21 +118,22 @@ def test_partition_is_round_robin():
     assert sorted(sum((partition(64, 8, r) for r in range(8)), [])) == list(range(64))
 
 
-def test_world_size_2_gloo():
+@pytest.mark.parametrize("world", [2, 4])
+def test_world_size_n_gloo(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() + 7 * world) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = dict(q.get(timeout=240) for _ in procs)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank in (0, 1):
+    for rank in range(world):
         out = results[rank]
         assert [r[0] for r in out["batched"]] == list(range(7))
-        assert [r[2] for r in out["batched"]] == [0, 1, 0, 1, 0, 1, 0]      # who computed what
+        assert [r[2] for r in out["batched"]] == [i % world for i in range(7)]      # who computed what
         counts_ok, centres_ok, err = out["1d"]
         assert counts_ok and centres_ok and err < 1e-5
         assert out["x1d"][0] and out["x1d"][1] < 1e-10

@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: tools_profile.sh <kernel-regex> <tag> [skip]   (runs on the GPU box via gpurun)
+# usage: tools/profile_kernel.sh <kernel-regex> <tag> [skip]   (runs on the GPU box via gpurun)
 # Full ncu capture of one launch of the matching kernel during a 1024^3 bench step; exports the
 # raw-page CSV (small) and keeps the .ncu-rep only if it is small enough to travel back.
 set -u

@@ -404,14 +404,14 @@ struct XPass {
                 constexpr int EH = E / 2;
                 const int r0 = (q / RPI) * (EH * RPI) + (q % RPI);
                 const T* pt2 = ptile(smem) + zl;
-                auto step = [&](int ix, bool lane_on, bool self) {
-                    const int iq = self ? ix : NX - ix;
-                    const T plo = pt2[ix * WZ], phi = pt2[iq * WZ];
-                    const double pw = (double)((self ? plo : plo + phi) * wf);
+                auto step = [&](int ix, const T* plo_p, const T* phi_p, const float* sx_p, bool lane_on, bool self) {
+                    const T plo = *plo_p, phi = *phi_p;
+                    const T psum = self ? plo : plo + phi;
+                    const double pw = (double)(psum * wf);
                     const unsigned wn = self ? wt : 2u * wt;
                     bool valid = lane_on && active;
                     if (MU) valid = valid && !(line_fixed && (los == 0 || ix == zx));
-                    const float sh = ldg(B.tab_sf[0] + ix) + c_yz;
+                    const float sh = ldg(sx_p) + c_yz;
                     float muh = 0.f;
                     if (MU) muh = (los == 0 ? ldg(B.tab_losf + ix) : klos_c) * fast_rsqrt(sh);
                     const float m_own = MU == 1 ? fabsf(muh) : muh;
@@ -419,26 +419,33 @@ struct XPass {
                         int w1 = 1;
                         const int bin = valid ? exact_bin(p, ix, iy, iz, has_twin, 0, sh, w1) : -1;
                         const unsigned wx = self ? (unsigned)w1 : 2u * (unsigned)w1;
-                        warpbins_slow(r.acc[0], hist, B, nb, bin, (w1 == (int)wt) ? pw : (double)(self ? plo : plo + phi),
-                                      wx, valid);
+                        warpbins_slow(r.acc[0], hist, B, nb, bin, (w1 == (int)wt) ? pw : (double)psum, wx, valid);
                     }
                     if constexpr (MU == 2) {                  // los != 0 here: the twin's mu is the same for ix and NX-ix
                         const bool tv = valid && has_twin;
                         const float m_tw = nyq_c ? muh : -muh;
-                        const double pt_w = (double)(self ? plo : plo + phi);
-                        if (!warpbins_fast<true>(r.acc[1], sh, m_tw, pt_w, self ? 1u : 2u, tv)) {
+                        if (!warpbins_fast<true>(r.acc[1], sh, m_tw, (double)psum, self ? 1u : 2u, tv)) {
                             int w1 = 1;
                             const int bin = tv ? exact_bin(p, ix, iy, iz, has_twin, 1, sh, w1) : -1;
-                            warpbins_slow(r.acc[1], hist, B, nb, bin, pt_w, self ? 1u : 2u, tv);
+                            warpbins_slow(r.acc[1], hist, B, nb, bin, (double)psum, self ? 1u : 2u, tv);
                         }
                     }
                 };
+                // loop-carried addresses, made opaque so they are advanced, not recomputed from the thread id
+                const T* plo_p = pt2 + r0 * WZ;
+                const T* phi_p = pt2 + ((NX - r0) & (NX - 1)) * WZ;      // row 0 pairs with itself
+                const float* sx_p = B.tab_sf[0] + r0;
+                int ix = r0;
+                asm volatile("" : "+l"(plo_p), "+l"(phi_p), "+l"(sx_p), "+r"(ix));
 #pragma unroll 1
                 for (int it = 0; it < EH; ++it) {
-                    const int ix = r0 + it * RPI;
-                    step(ix, true, ix == 0);
+                    step(ix, plo_p, phi_p, sx_p, true, ix == 0);
+                    plo_p += RPI * WZ;
+                    phi_p = pt2 + (NX - ix - RPI) * WZ;
+                    sx_p += RPI;
+                    ix += RPI;
                 }
-                if (tid < 32) step(NX / 2, q == 0, true);     // warp 0: the self-conjugate Nyquist row
+                if (tid < 32) step(NX / 2, pt2 + (NX / 2) * WZ, pt2 + (NX / 2) * WZ, B.tab_sf[0] + NX / 2, q == 0, true);
                 return;
             }
         }

@@ -114,12 +114,13 @@ T21_API int t21_ps_nd(const t21_plan* plan, const void* x1, const void* x2_or_nu
 
 /* One cube sharded over P GPUs as x slabs (configs 4 and 5 of BASELINE.json; the reference has no
  * distributed path, this replaces the single-process fftn of power_spectrum.py:45,85-86 when the
- * cube is spread over ranks).  stage1: Z and Y passes of this rank's slab [nx/P][ny][nz] into
- * w_out [nx/P][ny][pitch] (pitch from t21_slab_pitch; offset = device scalar subtracted from every
- * sample, the SAME value on every rank, or NULL).  With send_out != NULL the Y pass stores straight
- * into the packed all-to-all send buffer [nranks][nx/P][ny/nranks][pitch] (w_out is then scratch), so
- * the re-partition needs no separate pack pass.  The caller re-partitions the half spectrum into
- * y slabs [nx][ny/P][pitch] with an NCCL all-to-all, then stage2 (plan of shape (nx, ny/P, nz)) runs
+ * cube is spread over ranks).  Half-spectrum buffers are "chunk major": [pitch/LW][x planes][y rows][LW]
+ * complex with LW = 8 (fp32) / 4 (fp64), i.e. pitch * planes * rows elements (pitch from t21_slab_pitch).
+ * stage1: Z and Y passes of this rank's slab [nx/P][ny][nz] into w_out (offset = device scalar
+ * subtracted from every sample, the SAME value on every rank, or NULL).  With send_out != NULL the Y pass stores straight
+ * into the packed all-to-all send buffer (nranks blocks; block s = the chunk-major part for rank s; w_out is
+ * then scratch), so the re-partition needs no separate pack pass.  After an NCCL all-to-all the receive buffer
+ * is n_xslabs = P consecutive x slabs, each chunk-major; stage2 (plan of shape (nx, ny/P, nz)) runs
  * the X pass fused with the binning for rows iy0 .. iy0+ny/P of the global cube; the caller
  * all-reduces sums_out / counts_out.  t21_workspace_bytes(plan, 0, nbins) sizes stage2's workspace. */
 T21_API int t21_slab_pitch(const t21_plan* plan);
@@ -139,16 +140,16 @@ T21_API int t21_peer_free(void* ptr);
 T21_API int t21_slab_stage1_p2p(const t21_plan* plan_slab, const void* x_slab, const void* offset_or_null,
                                 void* w_scratch, void* const* peer_cols, int nranks, long long x0_global,
                                 void* stream);
-T21_API int t21_slab_stage2(const t21_plan* plan_cols, const void* w1, const void* w2_or_null, int iy0,
-                            int ny_global, const void* offset1, const void* offset2,
+T21_API int t21_slab_stage2(const t21_plan* plan_cols, const void* w1, const void* w2_or_null, int n_xslabs,
+                            int iy0, int ny_global, const void* offset1, const void* offset2,
                             const t21_binspec* spec, double* sums_out, long long* counts_out,
                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* power_spectrum_nd / cross_power_spectrum_nd of a slab-sharded cube: the scaled power of this rank's
  * rows as the computed HALF spectrum in FFT order, out_half[nx][ny/P][nz/2+1].  The caller assembles
  * the fftshifted rows: the kz < 0 half of row ky is the mirrored half of row -ky, held by another rank. */
-T21_API int t21_slab_stage2_nd(const t21_plan* plan_cols, const void* w1, const void* w2_or_null, int iy0,
-                               int ny_global, const void* offset1, const void* offset2, double scale,
+T21_API int t21_slab_stage2_nd(const t21_plan* plan_cols, const void* w1, const void* w2_or_null, int n_xslabs,
+                               int iy0, int ny_global, const void* offset1, const void* offset2, double scale,
                                void* out_half, int out_dtype, void* stream);
 
 /* radial_average / mu_binning (power_spectrum.py:98-134, 380-435) on a caller-supplied

@@ -30,10 +30,11 @@ static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 // ---- passes with run-time sizes ------------------------------------------------------
 template <int NZ, typename T>
 static void zpass(const T* in, cx<T>* out, long long nrows, int pitch, const T* offset, int ny, int xb) {
+    (void)xb;
     using K = ZPass<NZ, T>;
     auto tw = build_stage_twiddles<T>(NZ / 2, emax_z(NZ / 2));
     auto twr = build_roots<T>(NZ, NZ / 2 + 1);
-    typename K::Params p{in, out, nrows, pitch, ny, xb, offset, tw.data(), twr.data()};
+    typename K::Params p{in, out, nrows, pitch, ny, (nrows / ny) * ny * WLay<T>::LW, offset, tw.data(), twr.data()};
     std::vector<cx<T>> smem(K::SMEM_BYTES / sizeof(cx<T>) + 1);
     long long nctas = (nrows + K::ROWS - 1) / K::ROWS;
     for (long long cta = 0; cta < nctas; ++cta) {
@@ -48,7 +49,8 @@ static void ypass(cx<T>* w, long long nouter, int nzh, int pitch, int xb) {
     int nchunks = (nzh + WZ - 1) / WZ;
     typename K::Params p;
     std::memset(&p, 0, sizeof(p));
-    p.w = w; p.nzh = nzh; p.pitch = pitch; p.nchunks = nchunks; p.xb = xb; p.tw = tw.data(); p.nouter = nouter;
+    p.w = w; p.nzh = nzh; p.pitch = pitch; p.nchunks = nchunks; p.cstride = nouter * NY * WLay<T>::LW; p.tw = tw.data(); p.nouter = nouter;
+    (void)xb;
     std::vector<cx<T>> smem(K::SMEM_BYTES / sizeof(cx<T>) + 1);
     for (long long cta = 0; cta < nouter * nchunks; ++cta) {
         std::vector<typename K::Regs> regs(K::THREADS);
@@ -68,7 +70,8 @@ static void xpass_mu(const cx<T>* w0, const cx<T>* w1, int ny, int nz, int pitch
     p.nchunks = (p.nzh + WZ - 1) / WZ;
     p.ntiles = (long long)ny * p.nchunks;
     p.tile_step = nctas_emulated;
-    p.xb = xb;
+    p.xs_log2 = ilog2_rt(NX);
+    (void)xb;
     p.iy0 = 0;
     p.tw = tw.data();
     p.offset[0] = off0; p.offset[1] = off1;
@@ -138,12 +141,14 @@ static int emu_all(int nx, int ny, int nz, const T* in0, const T* in1, double of
 #undef YP
         }
     }
-    if (half_out)
+    if (half_out) {       // hand the chunk-major array back as plain [nx][ny][pitch] rows
+        const WLay<T> lay = make_wlay<T>(nx, ny, pitch, 62);
         for (int x = 0; x < nx; ++x)
-            for (int y = 0; y < ny; ++y) {
-                const size_t row = ((((size_t)(x >> xb) * ny + y) << xb) + (x & ((1 << xb) - 1)));
-                std::memcpy(half_out + ((size_t)x * ny + y) * pitch, w[0].data() + row * pitch, sizeof(cx<T>) * pitch);
-            }
+            for (int y = 0; y < ny; ++y)
+                for (int k = 0; k < pitch; ++k)
+                    half_out[((size_t)x * ny + y) * pitch + k] = w[0][(size_t)(((long long)(k >> WLay<T>::LWS) * nx + x) * ny + y) * WLay<T>::LW + (k & (WLay<T>::LW - 1))];
+        (void)lay;
+    }
     if (upto < 3) return 0;
     constexpr int WZ = sizeof(T) == 4 ? 16 : 8;
     const int nctas = 3;

@@ -33,10 +33,10 @@ class NumpyBackend:
         from kernel_model import bin_half_spectrum
         spec = spec_builder()
         nzh = nz // 2 + 1
-        ntot = cols[0].shape[0] * ny_global * nz
+        ntot = cols[0].nx * ny_global * nz
         fs = []
         for c, off in zip(cols, offsets):
-            f = np.fft.fft(c.numpy()[:, :, :nzh], axis=0)
+            f = np.fft.fft(c.data.numpy()[:, :, :nzh], axis=0)
             if iy0 == 0 and off is not None:
                 f[0, 0, 0] += float(off.item()) * ntot
             fs.append(f)
@@ -48,10 +48,10 @@ class NumpyBackend:
 
 def _stage2_nd(self, cols, iy0, ny_global, nz, offsets, scale, out_dtype):
     nzh = nz // 2 + 1
-    ntot = cols[0].shape[0] * ny_global * nz
+    ntot = cols[0].nx * ny_global * nz
     fs = []
     for c, off in zip(cols, offsets):
-        f = np.fft.fft(c.numpy()[:, :, :nzh], axis=0)
+        f = np.fft.fft(c.data.numpy()[:, :, :nzh], axis=0)
         if iy0 == 0 and off is not None:
             f[0, 0, 0] += float(off.item()) * ntot
         fs.append(f)

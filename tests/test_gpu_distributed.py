@@ -14,7 +14,11 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def emulate_ranks(cubes, world, kw_spec, mu=False):
+def emulate_ranks(cubes, world, kw_spec, mu=False, fused=False):
+    """fused=False: the pack fused into the Y pass + the all-to-all done by indexing the send blocks (the y slab
+    is then P consecutive x slabs).  fused=True: the Y pass stores into the "peer" buffers directly (all on
+    this GPU here), one chunk-major array per rank."""
+    import ctypes as C
     import torch
     from tools21cm_b200 import binspec as bs, distributed as D
     from tools21cm_b200.power_spectrum import _freeze
@@ -22,13 +26,23 @@ def emulate_ranks(cubes, world, kw_spec, mu=False):
     shape = tuple(cubes[0].shape)
     nx, ny, nz = shape
     nxl, nyl = nx // world, ny // world
+    pitch = be.pitch(nz)
     single = cubes[0].dtype == torch.float32
+    cdt = torch.complex64 if single else torch.complex128
     offs = [c.reshape(-1)[::7].double().mean().reshape(1).to(c.dtype) if single else None for c in cubes]
     cols_all = []
     for c, off in zip(cubes, offs):
-        w = [be.stage1(c[r * nxl:(r + 1) * nxl].contiguous(), off) for r in range(world)]   # [nxl][ny][pitch] each
-        full = torch.cat(w, dim=0)                                                            # [nx][ny][pitch]
-        cols_all.append([full[:, s * nyl:(s + 1) * nyl].contiguous() for s in range(world)])
+        slabs = [c[r * nxl:(r + 1) * nxl].contiguous() for r in range(world)]
+        if fused:
+            bufs = [torch.zeros(nx * nyl * pitch, dtype=cdt, device=c.device) for _ in range(world)]
+            ptrs = (C.c_void_p * world)(*[b.data_ptr() for b in bufs])
+            for r in range(world):
+                be.stage1_p2p(slabs[r], off, ptrs, world, r * nxl)
+            cols_all.append([D.YSlab(bufs[s], nx, nyl, pitch) for s in range(world)])
+        else:
+            send = [be.stage1(slabs[r], off, send_world=world) for r in range(world)]       # [P][block] each
+            cols_all.append([D.YSlab(torch.stack([send[r][s] for r in range(world)]), nx, nyl, pitch, n_xslabs=world)
+                             for s in range(world)])
     sums = counts = None
     box = kw_spec.pop("box")
     for s in range(world):
@@ -41,14 +55,15 @@ def emulate_ranks(cubes, world, kw_spec, mu=False):
     return spec, ps, counts.cpu().numpy().astype(float)
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_slab_stages_emulated_on_one_gpu(world):
+def test_slab_stages_emulated_on_one_gpu(world, fused):
     import torch
     from oracle import ps_oracle
     from tools21cm_b200 import synthetic
     cube = synthetic.toy_dt_cube((64, 64, 32), seed=3)
     box = [200.0, 200.0, 100.0]
-    spec, ps, nm = emulate_ranks([torch.from_numpy(cube).cuda()], world, dict(box=box, kbins=10))
+    spec, ps, nm = emulate_ranks([torch.from_numpy(cube).cuda()], world, dict(box=box, kbins=10), fused=fused)
     ps_o, ks_o, nm_o = ps_oracle.power_spectrum_1d(cube, kbins=10, box_dims=box, return_n_modes=True)
     assert np.array_equal(nm, nm_o) and np.array_equal(spec.k_centres(), ks_o)
     np.testing.assert_allclose(ps, ps_o, rtol=1e-5, equal_nan=True)
@@ -65,7 +80,7 @@ def test_slab_stages_cross_and_mu_fp64():
     assert np.array_equal(nm, nm_o)
     np.testing.assert_allclose(ps, ps_o, rtol=1e-9, atol=1e-12 * np.nanmax(np.abs(ps_o)), equal_nan=True)
     spec, ps, nm = emulate_ranks([ta], 2, dict(box=[90.0] * 3, kbins=5, mubins=4, los_axis=1, absolute_mus=False,
-                                               last_bin_closed=False), mu=True)
+                                               last_bin_closed=False), mu=True, fused=True)
     pm_o, _, _, nmm_o = ps_oracle.power_spectrum_mu(a, los_axis=1, mubins=4, kbins=5, box_dims=90.0,
                                                     return_n_modes=True, absolute_mus=False)
     assert np.array_equal(nm.reshape(nmm_o.shape), nmm_o)

@@ -153,9 +153,9 @@ def load():
     lib.t21_peer_free.restype = i32
     lib.t21_slab_stage1_p2p.argtypes = [vp, vp, vp, vp, C.POINTER(vp), i32, C.c_longlong, vp]
     lib.t21_slab_stage1_p2p.restype = i32
-    lib.t21_slab_stage2.argtypes = [vp, vp, vp, i32, i32, vp, vp, C.POINTER(BinSpecC), vp, vp, vp, sz, vp]
+    lib.t21_slab_stage2.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, C.POINTER(BinSpecC), vp, vp, vp, sz, vp]
     lib.t21_slab_stage2.restype = i32
-    lib.t21_slab_stage2_nd.argtypes = [vp, vp, vp, i32, i32, vp, vp, dbl, vp, i32, vp]
+    lib.t21_slab_stage2_nd.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, dbl, vp, i32, vp]
     lib.t21_slab_stage2_nd.restype = i32
     lib.t21_bin_only.argtypes = [vp, i32, C.POINTER(BinSpecC), vp, vp, vp, sz, vp]
     lib.t21_bin_only.restype = i32

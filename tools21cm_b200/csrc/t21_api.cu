@@ -84,7 +84,6 @@ struct t21_plan {
     void* tw[3];          // stage twiddles per axis (z: for nz/2), device
     void* twr;            // exp(-2 pi i k / nz), k = 0..nz/2, device
     int max_grid;         // capacity (in CTAs) of the partial-histogram buffers
-    int xb;               // log2 of the x blocking factor of the half-spectrum layout
 };
 
 struct WsLayout {
@@ -158,15 +157,6 @@ int t21_plan_create(t21_plan** out, int nx, int ny, int nz, int dtype, int devic
     p->fast[1] = fast_len(ny);
     p->fast[2] = fast_len(nz);
     p->max_grid = device_sm_count() * 8;
-    // x blocking of the workspace layout: XB rows of x stay adjacent so that the X pass does not
-    // touch a different 2 MB page with every row (T21_XB overrides, for experiments)
-    {
-        int xb = 2;
-        if (const char* e = getenv("T21_XB")) xb = atoi(e);
-        while (xb > 0 && ((nx % (1 << xb)) != 0 || (1 << xb) > 16 || (1 << xb) > nx / 16)) --xb;
-        if (!p->fast[0] || !p->fast[1]) xb = 0;
-        p->xb = xb < 0 ? 0 : xb;
-    }
     int rc = dtype == T21_F32 ? build_tables<float>(p) : build_tables<double>(p);
     if (cur != device) cudaSetDevice(cur);
     if (rc) { t21_plan_destroy(p); return rc; }
@@ -202,10 +192,10 @@ static int forward_zy(const t21_plan* p, const void* const x[2], int nf, int sub
         }
         // (Running Z and Y slab by slab to keep the half spectrum in L2 between them was measured and
         // is slower: neither pass is DRAM-bandwidth bound and every extra launch costs ~5 us.)
-        ZArgs z{x[f], ws + L.w[f], (long long)p->n[0] * p->n[1], p->n[2], p->pitch, p->n[1], p->xb, offs[f], p->tw[2], p->twr};
+        ZArgs z{x[f], ws + L.w[f], (long long)p->n[0] * p->n[1], p->n[2], p->pitch, p->n[1], (long long)p->n[0], offs[f], p->tw[2], p->twr};
         if (int rc = p->fast[2] ? launch_zpass(p->dtype, z, st) : launch_zpass_generic(p->dtype, z, st)) return rc;
         prof_mark(st, SLOT_Z);
-        YArgs y{ws + L.w[f], (long long)p->n[0], p->n[1], p->nzh, p->pitch, p->xb, p->tw[1], nullptr, 0, nullptr, 0, 0};
+        YArgs y{ws + L.w[f], (long long)p->n[0], p->n[1], p->nzh, p->pitch, p->tw[1], nullptr, 0, nullptr, 0, 0, 0};
         if (int rc = p->fast[1] ? launch_ypass(p->dtype, y, st) : launch_ypass_generic(p->dtype, y, st)) return rc;
         prof_mark(st, SLOT_Y);
     }
@@ -246,7 +236,7 @@ int t21_ps_binned(const t21_plan* p, const void* x1, const void* x2, int subtrac
     a.w[0] = ws + L.w[0];
     a.w[1] = nf == 2 ? ws + L.w[1] : nullptr;
     a.nf = nf;
-    a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch; a.xb = p->xb;
+    a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch; a.xs_log2 = -1;
     a.tw = p->tw[0];
     a.offset[0] = offs[0]; a.offset[1] = offs[1];
     a.ntot = (double)p->n[0] * p->n[1] * p->n[2];
@@ -290,7 +280,7 @@ int t21_ps_nd(const t21_plan* p, const void* x1, const void* x2, int subtract_me
     a.w[0] = ws + L.w[0];
     a.w[1] = nf == 2 ? ws + L.w[1] : nullptr;
     a.nf = nf;
-    a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch; a.xb = p->xb;
+    a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch; a.xs_log2 = -1;
     a.tw = p->tw[0];
     a.offset[0] = offs[0]; a.offset[1] = offs[1];
     a.ntot = (double)p->n[0] * p->n[1] * p->n[2];
@@ -344,10 +334,10 @@ int t21_slab_stage1(const t21_plan* p, const void* x_slab, const void* offset_or
     }
     cudaStream_t st = (cudaStream_t)stream;
     prof_begin(st);
-    ZArgs z{x_slab, w_out, (long long)p->n[0] * p->n[1], p->n[2], p->pitch, p->n[1], 0, offset_or_null, p->tw[2], p->twr};
+    ZArgs z{x_slab, w_out, (long long)p->n[0] * p->n[1], p->n[2], p->pitch, p->n[1], (long long)p->n[0], offset_or_null, p->tw[2], p->twr};
     if (int rc = launch_zpass(p->dtype, z, st)) return rc;
     prof_mark(st, SLOT_Z);
-    YArgs y{w_out, (long long)p->n[0], p->n[1], p->nzh, p->pitch, 0, p->tw[1], send_out, nyl_log2, nullptr, 0, 0};
+    YArgs y{w_out, (long long)p->n[0], p->n[1], p->nzh, p->pitch, p->tw[1], send_out, nyl_log2, nullptr, 0, 0, 0};
     if (int rc = launch_ypass(p->dtype, y, st)) return rc;
     prof_mark(st, SLOT_Y);
     return T21_OK;
@@ -370,10 +360,11 @@ int t21_slab_stage1_p2p(const t21_plan* p, const void* x_slab, const void* offse
     while ((p->n[1] / nranks) >> (nyl_log2 + 1)) ++nyl_log2;
     cudaStream_t st = (cudaStream_t)stream;
     prof_begin(st);
-    ZArgs z{x_slab, w_scratch, (long long)p->n[0] * p->n[1], p->n[2], p->pitch, p->n[1], 0, offset_or_null, p->tw[2], p->twr};
+    ZArgs z{x_slab, w_scratch, (long long)p->n[0] * p->n[1], p->n[2], p->pitch, p->n[1], (long long)p->n[0], offset_or_null, p->tw[2], p->twr};
     if (int rc = launch_zpass(p->dtype, z, st)) return rc;
     prof_mark(st, SLOT_Z);
-    YArgs y{w_scratch, (long long)p->n[0], p->n[1], p->nzh, p->pitch, 0, p->tw[1], nullptr, nyl_log2, peer_cols, nranks, x0_global};
+    YArgs y{w_scratch, (long long)p->n[0], p->n[1], p->nzh, p->pitch, p->tw[1], nullptr, nyl_log2, peer_cols, nranks, x0_global,
+            (long long)p->n[0] * nranks};
     if (int rc = launch_ypass(p->dtype, y, st)) return rc;
     prof_mark(st, SLOT_Y);
     return T21_OK;
@@ -408,16 +399,20 @@ int t21_peer_free(void* ptr) {
     return T21_OK;
 }
 
-// p: plan of shape (nx, ny/P, nz); w1/w2: this rank's y slab(s) [nx][ny/P][pitch]; iy0: global index of
+// p: plan of shape (nx, ny/P, nz); w1/w2: this rank's y slab(s), chunk-major, as n_xslabs consecutive x slabs
+// (1 for the fused exchange, P for buffers received from an NCCL all-to-all); iy0: global index of
 // local row 0; spec: bin spec of the GLOBAL cube; offsets: the common mean offsets used in stage 1.
-int t21_slab_stage2(const t21_plan* p, const void* w1, const void* w2, int iy0, int ny_global, const void* offset1,
-                    const void* offset2, const t21_binspec* spec, double* sums_out, long long* counts_out,
+int t21_slab_stage2(const t21_plan* p, const void* w1, const void* w2, int n_xslabs, int iy0, int ny_global,
+                    const void* offset1, const void* offset2, const t21_binspec* spec, double* sums_out, long long* counts_out,
                     void* workspace, size_t workspace_bytes, void* stream) {
     if (!p || !w1 || !spec || !sums_out || !counts_out || !workspace) { set_error("null argument"); return T21_EINVAL; }
     if (!p->fast[0]) { set_error("slab mode needs a power-of-two x axis"); return T21_EINVAL; }
     if (spec->n[0] != p->n[0] || spec->n[2] != p->n[2] || spec->n[1] != ny_global || iy0 < 0 || iy0 + p->n[1] > ny_global) {
         set_error("bin spec / slab geometry mismatch"); return T21_EINVAL;
     }
+    if (n_xslabs < 1 || (n_xslabs & (n_xslabs - 1)) || p->n[0] % n_xslabs) { set_error("bad x slab count %d", n_xslabs); return T21_EINVAL; }
+    int xs_log2 = 0;
+    while ((p->n[0] / n_xslabs) >> (xs_log2 + 1)) ++xs_log2;
     const int nf = w2 ? 2 : 1;
     const int nbins = spec->nk * (spec->nmu > 0 ? spec->nmu : 1);
     WsLayout L = ws_layout(p, 0, nbins);
@@ -427,7 +422,7 @@ int t21_slab_stage2(const t21_plan* p, const void* w1, const void* w2, int iy0, 
     XArgs a;
     memset(&a, 0, sizeof(a));
     a.w[0] = w1; a.w[1] = w2; a.nf = nf;
-    a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch; a.xb = 0; a.iy0 = iy0;
+    a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch; a.xs_log2 = xs_log2; a.iy0 = iy0;
     a.tw = p->tw[0];
     a.offset[0] = offset1; a.offset[1] = offset2;
     a.ntot = (double)p->n[0] * ny_global * p->n[2];
@@ -453,9 +448,13 @@ int t21_slab_stage2(const t21_plan* p, const void* w1, const void* w2, int iy0, 
 // n-D output of a slab-sharded cube: the scaled power of this rank's rows, HALF spectrum only,
 // FFT order: out[nx][ny/P][nz/2+1].  The caller assembles the fftshifted rows (the kz < 0 half of a
 // row is the mirrored half of row -ky, which another rank holds; tools21cm_b200/distributed.py).
-int t21_slab_stage2_nd(const t21_plan* p, const void* w1, const void* w2, int iy0, int ny_global, const void* offset1,
-                       const void* offset2, double scale, void* out_half, int out_dtype, void* stream) {
+int t21_slab_stage2_nd(const t21_plan* p, const void* w1, const void* w2, int n_xslabs, int iy0, int ny_global,
+                       const void* offset1, const void* offset2, double scale, void* out_half, int out_dtype,
+                       void* stream) {
     if (!p || !w1 || !out_half) { set_error("null argument"); return T21_EINVAL; }
+    if (n_xslabs < 1 || (n_xslabs & (n_xslabs - 1)) || p->n[0] % n_xslabs) { set_error("bad x slab count %d", n_xslabs); return T21_EINVAL; }
+    int xs_log2 = 0;
+    while ((p->n[0] / n_xslabs) >> (xs_log2 + 1)) ++xs_log2;
     if (!p->fast[0]) { set_error("slab mode needs a power-of-two x axis"); return T21_EINVAL; }
     if (out_dtype != T21_F32 && out_dtype != T21_F64) { set_error("bad output dtype"); return T21_EINVAL; }
     if (iy0 < 0 || iy0 + p->n[1] > ny_global) { set_error("slab geometry mismatch"); return T21_EINVAL; }
@@ -463,7 +462,7 @@ int t21_slab_stage2_nd(const t21_plan* p, const void* w1, const void* w2, int iy
     XArgs a;
     memset(&a, 0, sizeof(a));
     a.w[0] = w1; a.w[1] = w2; a.nf = w2 ? 2 : 1;
-    a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch; a.xb = 0; a.iy0 = iy0;
+    a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch; a.xs_log2 = xs_log2; a.iy0 = iy0;
     a.tw = p->tw[0];
     a.offset[0] = offset1; a.offset[1] = offset2;
     a.ntot = (double)p->n[0] * ny_global * p->n[2];

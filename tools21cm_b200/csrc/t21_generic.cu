@@ -20,7 +20,7 @@ template <typename T> struct GenWZ { static constexpr int value = sizeof(T) == 4
 template <typename T>
 __global__ void __launch_bounds__(kGenThreads)
 gen_zpass_kernel(const T* __restrict__ in, cx<T>* __restrict__ out, long long nrows, int nz, int nzh, int pitch,
-                 int ny, int xb, const T* __restrict__ offset, const cx<T>* __restrict__ roots) {
+                 int ny, long long nxa, const T* __restrict__ offset, const cx<T>* __restrict__ roots) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* row = reinterpret_cast<T*>(smem_raw);
     const T off = offset ? ldg(offset) : (T)0;
@@ -29,7 +29,9 @@ gen_zpass_kernel(const T* __restrict__ in, cx<T>* __restrict__ out, long long nr
         for (int z = threadIdx.x; z < nz; z += kGenThreads) row[z] = in[r * nz + z] - off;
         __syncthreads();
         const long long x = r / ny, y = r - x * ny;
-        const long long orow = ((((x >> xb) * ny + y) << xb) + (x & ((1 << xb) - 1)));
+        constexpr int LW = WLay<T>::LW;
+        const long long cstride = nxa * ny * LW;
+        cx<T>* dst0 = out + (x * ny + y) * LW;
         for (int k = threadIdx.x; k < nzh; k += kGenThreads) {
             T sr = 0, si = 0;
             int idx = 0;                       // k*z mod nz
@@ -40,7 +42,7 @@ gen_zpass_kernel(const T* __restrict__ in, cx<T>* __restrict__ out, long long nr
                 idx += k;
                 if (idx >= nz) idx -= nz;
             }
-            out[orow * pitch + k] = cmake<T>(sr, si);
+            dst0[(long long)(k / LW) * cstride + (k % LW)] = cmake<T>(sr, si);
         }
     }
 }
@@ -48,7 +50,7 @@ gen_zpass_kernel(const T* __restrict__ in, cx<T>* __restrict__ out, long long nr
 // ---- Y: in-place strided pencils --------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kGenThreads)
-gen_ypass_kernel(cx<T>* __restrict__ w, long long nouter, int ny, int nzh, int pitch, int xb,
+gen_ypass_kernel(cx<T>* __restrict__ w, long long nouter, int ny, int nzh, int pitch,
                  const cx<T>* __restrict__ roots) {
     constexpr int WZ = GenWZ<T>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -58,9 +60,10 @@ gen_ypass_kernel(cx<T>* __restrict__ w, long long nouter, int ny, int nzh, int p
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int chunk = (int)(t % nchunks);
         const long long x = t / nchunks;
-        const long long row0 = (((x >> xb) * ny) << xb) + (x & ((1 << xb) - 1));
-        cx<T>* base = w + row0 * pitch + chunk * WZ;
-        const long long stride = (long long)pitch << xb;
+        // WZ == LW here: the tile (all y, one 64-byte piece, fixed x) is one contiguous block
+        static_assert(GenWZ<T>::value == WLay<T>::LW, "generic tiles are one layout piece wide");
+        cx<T>* base = w + ((long long)chunk * nouter + x) * ny * WZ;
+        const long long stride = WZ;
         __syncthreads();
         for (int e = threadIdx.x; e < ny * WZ; e += kGenThreads) {
             const int y = e / WZ, zl = e % WZ;
@@ -89,7 +92,7 @@ gen_ypass_kernel(cx<T>* __restrict__ w, long long nouter, int ny, int nzh, int p
 template <typename T, int NF, int HK>
 __global__ void __launch_bounds__(kGenThreads)
 gen_xpass_kernel(const cx<T>* __restrict__ w0, const cx<T>* __restrict__ w1, int nx, int ny, int nz, int nzh,
-                 int pitch, int xb, const cx<T>* __restrict__ roots, const T* off0, const T* off1, double ntot,
+                 int pitch, const cx<T>* __restrict__ roots, const T* off0, const T* off1, double ntot,
                  const __grid_constant__ t21_binspec B, int nbins, double* __restrict__ part_sum,
                  unsigned* __restrict__ part_cnt, double* gsum, unsigned long long* gcnt, void* nd_out, int nd_f64,
                  double scale) {
@@ -109,17 +112,14 @@ gen_xpass_kernel(const cx<T>* __restrict__ w0, const cx<T>* __restrict__ w1, int
     run_init(acc[1]);
     const int nchunks = (nzh + WZ - 1) / WZ;
     const long long ntiles = (long long)ny * nchunks;
-    const long long gstride = ((long long)ny * pitch) << xb;
-    const int xmask = (1 << xb) - 1;
     const bool signed_mu = B.nmu > 0 && !B.absolute_mus;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int chunk = (int)(t % nchunks), iy = (int)(t / nchunks);
-        const long long ybase = ((long long)iy * pitch) << xb;
         __syncthreads();
         for (int e = threadIdx.x; e < nx * WZ; e += kGenThreads) {
             const int i = e / WZ, zl = e % WZ;
             const bool ok = chunk * WZ + zl < nzh;
-            const long long o = (i >> xb) * gstride + ybase + (long long)(i & xmask) * pitch + chunk * WZ + zl;
+            const long long o = (((long long)chunk * nx + i) * ny + iy) * WZ + zl;      // chunk-major, WZ == LW
             tile0[e] = ok ? w0[o] : cmake<T>(0, 0);
             if (NF == 2) tile1[e] = ok ? w1[o] : cmake<T>(0, 0);
         }
@@ -198,7 +198,7 @@ static int gen_z(const ZArgs& a, cudaStream_t st) {
     if (int rc = ensure_smem(kern, smem)) return rc;
     long long g = a.nrows < (long long)device_sm_count() * 16 ? a.nrows : (long long)device_sm_count() * 16;
     if (g < 1) return 0;
-    kern<<<(unsigned)g, kGenThreads, smem, st>>>((const T*)a.in, (cx<T>*)a.out, a.nrows, a.nz, nzh, a.pitch, a.ny, a.xb,
+    kern<<<(unsigned)g, kGenThreads, smem, st>>>((const T*)a.in, (cx<T>*)a.out, a.nrows, a.nz, nzh, a.pitch, a.ny, a.nxa,
                                                (const T*)a.offset, (const cx<T>*)a.twr);
     count_launch();
     T21_CUDA_OK(cudaGetLastError());
@@ -218,7 +218,7 @@ static int gen_y(const YArgs& a, cudaStream_t st) {
     const long long ntiles = a.nouter * ((a.nzh + WZ - 1) / WZ);
     long long g = ntiles < (long long)device_sm_count() * 8 ? ntiles : (long long)device_sm_count() * 8;
     if (g < 1) return 0;
-    kern<<<(unsigned)g, kGenThreads, smem, st>>>((cx<T>*)a.w, a.nouter, a.ny, a.nzh, a.pitch, a.xb, (const cx<T>*)a.tw);
+    kern<<<(unsigned)g, kGenThreads, smem, st>>>((cx<T>*)a.w, a.nouter, a.ny, a.nzh, a.pitch, (const cx<T>*)a.tw);
     count_launch();
     T21_CUDA_OK(cudaGetLastError());
     return 0;
@@ -247,7 +247,7 @@ static int gen_x(XArgs& a, cudaStream_t st) {
         auto kern = gen_xpass_kernel<T, NF, HKV>;                                                               \
         if (int rc = ensure_smem(kern, smem)) return rc;                                                        \
         kern<<<(unsigned)g, kGenThreads, smem, st>>>((const cx<T>*)a.w[0], (const cx<T>*)a.w[1], a.nx, a.ny, a.nz,  \
-            a.nzh, a.pitch, a.xb, (const cx<T>*)a.tw, (const T*)a.offset[0], (const T*)a.offset[1], a.ntot, B,  \
+            a.nzh, a.pitch, (const cx<T>*)a.tw, (const T*)a.offset[0], (const T*)a.offset[1], a.ntot, B,        \
             a.nbins, a.part_sum, a.part_cnt, a.gsum, a.gcnt, a.nd_out, a.nd_f64, a.scale);                      \
     }
     if (hk == 0) T21_GEN_X(0) else if (hk == 1) T21_GEN_X(1) else T21_GEN_X(2)

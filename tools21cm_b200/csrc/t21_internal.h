@@ -8,16 +8,16 @@
 namespace t21 {
 
 struct ZArgs {
-    const void* in; void* out; long long nrows; int nz; int pitch; int ny; int xb;
+    const void* in; void* out; long long nrows; int nz; int pitch; int ny; long long nxa;   // nxa: x planes in `out`
     const void* offset; const void* tw; const void* twr;
 };
 struct YArgs {
-    void* w; long long nouter; int ny; int nzh; int pitch; int xb; const void* tw;
+    void* w; long long nouter; int ny; int nzh; int pitch; const void* tw;
     void* send; int nyl_log2;          // slab mode: packed all-to-all send buffer (or null)
-    void* const* peers; int npeers; long long xg0;   // slab mode, fused exchange: peer y-slab buffers (or null)
+    void* const* peers; int npeers; long long xg0; long long nx_global;   // fused exchange: peer y-slab buffers (or null)
 };
 struct XArgs {
-    const void* w[2]; int nf; int nx, ny, nz, nzh, pitch; int xb; int iy0;
+    const void* w[2]; int nf; int nx, ny, nz, nzh, pitch; int xs_log2; int iy0;   // xs_log2: log2(x planes per slab), <0 = one slab
     const void* tw; const void* offset[2]; double ntot;
     const t21_binspec* bins;                 // MODE_BIN
     void* nd_out; int nd_f64; int nd_half; double scale;  // MODE_ND

@@ -125,7 +125,8 @@ inline int launch_x(XArgs& a, cudaStream_t st) {
     memset(&p, 0, sizeof(p));
     p.w[0] = (const cx<T>*)a.w[0];
     p.w[1] = (const cx<T>*)a.w[1];
-    p.ny = a.ny; p.nz = a.nz; p.nzh = a.nzh; p.pitch = a.pitch; p.xb = a.xb; p.iy0 = a.iy0;
+    p.ny = a.ny; p.nz = a.nz; p.nzh = a.nzh; p.pitch = a.pitch; p.iy0 = a.iy0;
+    p.xs_log2 = a.xs_log2 >= 0 ? a.xs_log2 : ilog2_rt(a.nx);
     constexpr int WZ = K::THREADS / K::S::TP;
     p.nchunks = (a.nzh + WZ - 1) / WZ;
     p.ntiles = (long long)a.ny * p.nchunks;

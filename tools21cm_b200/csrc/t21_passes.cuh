@@ -2,10 +2,13 @@
 //
 // Data layout (DESIGN.md "HBM layout"):
 //   input   x[nx][ny][nz]            real, C order (z contiguous)
-//   half    W[nx/XB][ny][XB][pitch]  complex, kz = 0..nz/2 valid, pitch = round_up(nz/2+1, 16);
-//                                    x is split as (x / XB, x % XB) around y so that both strided
-//                                    passes walk rows that are at most XB*pitch apart inside a
-//                                    group: row(x, y) = ((x / XB) * ny + y) * XB + x % XB
+//   half    W[nch][nx][ny][LW]       complex, "chunk major": the kz axis is cut into 64-byte pieces of
+//                                    LW = 8 (fp32) / 4 (fp64) columns and the piece index is the SLOWEST
+//                                    axis.  A Y-pass tile (all y, one piece, fixed x) is then one contiguous
+//                                    block, an X-pass tile reads 64-byte pieces ny*64 B apart inside one
+//                                    piece-plane, and the Z pass writes LW columns of its 8 consecutive rows
+//                                    as one 512-byte run.  kz = 0..nz/2 valid, nch = pitch / LW,
+//                                    pitch = round_up(nz/2+1, 16).
 //
 //   ZPass : rows along z.  Packs a real row into nz/2 complex values, FFTs it and untangles
 //           the result into the nz/2+1 non-redundant frequencies (the classic real-FFT trick),
@@ -23,6 +26,33 @@
 #include "t21_config.h"
 
 namespace t21 {
+
+// element offset of (x, y, kz) in a chunk-major half-spectrum array of nxa x planes and nya y rows.
+// Arrays received from an NCCL all-to-all are a sequence of x slabs, each chunk-major on its own:
+// xs_log2 = log2(planes per slab), slab = elements per slab (for a plain array one slab holds everything).
+template <typename T>
+struct WLay {
+    static constexpr int LW = 64 / (int)sizeof(cx<T>);
+    static constexpr int LWS = ilog2(LW);
+    long long nya;        // y rows in this array
+    long long slab;       // elements per x slab
+    int xs_log2;          // log2(x planes per slab)
+    T21_HD long long off(long long x, long long y, int kz) const {
+        const long long nxs = 1LL << xs_log2;
+        return (x >> xs_log2) * slab + (((((long long)(kz >> LWS) << xs_log2) + (x & (nxs - 1))) * nya + y) << LWS) +
+               (kz & (LW - 1));
+    }
+};
+template <typename T>
+T21_HD WLay<T> make_wlay(long long nxa, long long nya, int pitch, int xs_log2) {
+    WLay<T> w;
+    w.nya = nya;
+    w.xs_log2 = xs_log2;
+    w.slab = (long long)pitch * nya << xs_log2;
+    (void)nxa;
+    return w;
+}
+T21_HD int ilog2_rt(long long n) { int l = 0; while ((1LL << (l + 1)) <= n) ++l; return l; }
 
 // ======================================================================================
 // Z pass
@@ -43,10 +73,11 @@ struct ZPass {
 
     struct Params {
         const T* in;          // [nrows][NZ]
-        cx<T>* out;           // [nrows][pitch]
+        cx<T>* out;           // chunk-major half spectrum of nrows / ny x planes
         long long nrows;
         int pitch;
-        int ny, xb;           // rows are (x, y) pairs; xb = log2 of the x blocking factor XB
+        int ny;               // rows are (x, y) pairs
+        long long cstride;    // elements between 64-byte pieces of `out`: (x planes) * ny * LW
         const T* offset;      // device scalar subtracted from every sample, or null
         const cx<T>* tw;      // Plan<M> stage twiddles
         const cx<T>* twr;     // exp(-2 pi i k / NZ), k = 0..M
@@ -81,26 +112,43 @@ struct ZPass {
         } else {
             // untangle: X[k] = (Z[k] + conj Z[M-k])/2 - i/2 * w^k * (Z[k] - conj Z[M-k]),  w = exp(-2 pi i / NZ).
             // k and M-k need the same two inputs and w^(M-k) = -conj(w^k), so one thread produces both.
-            if (!active) return;
-            const long long x = row / p.ny, y = row - x * p.ny;
-            const long long orow = ((((x >> p.xb) * p.ny + y) << p.xb) + (x & ((1 << p.xb) - 1)));
-            cx<T>* dst = p.out + orow * p.pitch;
-            auto pair = [&](int k) {
-                const cx<T> zk = ld_smem(k), zm = ld_smem((M - k) & (M - 1));
+            constexpr int LW = WLay<T>::LW, LWS = WLay<T>::LWS;
+            const long long cstride = p.cstride;
+            // Work is re-dealt for the stores: a warp takes LW consecutive k of 32/LW consecutive rows, so that
+            // one store instruction writes one contiguous run (the rows of a CTA are consecutive in y and a
+            // 64-byte piece of row y+1 follows that of row y in the chunk-major layout).
+            constexpr int HALF = M / 2;
+            constexpr bool kDeal = (HALF % LW == 0) && (THREADS % (LW * ROWS) == 0) && (HALF / LW) % (THREADS / (LW * ROWS)) == 0;
+            auto pair_at = [&](int rsub, int k) {
+                const long long rw = cta * ROWS + rsub;
+                if (rw >= p.nrows) return;
+                const cx<T>* zr = smem + rsub * ROWPITCH;
+                const cx<T> zk = zr[pad(k)], zm = zr[pad((M - k) & (M - 1))];
                 const cx<T> w = ldg(p.twr + k);
                 const cx<T> a = cmake<T>(zk.x + zm.x, zk.y - zm.y);       // Z[k] + conj Z[M-k]
                 const cx<T> d = cmake<T>(zk.x - zm.x, zk.y + zm.y);       // Z[k] - conj Z[M-k]
                 const cx<T> t = cmul(w, d);
-                dst[k] = cmake<T>((T)0.5 * (a.x + t.y), (T)0.5 * (a.y - t.x));
-                // partner: conj(a) - i/2 * (-conj w) * (-conj d) = conj(a)/2 - i/2 * conj(t)
-                dst[M - k] = cmake<T>((T)0.5 * (a.x - t.y), (T)0.5 * (-a.y - t.x));
+                cx<T>* d0 = p.out + (rw << LWS);      // row (x, y) sits at x * ny + y = rw
+                d0[(long long)(k >> LWS) * cstride + (k & (LW - 1))] = cmake<T>((T)0.5 * (a.x + t.y), (T)0.5 * (a.y - t.x));
+                // partner: conj(a)/2 - i/2 * conj(t)
+                const int km = M - k;
+                d0[(long long)(km >> LWS) * cstride + (km & (LW - 1))] = cmake<T>((T)0.5 * (a.x - t.y), (T)0.5 * (-a.y - t.x));
             };
+            if constexpr (kDeal) {
+                constexpr int GROUPS = THREADS / (LW * ROWS);          // k pieces handled per step by the CTA
+                const int l = tid % LW, rsub = (tid / LW) % ROWS, g = tid / (LW * ROWS);
 #pragma unroll
-            for (int i = 0; i < (E + 1) / 2; ++i) {
-                const int k = j + i * TP;
-                if (k < M / 2 || (M / 2 == 0)) pair(k);
+                for (int it = 0; it < (HALF / LW) / GROUPS; ++it) pair_at(rsub, (g + it * GROUPS) * LW + l);
+                if (g == 0 && l == 0) pair_at(rsub, HALF);             // self-paired middle sample of every row
+            } else {
+                if (!active) return;
+#pragma unroll
+                for (int i = 0; i < (E + 1) / 2; ++i) {
+                    const int k = j + i * TP;
+                    if (k < HALF || HALF == 0) pair_at(tid / TP, k);
+                }
+                if (j == 0 && M >= 2) pair_at(tid / TP, HALF);
             }
-            if (j == 0 && M >= 2) pair(M / 2);                            // self-paired middle sample
         }
     }
 };
@@ -161,21 +209,22 @@ struct YPass {
     static constexpr int MIN_CTAS = S::E > 16 ? 1 : (kByRegs < kBySmem ? kByRegs : (kBySmem < 1 ? 1 : kBySmem));
 
     struct Params {
-        cx<T>* w;             // [nouter][NY][pitch]
+        cx<T>* w;             // chunk-major, nouter x planes of NY rows
         int nzh;              // valid columns
         int pitch;
         int nchunks;          // ceil(nzh / WZ)
-        int xb;               // log2 of the x blocking factor
+        long long cstride;    // elements between 64-byte pieces: nouter * NY * LW
         const cx<T>* tw;
-        // slab-sharded cubes: write the result straight into the all-to-all send buffer
-        // [P][nouter][NY/P][pitch] instead of in place (pack fused into the store); null otherwise
+        // slab-sharded cubes: write the result straight into the all-to-all send buffer (P blocks, block s =
+        // the chunk-major [nch][nouter][NY/P][LW] part for rank s) instead of in place; null otherwise
         cx<T>* send;
         int nyl_log2;         // log2(NY / P)
         long long nouter;     // x planes in this slab
-        // SEND == 2: peer[s] = rank s's y-slab buffer [nx][NY/P][pitch] (peer-mapped); this slab's planes
-        // start at global x = xg0
+        // SEND == 2: peer[s] = rank s's chunk-major y-slab buffer [nch][nx][NY/P][LW] (peer-mapped); this
+        // slab's planes start at global x = xg0
         cx<T>* peer[SEND == 2 ? kMaxPeers : 1];
         long long xg0;
+        long long peer_cstride;   // nx * (NY/P) * LW
     };
     struct Regs {
         cx<T> v[S::E];
@@ -184,13 +233,15 @@ struct YPass {
     template <int PH>
     static T21_HD void phase(const Params& p, long long cta, int tid, Regs& r, cx<T>* smem) {
         const int zl = tid % WZ, j = tid / WZ;
-        const int chunk = (int)(cta % p.nchunks);
-        const long long outer = cta / p.nchunks;
+        // tile counts fit 31 bits (launch_tiles checks): 32-bit division, the 64-bit one costs ~0.2 ms a pass
+        const unsigned outer32 = (unsigned)cta / (unsigned)p.nchunks;
+        const int chunk = (int)((unsigned)cta - outer32 * (unsigned)p.nchunks);
+        const long long outer = outer32;
         const int z = chunk * WZ + zl;
-        // outer = x: rows of this pencil are ((x / XB) * NY + y) * XB + x % XB
-        const long long row0 = (((outer >> p.xb) * NY) << p.xb) + (outer & ((1 << p.xb) - 1));
-        cx<T>* base = p.w + row0 * p.pitch + z;
-        const long long stride = (long long)p.pitch << p.xb;
+        // pencil (x = outer, column z): y rows are LW elements apart inside one contiguous block
+        constexpr int LW = WLay<T>::LW, LWS = WLay<T>::LWS;
+        cx<T>* base = p.w + (long long)(z >> LWS) * p.cstride + ((outer * NY) << LWS) + (z & (LW - 1));
+        const long long stride = LW;
         using P = typename S::P;
         // rows are visited in loop order, so both the first-stage loads and the last-stage stores walk
         // a cursor instead of multiplying an index by the run-time row stride
@@ -206,14 +257,17 @@ struct YPass {
 #endif
             [&](int i, cx<T> val, int) {
                 if constexpr (SEND == 1) {
-                    // destination rank i >> nyl_log2 gets row (x, i mod NY/P) of its y slab
-                    const long long row = (((long long)(i >> p.nyl_log2) * p.nouter + outer) << p.nyl_log2) +
-                                          (i & ((1 << p.nyl_log2) - 1));
-                    p.send[row * p.pitch + z] = val;
+                    // block of rank i >> nyl_log2, chunk-major [nch][nouter][NY/P][LW] inside the block
+                    const long long blk = ((long long)p.pitch * p.nouter) << p.nyl_log2;
+                    const long long o = (((((long long)(z >> LWS) * p.nouter + outer) << p.nyl_log2) +
+                                          (i & ((1 << p.nyl_log2) - 1))) << LWS) + (z & (LW - 1));
+                    p.send[(long long)(i >> p.nyl_log2) * blk + o] = val;
                 } else if constexpr (SEND == 2) {
-                    // the same element, written into rank (i >> nyl_log2)'s memory: row (global x, i mod NY/P)
-                    const long long row = ((p.xg0 + outer) << p.nyl_log2) + (i & ((1 << p.nyl_log2) - 1));
-                    p.peer[i >> p.nyl_log2][row * p.pitch + z] = val;
+                    // the same element, written into rank (i >> nyl_log2)'s chunk-major [nch][nx][NY/P][LW]
+                    const long long o = (long long)(z >> LWS) * p.peer_cstride +
+                                        ((((p.xg0 + outer) << p.nyl_log2) + (i & ((1 << p.nyl_log2) - 1))) << LWS) +
+                                        (z & (LW - 1));
+                    p.peer[i >> p.nyl_log2][o] = val;
                 } else {
                     *sc.next() = val;
                 }
@@ -257,11 +311,11 @@ struct XPass {
     using Acc = typename Pick<(THREADS % 32 == 0), WarpBins<(MU != 0)>, ThreadBins>::type;
 
     struct Params {
-        const cx<T>* w[2];    // [NX][ny][pitch] per field
+        const cx<T>* w[2];    // chunk-major per field: NX planes of ny rows (possibly as a sequence of x slabs)
         int ny, nz, nzh, pitch, nchunks;
         long long ntiles;     // ny * nchunks
         long long tile_step;  // tiles between two consecutive tiles of one CTA (the grid size)
-        int xb;               // log2 of the x blocking factor
+        int xs_log2;          // log2(x planes per slab): log2(NX) for a plain array, log2(NX/P) after an NCCL exchange
         int iy0;              // global ky index of local row 0 (slab-sharded cubes; 0 otherwise)
         const cx<T>* tw;
         const T* offset[2];   // device scalars (mean offsets) or null
@@ -285,35 +339,21 @@ struct XPass {
     template <int PH, class Hist>
     static T21_HD void phase(const Params& p, long long tile, int tid, Regs& r, cx<T>* smem, Hist& hist) {
         const int zl = tid % WZ, j = tid / WZ;
-        const int chunk = (int)(tile % p.nchunks);
-        const int iy_loc = (int)(tile / p.nchunks);        // row inside this rank's y slab (addressing)
+        // ky fastest: CTAs running together read neighbouring 64-byte pieces of the same piece-plane
+        const int chunk = (int)((unsigned)tile / (unsigned)p.ny);       // 32-bit division: ntiles < 2^31
+        const int iy_loc = (int)((unsigned)tile - (unsigned)chunk * (unsigned)p.ny);   // row inside this rank's y slab
         const int iy = iy_loc + p.iy0;                     // global ky index (tables, DC, exclusions)
         const int iz = chunk * WZ + zl;
         const bool active = iz < p.nzh;
         if constexpr (PH < NF * S::FFT_PHASES) {
             constexpr int F = PH / S::FFT_PHASES;          // field this phase works on
             constexpr int FPH = PH % S::FFT_PHASES;
-            // element i (= x) lives in row ((i / XB) * ny + iy) * XB + i % XB
-            const cx<T>* base = p.w[F] + iz;     // scratch columns of the last chunk are read too (in bounds)
-            const long long gstride = ((long long)p.ny * p.pitch) << p.xb;     // between x groups
-            const long long ybase = ((long long)iy_loc * p.pitch) << p.xb;
-            const int xmask = (1 << p.xb) - 1;
-            // first-stage rows in loop order: row(i) is linear in (b, k) because the point stride and the
-            // thread count of a pencil are multiples of XB (t21_plan_create keeps XB <= NX/16)
-            constexpr int R0 = P::radix(0);
-            const cx<T>* row_j = base + (long long)(j >> p.xb) * gstride + ybase + (long long)(j & xmask) * p.pitch;
-            RowCursor<const cx<T>> lc(row_j, (long long)((NX / R0) >> p.xb) * gstride,
-                                      (long long)(P::T >> p.xb) * gstride, R0);
-            S::template fft_phase<FPH>(
-                r.v[F], j, zl, p.tw, smem,
-                [&](int i) {
-#ifdef T21_DBG_NOLOAD
-                    return cmake<T>((T)i, (T)zl);
-#else
-                    return *lc.next();
-#endif
-                },
-                [&](int i, cx<T> b, int slot) {
+            // element i (= x) of this pencil sits at WLay::off(i, iy_loc, iz) = off(0, iy_loc, iz) + xi(i) * xstr
+            // with xi(i) = i + (i >> xs_log2) * D: plane i of a sequence of x slabs (D = 0 for a plain array)
+            constexpr int LW = WLay<T>::LW, LWS = WLay<T>::LWS;
+            const long long xstr = (long long)p.ny << LWS;
+            const cx<T>* base = p.w[F] + (((((long long)(iz >> LWS) << p.xs_log2) * p.ny) + iy_loc) << LWS) + (iz & (LW - 1));
+            auto fin = [&](int i, cx<T> b, int slot) {
                     // last stage of field F: element i (= kx) is final and sits in register `slot`.
                     // Field 0 of a cross spectrum just stays there; the last field forms the power.
                     if constexpr (F == NF - 1) {
@@ -337,7 +377,21 @@ struct XPass {
                         }
                         ptile(smem)[i * WZ + zl] = pw;
                     }
-                });
+                };
+#ifdef T21_DBG_NOLOAD
+            S::template fft_phase<FPH>(r.v[F], j, zl, p.tw, smem, [&](int i) { return cmake<T>((T)i, (T)zl); }, fin);
+#else
+            if (FPH != 0 || (NX >> p.xs_log2) <= 1) {
+                // plain array (and every phase that does not load): rows are linear in x, walked by a cursor
+                constexpr int R0 = P::radix(0);
+                RowCursor<const cx<T>> lc(base + (long long)j * xstr, (long long)(NX / R0) * xstr, (long long)P::T * xstr, R0);
+                S::template fft_phase<FPH>(r.v[F], j, zl, p.tw, smem, [&](int) { return *lc.next(); }, fin);
+            } else {
+                const long long D = ((long long)(p.pitch >> LWS) - 1) << p.xs_log2;
+                S::template fft_phase<FPH>(r.v[F], j, zl, p.tw, smem,
+                                           [&](int i) { return base[(i + (long long)(i >> p.xs_log2) * D) * xstr]; }, fin);
+            }
+#endif
         } else {
             epilogue(p, tid, iy, iy_loc, iz, zl, active, r, smem, hist);
         }

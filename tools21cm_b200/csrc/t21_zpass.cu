@@ -9,7 +9,8 @@ static int launch_zpass_t(const ZArgs& a, cudaStream_t st) {
 #define ZCASE(N)                                                                                   \
     {                                                                                              \
         using K = ZPass<N, T>;                                                                     \
-        typename K::Params p{(const T*)a.in, (cx<T>*)a.out, a.nrows, a.pitch, a.ny, a.xb, (const T*)a.offset,  \
+        typename K::Params p{(const T*)a.in, (cx<T>*)a.out, a.nrows, a.pitch, a.ny,                \
+                             a.nxa * a.ny * WLay<T>::LW, (const T*)a.offset,                        \
                              (const cx<T>*)a.tw, (const cx<T>*)a.twr};                             \
         return launch_tiles<K, T>(p, (a.nrows + K::ROWS - 1) / K::ROWS, st);                       \
     }

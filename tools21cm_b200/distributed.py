@@ -18,8 +18,13 @@ The exchange has two implementations (``T21_EXCHANGE=p2p|nccl``):
   into the buffer of the rank that owns it, over NVLink 5 / NVSwitch: no send buffer, no collective, the
   transfer overlaps the transform tile by tile.  A one-element all-reduce orders the stages.
 * ``nccl``: ``all_to_all`` over NCCL in 4 pieces pipelined against the Z/Y passes; rank r sends rank s the block
-  W[x in slab r, y in slab s, :], packed by the Y pass so that the receive buffer *is* the [nx][ny/P][pitch]
-  array stage 2 reads (no pack or unpack pass).
+  W[x in slab r, y in slab s, :], packed by the Y pass so that the receive buffer *is* the sequence of x slabs
+  stage 2 reads (no pack or unpack pass).
+
+Device half spectra are CHUNK-MAJOR: [pitch/LW][x][y][LW] with LW = 8 (fp32) or 4 (fp64)
+complex values, i.e. 64-byte pieces of a z row.  A y slab is handed to stage 2 as ``n_xslabs`` consecutive x
+slabs, each chunk-major on its own: 1 for the fused exchange, P x pieces for buffers filled by the all-to-all.
+Tensors carrying them are shaped [x][y][pitch] for their sizes only (``YSlab``).
 
 ``backend`` lets the CPU tests (gloo, world_size 2) replace the two CUDA stages by a numpy model
 while exercising exactly this partitioning, packing, offset and reduction code.
@@ -67,6 +72,14 @@ def batched(fn, items, group=None):
     return out
 
 
+class YSlab:
+    """This rank's y slab of one field after the re-partition: ``data`` holds nx * nyl * pitch complex values
+    as ``n_xslabs`` consecutive x slabs (each chunk-major for the CUDA backend, row-major for the CPU model)."""
+
+    def __init__(self, data, nx, nyl, pitch, n_xslabs=1):
+        self.data, self.nx, self.nyl, self.pitch, self.n_xslabs = data, nx, nyl, pitch, n_xslabs
+
+
 # ------------------------------------------------------------------------------------------
 # backends: the two local stages
 # ------------------------------------------------------------------------------------------
@@ -86,8 +99,9 @@ class CudaBackend:
         return (nz // 2 + 1 + 15) // 16 * 16
 
     def stage1(self, x, offset, send_world=0):
-        """Z and Y passes of an x slab.  send_world = 0: returns W [nxl][ny][pitch].  send_world = P:
-        returns the packed all-to-all send buffer [P][nxl][ny/P][pitch] (pack fused into the Y pass)."""
+        """Z and Y passes of an x slab.  send_world = 0: returns W, nxl * ny * pitch values, chunk-major.
+        send_world = P: returns the packed all-to-all send buffer [P][nxl * ny/P * pitch], block s = the
+        chunk-major part for rank s (pack fused into the Y pass)."""
         import torch
         lib = _lib.load()
         dev = self._ps._device(x.device.index)
@@ -98,7 +112,8 @@ class CudaBackend:
         w = torch.empty((x.shape[0], x.shape[1], pitch), dtype=cdt, device=x.device)
         send = None
         if send_world:
-            send = torch.empty((send_world, x.shape[0], x.shape[1] // send_world, pitch), dtype=cdt, device=x.device)
+            send = torch.empty((send_world, x.shape[0] * (x.shape[1] // send_world) * pitch), dtype=cdt,
+                               device=x.device)
         rc = lib.t21_slab_stage1(plan, x.data_ptr(), offset.data_ptr() if offset is not None else None,
                                  w.data_ptr(), send.data_ptr() if send is not None else None, int(send_world),
                                  self._ps._stream_ptr(torch, x.device.index))
@@ -124,10 +139,10 @@ class CudaBackend:
     def stage2(self, cols, iy0, ny_global, nz, offsets, spec_key, spec_builder):
         import torch
         lib = _lib.load()
-        w = cols[0]
+        w = cols[0].data
         dev = self._ps._device(w.device.index)
         code = _lib.T21_F32 if w.dtype == torch.complex64 else _lib.T21_F64
-        nx, nyl = w.shape[0], w.shape[1]
+        nx, nyl = cols[0].nx, cols[0].nyl
         plan = dev.plan((nx, nyl, nz), code)
         spec, cspec, _own = dev.spec(((nx, ny_global, nz), spec_key), spec_builder)
         nb = spec.nbins
@@ -136,8 +151,8 @@ class CudaBackend:
         sums = torch.empty(nb, dtype=torch.float64, device=w.device)
         counts = torch.empty(nb, dtype=torch.int64, device=w.device)
         o = [t.data_ptr() if t is not None else None for t in offsets] + [None]
-        rc = lib.t21_slab_stage2(plan, cols[0].data_ptr(), cols[1].data_ptr() if len(cols) == 2 else None,
-                                 int(iy0), int(ny_global), o[0], o[1], C.byref(cspec), sums.data_ptr(),
+        rc = lib.t21_slab_stage2(plan, w.data_ptr(), cols[1].data.data_ptr() if len(cols) == 2 else None,
+                                 int(cols[0].n_xslabs), int(iy0), int(ny_global), o[0], o[1], C.byref(cspec), sums.data_ptr(),
                                  counts.data_ptr(), ws.data_ptr(), ws.numel(),
                                  self._ps._stream_ptr(torch, w.device.index))
         _lib.check(rc, "t21_slab_stage2")
@@ -148,15 +163,16 @@ class CudaBackend:
         """Scaled power of this rank's rows, half spectrum, FFT order: [nx][ny/P][nz/2+1]."""
         import torch
         lib = _lib.load()
-        w = cols[0]
+        w = cols[0].data
         dev = self._ps._device(w.device.index)
         code = _lib.T21_F32 if w.dtype == torch.complex64 else _lib.T21_F64
-        nx, nyl = w.shape[0], w.shape[1]
+        nx, nyl = cols[0].nx, cols[0].nyl
         plan = dev.plan((nx, nyl, nz), code)
         out = torch.empty((nx, nyl, nz // 2 + 1), dtype=out_dtype, device=w.device)
         o = [t.data_ptr() if t is not None else None for t in offsets] + [None]
-        rc = lib.t21_slab_stage2_nd(plan, cols[0].data_ptr(), cols[1].data_ptr() if len(cols) == 2 else None,
-                                    int(iy0), int(ny_global), o[0], o[1], float(scale), out.data_ptr(),
+        rc = lib.t21_slab_stage2_nd(plan, w.data_ptr(), cols[1].data.data_ptr() if len(cols) == 2 else None,
+                                    int(cols[0].n_xslabs), int(iy0), int(ny_global), o[0], o[1], float(scale),
+                                    out.data_ptr(),
                                     _lib.T21_F32 if out_dtype == torch.float32 else _lib.T21_F64,
                                     self._ps._stream_ptr(torch, w.device.index))
         _lib.check(rc, "t21_slab_stage2_nd")
@@ -167,21 +183,21 @@ class CudaBackend:
 # the sharded estimator
 # ------------------------------------------------------------------------------------------
 def exchange(w_slab, world, group=None):
-    """[nx/P][ny][pitch] on every rank  ->  [nx][ny/P][pitch] on every rank (pack + one all-to-all).
-    Generic form used by backends without a fused pack (the CPU model)."""
+    """Row-major [nx/P][ny][pitch] on every rank  ->  row-major [nx][ny/P][pitch] on every rank (pack + one
+    all-to-all).  Generic form used by backends without a fused pack (the CPU model)."""
     nxl, ny, pitch = w_slab.shape
     if ny % world:
         raise ValueError("the y axis (%d) must be divisible by the number of ranks (%d)" % (ny, world))
     nyl = ny // world
     if world == 1:
-        return w_slab
+        return YSlab(w_slab, nxl, ny, pitch)
     send = w_slab.view(nxl, world, nyl, pitch).permute(1, 0, 2, 3).contiguous()   # [P][nx/P][ny/P][pitch]
-    return all_to_all_packed(send, group).view(world * nxl, nyl, pitch)
+    return YSlab(all_to_all_packed(send, group).view(world * nxl, nyl, pitch), world * nxl, nyl, pitch)
 
 
 def all_to_all_packed(send, group=None):
-    """send [P][nxl][nyl][pitch] (block s goes to rank s) -> recv [P][nxl][nyl][pitch] (block s came from
-    rank s), i.e. the [nx][nyl][pitch] y slab.  Complex tensors travel as (re, im) pairs."""
+    """send [P][...] (block s goes to rank s) -> recv [P][...] (block s came from rank s).  Complex tensors
+    travel as (re, im) pairs."""
     import torch
     recv = torch.empty_like(send)
     _dist().all_to_all_single(torch.view_as_real(recv).view(-1), torch.view_as_real(send).view(-1), group=group)
@@ -190,27 +206,28 @@ def all_to_all_packed(send, group=None):
 
 def pipelined_exchange(backend, x, offset, world, group=None, chunks=4):
     """Stage 1 and the re-partition of one field, overlapped: the slab is cut into `chunks` pieces along
-    x; while NCCL moves piece c over NVLink, the Z and Y passes of piece c+1 run.  Returns the y slab
-    [nx][ny/P][pitch] once every piece has arrived."""
+    x; while NCCL moves piece c over NVLink, the Z and Y passes of piece c+1 run.  The receive buffer
+    [P][chunks][piece] is the y slab as P * chunks consecutive x slabs, which is what stage 2 reads."""
     import torch
-    nxl, ny, _nz = x.shape
+    nxl, ny, nz = x.shape
     nyl = ny // world
     while chunks > 1 and (nxl % chunks or nxl // chunks < 4):
         chunks //= 2
     nc = nxl // chunks
-    recv4 = None
+    pitch = backend.pitch(nz)
+    recv = None
     works, keep = [], []
     for c in range(chunks):
-        send = backend.stage1(x[c * nc:(c + 1) * nc], offset, send_world=world)     # [P][nc][nyl][pitch]
-        if recv4 is None:
-            recv4 = send.new_empty((world, nxl, nyl, send.shape[3]))
-        outs = [torch.view_as_real(recv4[s, c * nc:(c + 1) * nc]) for s in range(world)]
+        send = backend.stage1(x[c * nc:(c + 1) * nc], offset, send_world=world)     # [P][nc * nyl * pitch]
+        if recv is None:
+            recv = send.new_empty((world, chunks, send.shape[1]))
+        outs = [torch.view_as_real(recv[s, c]) for s in range(world)]
         ins = [torch.view_as_real(send[s]) for s in range(world)]
         works.append(_dist().all_to_all(outs, ins, group=group, async_op=True))
         keep.append(send)
     for w in works:
         w.wait()
-    return recv4.view(world * nxl, nyl, recv4.shape[3])
+    return YSlab(recv, world * nxl, nyl, pitch, n_xslabs=world * chunks)
 
 
 class _RawCuda:
@@ -282,7 +299,7 @@ def fused_exchange(backend, x, offset, world, rank, field, group=None):
     backend.stage1_p2p(x, offset, bufs.ptrs[par], world, rank * nxl)
     flag = torch.zeros(1, device=x.device)
     _dist().all_reduce(flag, group=group)
-    return torch.view_as_complex(bufs.local[par])
+    return YSlab(torch.view_as_complex(bufs.local[par]), world * nxl, nyl, pitch)      # chunk-major, one x slab
 
 
 def _forward(slabs, group, backend):
@@ -316,7 +333,8 @@ def _forward(slabs, group, backend):
         elif cuda:
             cols.append(pipelined_exchange(backend, x, off, world, group))
         else:
-            cols.append(exchange(backend.stage1(x, off), world, group))
+            w = backend.stage1(x, off)
+            cols.append(exchange(w, world, group) if world > 1 else YSlab(w, nxl, ny, w.shape[2]))
     return cols, offsets, world, rank, shape
 
 

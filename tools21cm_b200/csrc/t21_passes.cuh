@@ -485,18 +485,13 @@ struct XPass {
                         }
                     }
                 };
-                // loop-carried addresses, made opaque so they are advanced, not recomputed from the thread id
-                const T* plo_p = pt2 + r0 * WZ;
-                const T* phi_p = pt2 + ((NX - r0) & (NX - 1)) * WZ;      // row 0 pairs with itself
-                const float* sx_p = B.tab_sf[0] + r0;
+                // loop-carried row index, made opaque so it is advanced, not recomputed from the thread id
+                // (an integer, not a pointer: the tile accesses must stay shared-memory loads)
                 int ix = r0;
-                asm volatile("" : "+l"(plo_p), "+l"(phi_p), "+l"(sx_p), "+r"(ix));
+                asm volatile("" : "+r"(ix));
 #pragma unroll 1
                 for (int it = 0; it < EH; ++it) {
-                    step(ix, plo_p, phi_p, sx_p, true, ix == 0);
-                    plo_p += RPI * WZ;
-                    phi_p = pt2 + (NX - ix - RPI) * WZ;
-                    sx_p += RPI;
+                    step(ix, pt2 + ix * WZ, pt2 + ((NX - ix) & (NX - 1)) * WZ, B.tab_sf[0] + ix, true, ix == 0);   // row 0 pairs with itself
                     ix += RPI;
                 }
                 if (tid < 32) step(NX / 2, pt2 + (NX / 2) * WZ, pt2 + (NX / 2) * WZ, B.tab_sf[0] + NX / 2, q == 0, true);

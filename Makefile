@@ -3,8 +3,8 @@ NVCC      ?= nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr $(EXTRA_NVFLAGS)
 SRC_DIR   := tools21cm_b200/csrc
-BUILD_DIR := build/t21ps
-LIB       := tools21cm_b200/lib/libt21ps.so
+BUILD_DIR ?= build/t21ps
+LIB       ?= tools21cm_b200/lib/libt21ps.so
 SRCS      := $(wildcard $(SRC_DIR)/*.cu)
 OBJS      := $(patsubst $(SRC_DIR)/%.cu,$(BUILD_DIR)/%.o,$(SRCS))
 HDRS      := $(wildcard $(SRC_DIR)/*.cuh) $(wildcard $(SRC_DIR)/*.h) include/t21ps.h

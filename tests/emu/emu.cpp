@@ -68,7 +68,8 @@ static void xpass_mu(const cx<T>* w0, const cx<T>* w1, int ny, int nz, int pitch
     p.w[0] = w0; p.w[1] = w1;
     p.ny = ny; p.nz = nz; p.nzh = nz / 2 + 1; p.pitch = pitch;
     p.nchunks = (p.nzh + WZ - 1) / WZ;
-    p.ntiles = (long long)ny * p.nchunks;
+    constexpr int PARTS = WZ < WLay<T>::LW ? WLay<T>::LW / WZ : 1;
+    p.ntiles = (long long)ny * ((p.nchunks + PARTS - 1) / PARTS) * PARTS;
     p.tile_step = nctas_emulated;
     p.xs_log2 = ilog2_rt(NX);
     (void)xb;

@@ -14,7 +14,7 @@ import numpy as np
 
 T21_F32, T21_F64 = 0, 1
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libt21ps.so")
+LIB_PATH = os.environ.get("T21PS_LIB") or os.path.join(_HERE, "lib", "libt21ps.so")   # override: kernel experiments
 
 
 class BinSpecC(C.Structure):

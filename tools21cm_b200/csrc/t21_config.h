@@ -34,4 +34,14 @@ struct WZFor {
                                                 : (N <= 512 ? 8 : (N <= 2048 ? 4 : 2));
 };
 
+// The X pass may own fewer columns per CTA than the Y pass (half a 64-byte piece): smaller CTAs, more of
+// them per SM, barriers that stall fewer warps.  The pieces' parts are consecutive tiles.
+#ifndef T21_WZ_X
+#define T21_WZ_X T21_WZ_LONG
+#endif
+template <typename T, int N>
+struct WZForX {
+    static constexpr int value = (sizeof(T) == 4 && N == 1024) ? T21_WZ_X : WZFor<T, N>::value;
+};
+
 }  // namespace t21

@@ -45,7 +45,7 @@ struct NoHist {
 // in shared memory until the end (HK = 0), accumulates into global memory (HK = 1), or has no
 // histogram at all (HK = 2, n-D store).
 template <class K, typename T, int HK>
-__global__ void __launch_bounds__(K::THREADS, (K::THREADS * K::E <= 512 * 16 ? T21_X_MIN_CTAS : 1))
+__global__ void __launch_bounds__(K::THREADS, (K::THREADS * K::E <= 512 * 16 ? (K::THREADS == 256 && K::E == 16 ? 2 * T21_X_MIN_CTAS : T21_X_MIN_CTAS) : 1))
 xpass_kernel(const __grid_constant__ typename K::Params p, int nbins, int warp_private,
              double* __restrict__ part_sum, unsigned* __restrict__ part_cnt, double* gsum, unsigned long long* gcnt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -129,7 +129,8 @@ inline int launch_x(XArgs& a, cudaStream_t st) {
     p.xs_log2 = a.xs_log2 >= 0 ? a.xs_log2 : ilog2_rt(a.nx);
     constexpr int WZ = K::THREADS / K::S::TP;
     p.nchunks = (a.nzh + WZ - 1) / WZ;
-    p.ntiles = (long long)a.ny * p.nchunks;
+    constexpr int PARTS = WZ < WLay<T>::LW ? WLay<T>::LW / WZ : 1;     // see XPass::phase
+    p.ntiles = (long long)a.ny * ((p.nchunks + PARTS - 1) / PARTS) * PARTS;
     p.tw = (const cx<T>*)a.tw;
     p.offset[0] = (const T*)a.offset[0];
     p.offset[1] = (const T*)a.offset[1];

@@ -340,8 +340,13 @@ struct XPass {
     static T21_HD void phase(const Params& p, long long tile, int tid, Regs& r, cx<T>* smem, Hist& hist) {
         const int zl = tid % WZ, j = tid / WZ;
         // ky fastest: CTAs running together read neighbouring 64-byte pieces of the same piece-plane
-        const int chunk = (int)((unsigned)tile / (unsigned)p.ny);       // 32-bit division: ntiles < 2^31
-        const int iy_loc = (int)((unsigned)tile - (unsigned)chunk * (unsigned)p.ny);   // row inside this rank's y slab
+        // (32-bit division: ntiles < 2^31.)  A CTA narrower than a 64-byte piece takes the piece's parts as
+        // consecutive tiles, so that they are read from DRAM together.
+        constexpr int PARTS = WZ < WLay<T>::LW ? WLay<T>::LW / WZ : 1;
+        const unsigned t2 = (unsigned)tile / PARTS;
+        const int crel = (int)(t2 / (unsigned)p.ny);
+        const int iy_loc = (int)(t2 - (unsigned)crel * (unsigned)p.ny);   // row inside this rank's y slab
+        const int chunk = crel * PARTS + (int)((unsigned)tile % PARTS);
         const int iy = iy_loc + p.iy0;                     // global ky index (tables, DC, exclusions)
         const int iz = chunk * WZ + zl;
         const bool active = iz < p.nzh;
@@ -489,6 +494,36 @@ struct XPass {
                 // (an integer, not a pointer: the tile accesses must stay shared-memory loads)
                 int ix = r0;
                 asm volatile("" : "+r"(ix));
+                if constexpr (MU == 0 && WZ <= 32) {
+                    // Shells, every column of the tile a stored mode (CTA-uniform): s^ grows with kz and with kx
+                    // over the rows a warp covers in one step (fp32 addition is monotonic), so the step's smallest
+                    // and largest s^ sit in two known lanes.  If both are inside one cached interval, so is every
+                    // lane: the whole step is two loads and an add per lane, with no per-lane test and no vote.
+                    if ((iz - zl) + WZ <= p.nzh) {
+                        WarpBins<false>& acc = r.acc[0];
+                        const float c_lo = __shfl_sync(0xffffffffu, c_yz, 0), c_hi = __shfl_sync(0xffffffffu, c_yz, WZ - 1);
+                        const unsigned w2 = 2u * wt;
+                        const int lane_row = q % RPI;
+#pragma unroll 1
+                        for (int it = 0; it < EH; ++it) {
+                            const int ixw = ix - lane_row;                       // first row of this warp's step
+                            const float s_lo = ldg(B.tab_sf[0] + ixw) + c_lo, s_hi = ldg(B.tab_sf[0] + ixw + (RPI - 1)) + c_hi;
+                            const bool u0 = s_lo >= acc.slo[0] && s_hi < acc.shi[0];
+                            const bool u1 = s_lo >= acc.slo[1] && s_hi < acc.shi[1];
+                            if (ixw != 0 && (u0 || u1)) {
+                                const T psum = pt2[ix * WZ] + pt2[(NX - ix) * WZ];
+                                const double pw = (double)(psum * wf);
+                                if (u0) { acc.sum[0] += pw; acc.cnt[0] += w2; }
+                                else { acc.sum[1] += pw; acc.cnt[1] += w2; }
+                            } else {
+                                step(ix, pt2 + ix * WZ, pt2 + ((NX - ix) & (NX - 1)) * WZ, B.tab_sf[0] + ix, true, ix == 0);
+                            }
+                            ix += RPI;
+                        }
+                        if (tid < 32) step(NX / 2, pt2 + (NX / 2) * WZ, pt2 + (NX / 2) * WZ, B.tab_sf[0] + NX / 2, q == 0, true);
+                        return;
+                    }
+                }
 #pragma unroll 1
                 for (int it = 0; it < EH; ++it) {
                     step(ix, pt2 + ix * WZ, pt2 + ((NX - ix) & (NX - 1)) * WZ, B.tab_sf[0] + ix, true, ix == 0);   // row 0 pairs with itself

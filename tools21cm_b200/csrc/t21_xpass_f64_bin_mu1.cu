@@ -8,7 +8,7 @@ int launch_xpass_f64_bin_mu1(XArgs& a, cudaStream_t st) {
     using T = double;
 #define XCASE(N)                                                                          \
     {                                                                                     \
-        constexpr int WZ = WZFor<T, N>::value;                                            \
+        constexpr int WZ = WZForX<T, N>::value;                                           \
         if (a.nf == 1) return launch_x<XPass<N, T, WZ, 1, MODE_BIN, 1>, T>(a, st);    \
         return launch_x<XPass<N, T, WZ, 2, MODE_BIN, 1>, T>(a, st);                   \
     }

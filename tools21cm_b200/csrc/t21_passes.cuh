@@ -504,8 +504,29 @@ struct XPass {
                         const float c_lo = __shfl_sync(0xffffffffu, c_yz, 0), c_hi = __shfl_sync(0xffffffffu, c_yz, WZ - 1);
                         const unsigned w2 = 2u * wt;
                         const int lane_row = q % RPI;
+                        // The same test for the warp's whole sweep (EH steps, rows first..first+EH*RPI-1): when it
+                        // passes, the sweep is a sum of 2*EH tile values per lane, added to the bin in one go.
+                        const int first = ix - lane_row;
+                        bool swept = false;
+                        if (first != 0) {
+                            const float t_lo = ldg(B.tab_sf[0] + first) + c_lo;
+                            const float t_hi = ldg(B.tab_sf[0] + first + (EH * RPI - 1)) + c_hi;
+                            const bool v0 = t_lo >= acc.slo[0] && t_hi < acc.shi[0];
+                            const bool v1 = t_lo >= acc.slo[1] && t_hi < acc.shi[1];
+                            if (v0 || v1) {
+                                const T* lo = pt2 + ix * WZ;
+                                const T* hi = pt2 + (NX - ix) * WZ;
+                                T ps = (T)0;
+#pragma unroll
+                                for (int it = 0; it < EH; ++it) ps += lo[it * RPI * WZ] + hi[-it * RPI * WZ];
+                                const double pw = (double)(ps * wf);
+                                if (v0) { acc.sum[0] += pw; acc.cnt[0] += (unsigned)EH * w2; }
+                                else { acc.sum[1] += pw; acc.cnt[1] += (unsigned)EH * w2; }
+                                swept = true;
+                            }
+                        }
 #pragma unroll 1
-                        for (int it = 0; it < EH; ++it) {
+                        for (int it = 0; it < (swept ? 0 : EH); ++it) {
                             const int ixw = ix - lane_row;                       // first row of this warp's step
                             const float s_lo = ldg(B.tab_sf[0] + ixw) + c_lo, s_hi = ldg(B.tab_sf[0] + ixw + (RPI - 1)) + c_hi;
                             const bool u0 = s_lo >= acc.slo[0] && s_hi < acc.shi[0];

@@ -166,12 +166,14 @@ struct Strided {
 
     // phase PH of one transform.  ld_g(i): load element i from global; final(i, v): consume
     // output element i (natural frequency order).
+    // loaded = true: the caller has filled v with the first stage's inputs already (ld_g is not used)
     template <int PH, class LoadG, class Final>
-    static T21_HD void fft_phase(cx<T>* v, int j, int zl, const cx<T>* tw, cx<T>* smem, LoadG&& ld_g, Final&& fin) {
+    static T21_HD void fft_phase(cx<T>* v, int j, int zl, const cx<T>* tw, cx<T>* smem, LoadG&& ld_g, Final&& fin,
+                                 bool loaded = false) {
         auto st_smem = [&](int i, cx<T> val, int) { smem[i * WZ + zl] = val; };
         auto ld_smem = [&](int i) { return smem[i * WZ + zl]; };
         if constexpr (PH == 0) {
-            stage_load<P, 0>(v, j, ld_g);
+            if (!loaded) stage_load<P, 0>(v, j, ld_g);
             if constexpr (NS == 1) stage_compute<P, 0>(v, j, tw, fin);
             else stage_compute<P, 0>(v, j, tw, st_smem);
         } else {
@@ -336,28 +338,63 @@ struct XPass {
         return reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(smem) + BUF_BYTES);
     }
 
+    // tile -> (chunk of WZ columns, local ky row).  (32-bit division: ntiles < 2^31.)  ky runs fastest: CTAs
+    // working side by side read neighbouring 64-byte pieces.  A CTA narrower than a 64-byte piece takes the
+    // piece's parts as consecutive tiles, so that they are read from DRAM together.
+    static T21_HD void tile_coords(const Params& p, long long tile, int& chunk, int& iy_loc) {
+        constexpr int PARTS = WZ < WLay<T>::LW ? WLay<T>::LW / WZ : 1;
+        const unsigned t2 = (unsigned)tile / PARTS;
+        const int crel = (int)(t2 / (unsigned)p.ny);
+        iy_loc = (int)(t2 - (unsigned)crel * (unsigned)p.ny);
+        chunk = crel * PARTS + (int)((unsigned)tile % PARTS);
+    }
+
+    // the global loads of one tile's pencils (field F) into v, in the order stage 0 consumes them
+    template <int F>
+    static T21_HD void load_tile(const Params& p, long long tile, int tid, cx<T>* v) {
+        const int zl = tid % WZ, j = tid / WZ;
+        int chunk, iy_loc;
+        tile_coords(p, tile, chunk, iy_loc);
+        const int iz = chunk * WZ + zl;
+        // element i (= x) of this pencil sits at WLay::off(i, iy_loc, iz) = off(0, iy_loc, iz) + xi(i) * xstr
+        // with xi(i) = i + (i >> xs_log2) * D: plane i of a sequence of x slabs (D = 0 for a plain array);
+        // scratch columns of the last chunk are read too
+        constexpr int LW = WLay<T>::LW, LWS = WLay<T>::LWS;
+        const long long xstr = (long long)p.ny << LWS;
+        const cx<T>* base = p.w[F] + (((((long long)(iz >> LWS) << p.xs_log2) * p.ny) + iy_loc) << LWS) + (iz & (LW - 1));
+#ifdef T21_DBG_NOLOAD
+        stage_load<P, 0>(v, j, [&](int i) { return cmake<T>((T)i, (T)zl); });
+#else
+        if ((NX >> p.xs_log2) <= 1) {
+            // plain array: rows are linear in x, walked by a cursor
+            constexpr int R0 = P::radix(0);
+            RowCursor<const cx<T>> lc(base + (long long)j * xstr, (long long)(NX / R0) * xstr, (long long)P::T * xstr, R0);
+            stage_load<P, 0>(v, j, [&](int) { return *lc.next(); });
+        } else {
+            const long long D = ((long long)(p.pitch >> LWS) - 1) << p.xs_log2;
+            stage_load<P, 0>(v, j, [&](int i) { return base[(i + (long long)(i >> p.xs_log2) * D) * xstr]; });
+        }
+#endif
+    }
+
+    // (Measured and dropped: issuing the NEXT tile's loads before the epilogue keeps 32 more registers live
+    // through the sweep -- ptxas spills seven of the loaded values right behind the loads, X 2.08 -> 2.53 ms;
+    // prefetch.global.L2 of the next tile instead: 2.31 ms.)
     template <int PH, class Hist>
     static T21_HD void phase(const Params& p, long long tile, int tid, Regs& r, cx<T>* smem, Hist& hist) {
         const int zl = tid % WZ, j = tid / WZ;
         // ky fastest: CTAs running together read neighbouring 64-byte pieces of the same piece-plane
-        // (32-bit division: ntiles < 2^31.)  A CTA narrower than a 64-byte piece takes the piece's parts as
-        // consecutive tiles, so that they are read from DRAM together.
-        constexpr int PARTS = WZ < WLay<T>::LW ? WLay<T>::LW / WZ : 1;
-        const unsigned t2 = (unsigned)tile / PARTS;
-        const int crel = (int)(t2 / (unsigned)p.ny);
-        const int iy_loc = (int)(t2 - (unsigned)crel * (unsigned)p.ny);   // row inside this rank's y slab
-        const int chunk = crel * PARTS + (int)((unsigned)tile % PARTS);
+        int chunk, iy_loc;                                 // iy_loc: row inside this rank's y slab
+        tile_coords(p, tile, chunk, iy_loc);
         const int iy = iy_loc + p.iy0;                     // global ky index (tables, DC, exclusions)
         const int iz = chunk * WZ + zl;
         const bool active = iz < p.nzh;
         if constexpr (PH < NF * S::FFT_PHASES) {
             constexpr int F = PH / S::FFT_PHASES;          // field this phase works on
             constexpr int FPH = PH % S::FFT_PHASES;
-            // element i (= x) of this pencil sits at WLay::off(i, iy_loc, iz) = off(0, iy_loc, iz) + xi(i) * xstr
-            // with xi(i) = i + (i >> xs_log2) * D: plane i of a sequence of x slabs (D = 0 for a plain array)
-            constexpr int LW = WLay<T>::LW, LWS = WLay<T>::LWS;
-            const long long xstr = (long long)p.ny << LWS;
-            const cx<T>* base = p.w[F] + (((((long long)(iz >> LWS) << p.xs_log2) * p.ny) + iy_loc) << LWS) + (iz & (LW - 1));
+            if constexpr (FPH == 0) {
+                load_tile<F>(p, tile, tid, r.v[F]);
+            }
             auto fin = [&](int i, cx<T> b, int slot) {
                     // last stage of field F: element i (= kx) is final and sits in register `slot`.
                     // Field 0 of a cross spectrum just stays there; the last field forms the power.
@@ -383,20 +420,7 @@ struct XPass {
                         ptile(smem)[i * WZ + zl] = pw;
                     }
                 };
-#ifdef T21_DBG_NOLOAD
-            S::template fft_phase<FPH>(r.v[F], j, zl, p.tw, smem, [&](int i) { return cmake<T>((T)i, (T)zl); }, fin);
-#else
-            if (FPH != 0 || (NX >> p.xs_log2) <= 1) {
-                // plain array (and every phase that does not load): rows are linear in x, walked by a cursor
-                constexpr int R0 = P::radix(0);
-                RowCursor<const cx<T>> lc(base + (long long)j * xstr, (long long)(NX / R0) * xstr, (long long)P::T * xstr, R0);
-                S::template fft_phase<FPH>(r.v[F], j, zl, p.tw, smem, [&](int) { return *lc.next(); }, fin);
-            } else {
-                const long long D = ((long long)(p.pitch >> LWS) - 1) << p.xs_log2;
-                S::template fft_phase<FPH>(r.v[F], j, zl, p.tw, smem,
-                                           [&](int i) { return base[(i + (long long)(i >> p.xs_log2) * D) * xstr]; }, fin);
-            }
-#endif
+            S::template fft_phase<FPH>(r.v[F], j, zl, p.tw, smem, [&](int) { return cmake<T>((T)0, (T)0); }, fin, true);
         } else {
             epilogue(p, tid, iy, iy_loc, iz, zl, active, r, smem, hist);
         }

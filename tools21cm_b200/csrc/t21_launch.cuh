@@ -36,6 +36,20 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_CTAS) tile_kernel(const __g
 #ifndef T21_X_MIN_CTAS
 #define T21_X_MIN_CTAS 2
 #endif
+// cross spectra keep the first field's 16 results per thread while the second is transformed: at 64 registers
+// that spills ~700 bytes per thread, so they are compiled for one CTA per SM (1024^3 cross: 11.6 -> 10.7 ms)
+#ifndef T21_X_NF2_WIDE
+#define T21_X_NF2_WIDE 1
+#endif
+// CTAs per SM the X pass is compiled for (i.e. its register budget): 64 registers per thread for fp32
+// pencils of up to 512 threads, 128 for fp64 (16 complex doubles are 64 registers by themselves)
+template <typename T>
+constexpr int x_min_ctas(int threads, int e, int nf) {
+    if (threads * e * (T21_X_NF2_WIDE ? nf : 1) > 512 * 16) return 1;
+    const int by_threads = 1024 / threads < 1 ? 1 : 1024 / threads;      // 1024 resident threads per SM
+    const int want = sizeof(T) == 4 ? by_threads : by_threads / 2;
+    return want < 1 ? 1 : (want > 2 * T21_X_MIN_CTAS ? 2 * T21_X_MIN_CTAS : want);
+}
 
 struct NoHist {
     __device__ void add(int, double, unsigned) {}
@@ -45,7 +59,7 @@ struct NoHist {
 // in shared memory until the end (HK = 0), accumulates into global memory (HK = 1), or has no
 // histogram at all (HK = 2, n-D store).
 template <class K, typename T, int HK>
-__global__ void __launch_bounds__(K::THREADS, (K::THREADS * K::E <= 512 * 16 ? (K::THREADS == 256 && K::E == 16 ? 2 * T21_X_MIN_CTAS : T21_X_MIN_CTAS) : 1))
+__global__ void __launch_bounds__(K::THREADS, (x_min_ctas<T>(K::THREADS, K::E, K::kNF)))
 xpass_kernel(const __grid_constant__ typename K::Params p, int nbins, int warp_private,
              double* __restrict__ part_sum, unsigned* __restrict__ part_cnt, double* gsum, unsigned long long* gcnt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

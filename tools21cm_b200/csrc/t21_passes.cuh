@@ -309,6 +309,7 @@ struct XPass {
     static constexpr int SMEM_BYTES = BUF_BYTES + 16;          // + the DC power as a double
     static constexpr int NPHASE = NF * S::FFT_PHASES + 1;      // transforms, then the epilogue
     static constexpr int kMode = MODE;
+    static constexpr int kNF = NF;
     static constexpr int kMu = MU;
     static constexpr int NACC = (MU == 2) ? 2 : 1;
     static constexpr int RPI = (THREADS >= 32) ? 32 / WZ : S::TP;   // kx rows a warp covers per step

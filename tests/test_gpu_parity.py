@@ -216,7 +216,9 @@ def test_cross_of_a_cube_with_itself_is_its_auto_spectrum_512(t2c):
     a = t2c.power_spectrum_1d(x, kbins=15, box_dims=300.0, return_n_modes=True)
     c = t2c.cross_power_spectrum_1d(x, x.clone(), kbins=15, box_dims=300.0, return_n_modes=True)
     assert np.array_equal(a[2], c[2])
-    np.testing.assert_allclose(a[0], c[0], rtol=1e-12)
+    # the per-mode powers are the same fp32 numbers; the two kernels run with different numbers of CTAs, which
+    # changes where a warp's partial sums are cut (fp32 partial sums of 16 modes, then float64): ~1e-11
+    np.testing.assert_allclose(a[0], c[0], rtol=1e-9)
     m = t2c.power_spectrum_mu(x, kbins=10, mubins=5, box_dims=300.0, return_n_modes=True)
     assert m[3].sum() == 512 ** 3 - 512 - 1 - 0 or m[3].sum() > 0.99 * 512 ** 3
 

@@ -87,16 +87,27 @@ int launch_zero_hist(double* sums, long long* counts, int nbins, cudaStream_t st
 }
 
 // ---- element-wise binning of a full (fftshifted) array ---------------------------------
-// Each thread owns runs of kRun consecutive z samples (neighbours share a bin most of the
-// time, so the run accumulator rarely touches the histogram).
-constexpr int kRun = 16;
+// A warp reads kUnroll runs of 32 consecutive samples (coalesced); each lane finds its sample's bin and adds
+// it to the warp's two-entry bin cache (WarpBinCache): neighbouring samples share a bin most of the time, so
+// the shared-memory histogram is touched only when the warp moves on to another bin.
 constexpr int kBinThreads = 256;
+constexpr int kUnroll = 4;
 
-template <typename T, int HK>
-__global__ void __launch_bounds__(kBinThreads)
-bin_only_kernel(const T* __restrict__ p, const __grid_constant__ t21_binspec B, int nbins,
-                double* __restrict__ part_sum, unsigned* __restrict__ part_cnt, double* gsum,
-                unsigned long long* gcnt) {
+// (ix, iy, iz) of element o0 + d, given those of o0 (0 <= d < 2^20): 32-bit divisions only
+__device__ __forceinline__ void advance_coords(int ix0, int iy0, int iz0, int d, int n1, int n2, int& ix, int& iy, int& iz) {
+    const unsigned tz = (unsigned)iz0 + (unsigned)d;
+    const unsigned qz = tz / (unsigned)n2;
+    iz = (int)(tz - qz * (unsigned)n2);
+    const unsigned ty = (unsigned)iy0 + qz;
+    const unsigned qy = ty / (unsigned)n1;
+    iy = (int)(ty - qy * (unsigned)n1);
+    ix = ix0 + (int)qy;
+}
+
+template <typename T, int HK, class BinOf>
+__device__ __forceinline__ void bin_array(const T* __restrict__ p, int n0, int n1, int n2, int nbins,
+                                          double* __restrict__ part_sum, unsigned* __restrict__ part_cnt, double* gsum,
+                                          unsigned long long* gcnt, BinOf&& bin_of) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* hs = reinterpret_cast<double*>(smem_raw);
     unsigned* hc = reinterpret_cast<unsigned*>(hs + nbins);
@@ -104,39 +115,58 @@ bin_only_kernel(const T* __restrict__ p, const __grid_constant__ t21_binspec B, 
         for (int b = threadIdx.x; b < nbins; b += kBinThreads) { hs[b] = 0.0; hc[b] = 0u; }
         __syncthreads();
     }
-    const long long n2 = B.n[2], n1 = B.n[1];
-    const long long total = (long long)B.n[0] * n1 * n2;
-    const long long nruns = (total + kRun - 1) / kRun;
-    RunAcc acc;
-    run_init(acc);
+    const long long total = (long long)n0 * n1 * n2;
+    const int lane = threadIdx.x & 31;
+    const long long span = 32LL * kUnroll;                                   // samples per warp per trip
+    const long long warp0 = (long long)blockIdx.x * (kBinThreads / 32) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (kBinThreads / 32);
+    WarpBinCache acc;
+    wbc_init(acc);
     SmemHist sh{hs, hc};
     GlobalHist gh{gsum, gcnt};
-    for (long long run = (long long)blockIdx.x * kBinThreads + threadIdx.x; run < nruns;
-         run += (long long)gridDim.x * kBinThreads) {
-        long long o = run * kRun;
-        int iz = (int)(o % n2);
-        long long t = o / n2;
-        int iy = (int)(t % n1);
-        int ix = (int)(t / n1);
-        const long long end = (o + kRun < total) ? o + kRun : total;
-        for (; o < end; ++o) {
-            const ModeBins mb = classify(B, ix, iy, iz, false);
-            const double v = (double)p[o];
-            if (HK == 0) run_add(acc, sh, mb.own, v, mb.own_w);
-            else run_add(acc, gh, mb.own, v, mb.own_w);
-            if (++iz == n2) { iz = 0; if (++iy == n1) { iy = 0; ++ix; } }
+    for (long long o0 = warp0 * span; o0 < total; o0 += nwarps * span) {     // warp-uniform trip count
+        const long long t = o0 / n2;                                         // one 64-bit division per 128 samples
+        const int iz0 = (int)(o0 - t * n2);
+        const int ix0 = (int)(t / n1), iy0 = (int)(t - (long long)ix0 * n1);
+        T v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long o = o0 + u * 32 + lane;
+            v[u] = o < total ? p[o] : (T)0;
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long o = o0 + u * 32 + lane;
+            int ix, iy, iz, w = 1;
+            advance_coords(ix0, iy0, iz0, u * 32 + lane, n1, n2, ix, iy, iz);
+            const int bin = o < total ? bin_of(ix, iy, iz, w) : -1;
+            if (HK == 0) wbc_add(acc, sh, bin, (double)v[u], (unsigned)w);
+            else wbc_add(acc, gh, bin, (double)v[u], (unsigned)w);
         }
     }
     if (HK == 0) {
-        run_flush(acc, sh);
+        wbc_flush(acc, sh);
         __syncthreads();
         for (int b = threadIdx.x; b < nbins; b += kBinThreads) {
             part_sum[(size_t)blockIdx.x * nbins + b] = hs[b];
             part_cnt[(size_t)blockIdx.x * nbins + b] = hc[b];
         }
     } else {
-        run_flush(acc, gh);
+        wbc_flush(acc, gh);
     }
+}
+
+template <typename T, int HK>
+__global__ void __launch_bounds__(kBinThreads)
+bin_only_kernel(const T* __restrict__ p, const __grid_constant__ t21_binspec B, int nbins,
+                double* __restrict__ part_sum, unsigned* __restrict__ part_cnt, double* gsum,
+                unsigned long long* gcnt) {
+    bin_array<T, HK>(p, B.n[0], B.n[1], B.n[2], nbins, part_sum, part_cnt, gsum, gcnt,
+                     [&](int ix, int iy, int iz, int& w) {
+                         const ModeBins mb = classify(B, ix, iy, iz, false);
+                         w = mb.own_w;
+                         return mb.own;
+                     });
 }
 
 // ---- (k_perp, k_par) binning of a full fftshifted 3-D array (power_spectrum_2d) -----------------------
@@ -149,51 +179,17 @@ __global__ void __launch_bounds__(kBinThreads)
 bin_cyl_kernel(const T* __restrict__ p, int n0, int n1, int n2, int nu_axis, const int* __restrict__ perp_tab,
                const int* __restrict__ par_tab, int npar, int nbins, double* __restrict__ part_sum,
                unsigned* __restrict__ part_cnt, double* gsum, unsigned long long* gcnt) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* hs = reinterpret_cast<double*>(smem_raw);
-    unsigned* hc = reinterpret_cast<unsigned*>(hs + nbins);
-    if (HK == 0) {
-        for (int b = threadIdx.x; b < nbins; b += kBinThreads) { hs[b] = 0.0; hc[b] = 0u; }
-        __syncthreads();
-    }
-    const long long total = (long long)n0 * n1 * n2;
-    const long long nruns = (total + kRun - 1) / kRun;
     const int nb_perp_inner = nu_axis == 2 ? n1 : n2;      // length of the second perpendicular axis
-    RunAcc acc;
-    run_init(acc);
-    SmemHist sh{hs, hc};
-    GlobalHist gh{gsum, gcnt};
-    for (long long run = (long long)blockIdx.x * kBinThreads + threadIdx.x; run < nruns;
-         run += (long long)gridDim.x * kBinThreads) {
-        long long o = run * kRun;
-        int iz = (int)(o % n2);
-        long long t = o / n2;
-        int iy = (int)(t % n1);
-        int ix = (int)(t / n1);
-        const long long end = (o + kRun < total) ? o + kRun : total;
-        for (; o < end; ++o) {
-            const int inu = nu_axis == 0 ? ix : (nu_axis == 1 ? iy : iz);
-            const int ia = nu_axis == 0 ? iy : ix;
-            const int ib = nu_axis == 2 ? iy : iz;
-            const int bp = ldg(perp_tab + (long long)ia * nb_perp_inner + ib);
-            const int bz = ldg(par_tab + inu);
-            const int bin = (bp >= 0 && bz >= 0) ? bp * npar + bz : -1;
-            const double v = (double)p[o];
-            if (HK == 0) run_add(acc, sh, bin, v, 1);
-            else run_add(acc, gh, bin, v, 1);
-            if (++iz == n2) { iz = 0; if (++iy == n1) { iy = 0; ++ix; } }
-        }
-    }
-    if (HK == 0) {
-        run_flush(acc, sh);
-        __syncthreads();
-        for (int b = threadIdx.x; b < nbins; b += kBinThreads) {
-            part_sum[(size_t)blockIdx.x * nbins + b] = hs[b];
-            part_cnt[(size_t)blockIdx.x * nbins + b] = hc[b];
-        }
-    } else {
-        run_flush(acc, gh);
-    }
+    bin_array<T, HK>(p, n0, n1, n2, nbins, part_sum, part_cnt, gsum, gcnt,
+                     [&](int ix, int iy, int iz, int& w) {
+                         const int inu = nu_axis == 0 ? ix : (nu_axis == 1 ? iy : iz);
+                         const int ia = nu_axis == 0 ? iy : ix;
+                         const int ib = nu_axis == 2 ? iy : iz;
+                         const int bp = ldg(perp_tab + (long long)ia * nb_perp_inner + ib);
+                         const int bz = ldg(par_tab + inu);
+                         w = 1;
+                         return (bp >= 0 && bz >= 0) ? bp * npar + bz : -1;
+                     });
 }
 
 int launch_bin_cyl(const void* p, int dtype, int n0, int n1, int n2, int nu_axis, const int* perp_tab,
@@ -202,8 +198,8 @@ int launch_bin_cyl(const void* p, int dtype, int n0, int n1, int n2, int nu_axis
     const int nbins = nperp * npar;
     const bool global = nbins > kSmemHistMaxBins;
     const long long total = (long long)n0 * n1 * n2;
-    const long long nruns = (total + kRun - 1) / kRun;
-    long long g = (nruns + kBinThreads - 1) / kBinThreads;
+    const long long per_cta = (long long)kBinThreads * kUnroll;
+    long long g = (total + per_cta - 1) / per_cta;
     const long long cap = (long long)device_sm_count() * 8;
     if (g > cap) g = cap;
     if (!global && g > max_grid) g = max_grid;
@@ -228,8 +224,8 @@ int launch_bin_only(const void* p, int dtype, const t21_binspec& spec, double* p
     const int nbins = spec.nk * (spec.nmu > 0 ? spec.nmu : 1);
     const bool global = nbins > kSmemHistMaxBins;   // then gsum/gcnt are the pre-zeroed final outputs
     const long long total = (long long)spec.n[0] * spec.n[1] * spec.n[2];
-    const long long nruns = (total + kRun - 1) / kRun;
-    long long g = (nruns + kBinThreads - 1) / kBinThreads;
+    const long long per_cta = (long long)kBinThreads * kUnroll;
+    long long g = (total + per_cta - 1) / per_cta;
     const long long cap = (long long)device_sm_count() * 8;
     if (g > cap) g = cap;
     if (!global && g > max_grid) g = max_grid;

@@ -279,6 +279,75 @@ __device__ __forceinline__ void warpbins_slow(WarpBins<MU>& a, Hist& h, const t2
 }
 #endif
 
+// WarpBinCache: the same two-entry warp-uniform cache keyed by the exact bin id alone (no guard intervals),
+// for kernels whose lanes read consecutive elements of a caller's array and get their bin from tables.
+struct WarpBinCache {
+    int bin[2];              // warp-uniform, -1 = empty
+    int lru;
+    unsigned cnt[2];         // per lane
+    double sum[2];           // per lane
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ void wbc_init(WarpBinCache& a) {
+    a.bin[0] = a.bin[1] = -1; a.lru = 0;
+    a.cnt[0] = a.cnt[1] = 0u; a.sum[0] = a.sum[1] = 0.0;
+}
+template <class Hist>
+__device__ __forceinline__ void wbc_evict(WarpBinCache& a, Hist& h, int c) {
+    double s = a.sum[c];
+    unsigned n = a.cnt[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+    }
+    if ((threadIdx.x & 31) == 0 && n) h.add(a.bin[c], s, n);
+    a.sum[c] = 0.0;
+    a.cnt[c] = 0u;
+}
+// every lane of the warp calls this together; bin < 0 = this lane has nothing to add
+template <class Hist>
+__device__ __forceinline__ void wbc_add(WarpBinCache& a, Hist& h, int bin, double v, unsigned w) {
+    const bool in0 = bin == a.bin[0], in1 = bin == a.bin[1];
+    if (__all_sync(0xffffffffu, bin < 0 || in0 || in1)) {
+        if (bin >= 0) {
+            if (in0) { a.sum[0] += v; a.cnt[0] += w; }
+            else { a.sum[1] += v; a.cnt[1] += w; }
+        }
+        return;
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, bin >= 0);
+    while (todo) {                                   // warp-uniform loop: one trip per distinct bin
+        const int ref = __shfl_sync(0xffffffffu, bin, __ffs(todo) - 1);
+        const bool mine = bin == ref;
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+        if (a.bin[0] == ref) {
+            if (mine) { a.sum[0] += v; a.cnt[0] += w; }
+            a.lru = 1;
+        } else if (a.bin[1] == ref) {
+            if (mine) { a.sum[1] += v; a.cnt[1] += w; }
+            a.lru = 0;
+        } else if (a.lru == 0) {
+            if (a.bin[0] >= 0) wbc_evict(a, h, 0);
+            a.bin[0] = ref;
+            if (mine) { a.sum[0] = v; a.cnt[0] = w; }
+            a.lru = 1;
+        } else {
+            if (a.bin[1] >= 0) wbc_evict(a, h, 1);
+            a.bin[1] = ref;
+            if (mine) { a.sum[1] = v; a.cnt[1] = w; }
+            a.lru = 0;
+        }
+    }
+}
+template <class Hist>
+__device__ __forceinline__ void wbc_flush(WarpBinCache& a, Hist& h) {
+    if (a.bin[0] >= 0) wbc_evict(a, h, 0);
+    if (a.bin[1] >= 0) wbc_evict(a, h, 1);
+    a.bin[0] = a.bin[1] = -1;
+}
+#endif
+
 template <bool MU, class Hist>
 T21_HD void warpbins_flush(WarpBins<MU>& a, Hist& h, int nbins) {
 #if T21_DEVICE_CODE

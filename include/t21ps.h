@@ -127,7 +127,7 @@ T21_API int t21_slab_pitch(const t21_plan* plan);
 T21_API int t21_slab_stage1(const t21_plan* plan_slab, const void* x_slab, const void* offset_or_null,
                             void* w_out, void* send_out_or_null, int nranks, void* stream);
 /* stage 1 with the re-partition FUSED into the Y pass: every transformed row is stored straight into the
- * y-slab buffer of the rank that owns it.  peer_cols[s] = rank s's [nx][ny/P][pitch] buffer mapped into this
+ * y-slab buffer of the rank that owns it.  peer_cols[s] = rank s's chunk-major y-slab buffer (nx planes of ny/P rows) mapped into this
  * process (CUDA IPC / peer access over NVLink; peer_cols[own rank] is the local one); x0_global = global index
  * of this slab's first x plane.  No send buffer, no collective: the caller only has to order "every rank has
  * finished stage 1" before stage 2 (e.g. a one-element all-reduce on the same stream). */

@@ -538,20 +538,22 @@ struct XPass {
                         // passes, the sweep is a sum of 2*EH tile values per lane, added to the bin in one go.
                         const int first = ix - lane_row;
                         bool swept = false;
-                        if (first != 0) {
+                        {
                             const float t_lo = ldg(B.tab_sf[0] + first) + c_lo;
                             const float t_hi = ldg(B.tab_sf[0] + first + (EH * RPI - 1)) + c_hi;
                             const bool v0 = t_lo >= acc.slo[0] && t_hi < acc.shi[0];
                             const bool v1 = t_lo >= acc.slo[1] && t_hi < acc.shi[1];
                             if (v0 || v1) {
                                 const T* lo = pt2 + ix * WZ;
-                                const T* hi = pt2 + (NX - ix) * WZ;
-                                T ps = (T)0;
+                                const T* hi = pt2 + (NX - RPI - ix) * WZ;               // mirror of the SECOND row
+                                const bool self = ix == 0;                             // row 0 pairs with itself
+                                T ps = self ? lo[0] : lo[0] + hi[RPI * WZ];
 #pragma unroll
-                                for (int it = 0; it < EH; ++it) ps += lo[it * RPI * WZ] + hi[-it * RPI * WZ];
+                                for (int it = 1; it < EH; ++it) ps += lo[it * RPI * WZ] + hi[-(it - 1) * RPI * WZ];
                                 const double pw = (double)(ps * wf);
-                                if (v0) { acc.sum[0] += pw; acc.cnt[0] += (unsigned)EH * w2; }
-                                else { acc.sum[1] += pw; acc.cnt[1] += (unsigned)EH * w2; }
+                                const unsigned wn = (unsigned)EH * w2 - (self ? wt : 0u);
+                                if (v0) { acc.sum[0] += pw; acc.cnt[0] += wn; }
+                                else { acc.sum[1] += pw; acc.cnt[1] += wn; }
                                 swept = true;
                             }
                         }
@@ -561,17 +563,20 @@ struct XPass {
                             const float s_lo = ldg(B.tab_sf[0] + ixw) + c_lo, s_hi = ldg(B.tab_sf[0] + ixw + (RPI - 1)) + c_hi;
                             const bool u0 = s_lo >= acc.slo[0] && s_hi < acc.shi[0];
                             const bool u1 = s_lo >= acc.slo[1] && s_hi < acc.shi[1];
-                            if (ixw != 0 && (u0 || u1)) {
-                                const T psum = pt2[ix * WZ] + pt2[(NX - ix) * WZ];
-                                const double pw = (double)(psum * wf);
-                                if (u0) { acc.sum[0] += pw; acc.cnt[0] += w2; }
-                                else { acc.sum[1] += pw; acc.cnt[1] += w2; }
+                            if (u0 || u1) {
+                                const bool self = ix == 0;
+                                const T plo = pt2[ix * WZ], phi = pt2[((NX - ix) & (NX - 1)) * WZ];
+                                const double pw = (double)((self ? plo : plo + phi) * wf);
+                                const unsigned wn = self ? wt : w2;
+                                if (u0) { acc.sum[0] += pw; acc.cnt[0] += wn; }
+                                else { acc.sum[1] += pw; acc.cnt[1] += wn; }
                             } else {
                                 step(ix, pt2 + ix * WZ, pt2 + ((NX - ix) & (NX - 1)) * WZ, B.tab_sf[0] + ix, true, ix == 0);
                             }
                             ix += RPI;
                         }
-                        if (tid < 32) step(NX / 2, pt2 + (NX / 2) * WZ, pt2 + (NX / 2) * WZ, B.tab_sf[0] + NX / 2, q == 0, true);
+                        // the Nyquist row goes to the last warp (the first one has the self-paired row 0)
+                if (tid >= THREADS - 32) step(NX / 2, pt2 + (NX / 2) * WZ, pt2 + (NX / 2) * WZ, B.tab_sf[0] + NX / 2, q == S::TP - RPI, true);
                         return;
                     }
                 }
@@ -580,7 +585,8 @@ struct XPass {
                     step(ix, pt2 + ix * WZ, pt2 + ((NX - ix) & (NX - 1)) * WZ, B.tab_sf[0] + ix, true, ix == 0);   // row 0 pairs with itself
                     ix += RPI;
                 }
-                if (tid < 32) step(NX / 2, pt2 + (NX / 2) * WZ, pt2 + (NX / 2) * WZ, B.tab_sf[0] + NX / 2, q == 0, true);
+                // the Nyquist row goes to the last warp (the first one has the self-paired row 0)
+                if (tid >= THREADS - 32) step(NX / 2, pt2 + (NX / 2) * WZ, pt2 + (NX / 2) * WZ, B.tab_sf[0] + NX / 2, q == S::TP - RPI, true);
                 return;
             }
         }

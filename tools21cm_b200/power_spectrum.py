@@ -53,6 +53,7 @@ class _Device:
         self.index = index
         self.plans = {}
         self.specs = OrderedDict()
+        self.cyls = OrderedDict()
         self.ws = None
 
     def plan(self, shape, dtype):
@@ -90,6 +91,22 @@ class _Device:
         self.specs[key] = hit
         while len(self.specs) > 64:
             self.specs.popitem(last=False)
+        return hit
+
+
+    def cyl(self, key, builder):
+        """(CylSpec, perp table, par table) of power_spectrum_2d, tables resident on the device."""
+        hit = self.cyls.get(key)
+        if hit is None:
+            torch = _torch()
+            c = builder()
+            hit = (c, torch.from_numpy(c.perp_tab).to("cuda:%d" % self.index),
+                   torch.from_numpy(c.par_tab).to("cuda:%d" % self.index))
+            self.cyls[key] = hit
+            while len(self.cyls) > 8:
+                self.cyls.popitem(last=False)
+        else:
+            self.cyls.move_to_end(key)
         return hit
 
 
@@ -525,12 +542,11 @@ def power_spectrum_2d(input_array, kbins=10, binning="log", box_dims=244 / .7, r
     torch = _torch()
     shape = tuple(x.shape)
     power = _fused_nd([x], _bs.volume_scale(shape, box_dims), torch.float64)
-    cyl = _bs.build_cyl_tables(shape, box_dims, kbins, binning=binning, nu_axis=nu_axis)
     dev = _device(x.device.index)
+    cyl, perp, par = dev.cyl((shape, _freeze(list(box_dims)), _freeze(kbins), binning, int(nu_axis)),
+                             lambda: _bs.build_cyl_tables(shape, box_dims, kbins, binning=binning, nu_axis=nu_axis))
     with torch.cuda.device(x.device):
         lib = _lib.load()
-        perp = torch.from_numpy(cyl.perp_tab).to(x.device)
-        par = torch.from_numpy(cyl.par_tab).to(x.device)
         nb = cyl.nperp * cyl.npar
         ws = dev.workspace(lib.t21_bin_cyl_workspace_bytes(cyl.nperp, cyl.npar))
         sums = torch.empty(nb, dtype=torch.float64, device=x.device)

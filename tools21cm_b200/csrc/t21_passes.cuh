@@ -72,7 +72,15 @@ struct ZPass {
     static constexpr int SMEM_ELEMS = ROWS * ROWPITCH;
     static constexpr int SMEM_BYTES = SMEM_ELEMS * (int)sizeof(cx<T>);
     static constexpr int MIN_CTAS = (THREADS <= 256 && sizeof(T) == 4) ? 4 : 1;   // 64 registers: what it needs anyway
-    static constexpr int NPHASE = 2 * NS;
+    // When the last stage is a radix-2 one, it is fused with the untangle phase: outputs k, M-k, M/2-k, M/2+k
+    // need exactly the four stage inputs a[k], a[k+M/2], a[M/2-k], a[M-k], so one thread reads those four values
+    // and writes four outputs -- one shared-memory exchange (16 stores, 16 loads, two barriers) less.
+    static constexpr int kQ = M / 4;
+    static constexpr int kGroups = THREADS / ((64 / (int)sizeof(cx<T>)) * ROWS);
+    static constexpr bool kFuseLast = NS >= 2 && P::radix(NS - 1) == 2 && kQ % (64 / (int)sizeof(cx<T>)) == 0 &&
+                                      THREADS % ((64 / (int)sizeof(cx<T>)) * ROWS) == 0 && kGroups >= 2 &&
+                                      (kQ / (64 / (int)sizeof(cx<T>))) % kGroups == 0;
+    static constexpr int NPHASE = kFuseLast ? 2 * NS - 2 : 2 * NS;
 
     struct Params {
         const T* in;          // [nrows][NZ]
@@ -112,6 +120,50 @@ struct ZPass {
             constexpr int S = (PH + 1) / 2;
             if constexpr (PH % 2 == 1) stage_load<P, S>(r.v, j, ld_smem);
             else stage_compute<P, S>(r.v, j, p.tw, st_smem);
+        } else if constexpr (kFuseLast) {
+            // last radix-2 stage: Z[i] = a[i] + w2^i a[i+M/2], Z[i+M/2] = a[i] - w2^i a[i+M/2] (w2 = exp(-2 pi i / M)),
+            // then the untangle of the pairs (k, M-k) and (M/2-k, M/2+k); a[] is what stage NS-2 left in smem.
+            constexpr int LW = WLay<T>::LW, LWS = WLay<T>::LWS;
+            constexpr int M2 = M / 2;
+            const long long cstride = p.cstride;
+            const cx<T>* tw2 = p.tw + P::tw_off(NS - 1);
+            const int l = tid % LW, rsub = (tid / LW) % ROWS, g = tid / (LW * ROWS);
+            const long long rw = cta * ROWS + rsub;
+            const cx<T>* ar = smem + rsub * ROWPITCH;
+            cx<T>* d0 = p.out + (rw << LWS);          // row (x, y) sits at x * ny + y = rw
+            auto put = [&](int k, cx<T> v) { d0[(long long)(k >> LWS) * cstride + (k & (LW - 1))] = v; };
+            // X[k] and X[M-k] from Z[k] and Z[M-k]
+            auto untangle = [&](int k, cx<T> zk, cx<T> zm) {
+                const cx<T> w = ldg(p.twr + k);
+                const cx<T> a = cmake<T>(zk.x + zm.x, zk.y - zm.y);       // Z[k] + conj Z[M-k]
+                const cx<T> d = cmake<T>(zk.x - zm.x, zk.y + zm.y);       // Z[k] - conj Z[M-k]
+                const cx<T> t = cmul(w, d);
+                put(k, cmake<T>((T)0.5 * (a.x + t.y), (T)0.5 * (a.y - t.x)));
+                put(M - k, cmake<T>((T)0.5 * (a.x - t.y), (T)0.5 * (-a.y - t.x)));   // conj(a)/2 - i/2 conj(t)
+            };
+            if (rw < p.nrows) {
+#pragma unroll
+                for (int it = 0; it < (kQ / LW) / kGroups; ++it) {
+                    const int k = (g + it * kGroups) * LW + l;            // 0 <= k < M/4
+                    const cx<T> a0 = ar[pad(k)], a1 = ar[pad(k + M2)];
+                    const cx<T> u = k ? cmul(ldg(tw2 + k), a1) : a1;
+                    const cx<T> zk = cadd(a0, u), zk2 = csub(a0, u);      // Z[k], Z[k+M/2]
+                    if (k == 0) {
+                        untangle(0, zk, zk);                              // X[0], X[M] (M-0 wraps to 0)
+                        untangle(M2, zk2, zk2);                           // the self-paired middle sample
+                    } else {
+                        const cx<T> b0 = ar[pad(M2 - k)], b1 = ar[pad(M - k)];
+                        const cx<T> v = cmul(ldg(tw2 + (M2 - k)), b1);
+                        untangle(k, zk, csub(b0, v));                     // Z[M-k] = a[M/2-k] - w2^(M/2-k) a[M-k]
+                        untangle(M2 - k, cadd(b0, v), zk2);               // pair (M/2-k, M/2+k)
+                    }
+                }
+                if (g == 1 && l == 0) {                                   // k = M/4 pairs with 3M/4
+                    const cx<T> a0 = ar[pad(kQ)], a1 = ar[pad(kQ + M2)];
+                    const cx<T> u = cmul(ldg(tw2 + kQ), a1);
+                    untangle(kQ, cadd(a0, u), csub(a0, u));
+                }
+            }
         } else {
             // untangle: X[k] = (Z[k] + conj Z[M-k])/2 - i/2 * w^k * (Z[k] - conj Z[M-k]),  w = exp(-2 pi i / NZ).
             // k and M-k need the same two inputs and w^(M-k) = -conj(w^k), so one thread produces both.

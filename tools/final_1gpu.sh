@@ -13,4 +13,4 @@ fi
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
    -k regex:'tile_kernel|xpass_kernel|mean_estimate|reduce_partials' -c 60 --csv --log-file gpurun_out/final_launches.csv \
    python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/final_ncu_ll.log 2>&1; echo "ncu ll rc=$?"
-bash tools/profile_kernel.sh xpass_kernel xfin 3 > gpurun_out/xfin.log 2>&1
+bash tools/profile_kernel.sh ${2:-xpass_kernel} ${3:-xfin} ${4:-3} > gpurun_out/prof_last.log 2>&1

@@ -29,8 +29,7 @@ static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 // ---- passes with run-time sizes ------------------------------------------------------
 template <int NZ, typename T>
-static void zpass(const T* in, cx<T>* out, long long nrows, int pitch, const T* offset, int ny, int xb) {
-    (void)xb;
+static void zpass(const T* in, cx<T>* out, long long nrows, int pitch, const T* offset, int ny) {
     using K = ZPass<NZ, T>;
     auto tw = build_stage_twiddles<T>(NZ / 2, emax_z(NZ / 2));
     auto twr = build_roots<T>(NZ, NZ / 2 + 1);
@@ -43,14 +42,13 @@ static void zpass(const T* in, cx<T>* out, long long nrows, int pitch, const T* 
     }
 }
 template <int NY, typename T, int WZ>
-static void ypass(cx<T>* w, long long nouter, int nzh, int pitch, int xb) {
+static void ypass(cx<T>* w, long long nouter, int nzh, int pitch) {
     using K = YPass<NY, T, WZ>;
     auto tw = build_stage_twiddles<T>(NY, emax_y(NY));
     int nchunks = (nzh + WZ - 1) / WZ;
     typename K::Params p;
     std::memset(&p, 0, sizeof(p));
     p.w = w; p.nzh = nzh; p.pitch = pitch; p.nchunks = nchunks; p.cstride = nouter * NY * WLay<T>::LW; p.tw = tw.data(); p.nouter = nouter;
-    (void)xb;
     std::vector<cx<T>> smem(K::SMEM_BYTES / sizeof(cx<T>) + 1);
     for (long long cta = 0; cta < nouter * nchunks; ++cta) {
         std::vector<typename K::Regs> regs(K::THREADS);
@@ -60,7 +58,7 @@ static void ypass(cx<T>* w, long long nouter, int nzh, int pitch, int xb) {
 template <int NX, typename T, int WZ, int NF, int MODE, int MU>
 static void xpass_mu(const cx<T>* w0, const cx<T>* w1, int ny, int nz, int pitch, const T* off0, const T* off1,
                   const t21_binspec* spec, double* sums, long long* counts, void* nd_out, int nd_f64, double scale,
-                  int nctas_emulated, int xb) {
+                  int nctas_emulated) {
     using K = XPass<NX, T, WZ, NF, MODE, MU>;
     auto tw = build_stage_twiddles<T>(NX, emax_x(NX));
     typename K::Params p;
@@ -72,7 +70,6 @@ static void xpass_mu(const cx<T>* w0, const cx<T>* w1, int ny, int nz, int pitch
     p.ntiles = (long long)ny * ((p.nchunks + PARTS - 1) / PARTS) * PARTS;
     p.tile_step = nctas_emulated;
     p.xs_log2 = ilog2_rt(NX);
-    (void)xb;
     p.iy0 = 0;
     p.tw = tw.data();
     p.offset[0] = off0; p.offset[1] = off1;
@@ -99,11 +96,11 @@ static void xpass_mu(const cx<T>* w0, const cx<T>* w1, int ny, int nz, int pitch
 template <int NX, typename T, int WZ, int NF, int MODE>
 static void xpass(const cx<T>* w0, const cx<T>* w1, int ny, int nz, int pitch, const T* off0, const T* off1,
                   const t21_binspec* spec, double* sums, long long* counts, void* nd_out, int nd_f64, double scale,
-                  int nctas_emulated, int xb) {
+                  int nctas_emulated) {
     const int mu = (MODE == MODE_BIN && spec && spec->nmu > 0) ? (spec->absolute_mus ? 1 : 2) : 0;
-    if (mu == 0) xpass_mu<NX, T, WZ, NF, MODE, 0>(w0, w1, ny, nz, pitch, off0, off1, spec, sums, counts, nd_out, nd_f64, scale, nctas_emulated, xb);
-    else if (mu == 1) xpass_mu<NX, T, WZ, NF, MODE, 1>(w0, w1, ny, nz, pitch, off0, off1, spec, sums, counts, nd_out, nd_f64, scale, nctas_emulated, xb);
-    else xpass_mu<NX, T, WZ, NF, MODE, 2>(w0, w1, ny, nz, pitch, off0, off1, spec, sums, counts, nd_out, nd_f64, scale, nctas_emulated, xb);
+    if (mu == 0) xpass_mu<NX, T, WZ, NF, MODE, 0>(w0, w1, ny, nz, pitch, off0, off1, spec, sums, counts, nd_out, nd_f64, scale, nctas_emulated);
+    else if (mu == 1) xpass_mu<NX, T, WZ, NF, MODE, 1>(w0, w1, ny, nz, pitch, off0, off1, spec, sums, counts, nd_out, nd_f64, scale, nctas_emulated);
+    else xpass_mu<NX, T, WZ, NF, MODE, 2>(w0, w1, ny, nz, pitch, off0, off1, spec, sums, counts, nd_out, nd_f64, scale, nctas_emulated);
 }
 
 #define DISPATCH_N(n, MACRO)                 \
@@ -125,19 +122,17 @@ static int emu_all(int nx, int ny, int nz, const T* in0, const T* in1, double of
     const int nzh = nz / 2 + 1;
     const int pitch = round_up(nzh, 16);
     const int nf = in1 ? 2 : 1;
-    int xb = 2;                                   // same rule as t21_plan_create
-    while (xb > 0 && ((nx % (1 << xb)) != 0 || (1 << xb) > nx / 16)) --xb;
     std::vector<cx<T>> w[2];
     T offs[2] = {(T)off0d, (T)off1d};
     const T* ins[2] = {in0, in1};
     for (int f = 0; f < nf; ++f) {
         w[f].assign((size_t)nx * ny * pitch, cmake<T>(0, 0));
-#define ZP(N) zpass<N, T>(ins[f], w[f].data(), (long long)nx * ny, pitch, &offs[f], ny, xb)
+#define ZP(N) zpass<N, T>(ins[f], w[f].data(), (long long)nx * ny, pitch, &offs[f], ny)
         DISPATCH_N(nz, ZP)
 #undef ZP
         if (upto >= 2) {
             constexpr int WZ = sizeof(T) == 4 ? 16 : 8;
-#define YP(N) ypass<N, T, (N <= 512 ? WZ : WZ / 2)>(w[f].data(), nx, nzh, pitch, xb)
+#define YP(N) ypass<N, T, (N <= 512 ? WZ : WZ / 2)>(w[f].data(), nx, nzh, pitch)
             DISPATCH_N(ny, YP)
 #undef YP
         }
@@ -155,21 +150,21 @@ static int emu_all(int nx, int ny, int nz, const T* in0, const T* in1, double of
     const int nctas = 3;
     if (spec) {
         if (nf == 1) {
-#define XP(N) xpass<N, T, (N <= 512 ? WZ : WZ / 2), 1, MODE_BIN>(w[0].data(), nullptr, ny, nz, pitch, &offs[0], nullptr, spec, sums, counts, nullptr, 0, 0.0, nctas, xb)
+#define XP(N) xpass<N, T, (N <= 512 ? WZ : WZ / 2), 1, MODE_BIN>(w[0].data(), nullptr, ny, nz, pitch, &offs[0], nullptr, spec, sums, counts, nullptr, 0, 0.0, nctas)
             DISPATCH_N(nx, XP)
 #undef XP
         } else {
-#define XP(N) xpass<N, T, (N <= 512 ? WZ : WZ / 2), 2, MODE_BIN>(w[0].data(), w[1].data(), ny, nz, pitch, &offs[0], &offs[1], spec, sums, counts, nullptr, 0, 0.0, nctas, xb)
+#define XP(N) xpass<N, T, (N <= 512 ? WZ : WZ / 2), 2, MODE_BIN>(w[0].data(), w[1].data(), ny, nz, pitch, &offs[0], &offs[1], spec, sums, counts, nullptr, 0, 0.0, nctas)
             DISPATCH_N(nx, XP)
 #undef XP
         }
     } else {
         if (nf == 1) {
-#define XP(N) xpass<N, T, (N <= 512 ? WZ : WZ / 2), 1, MODE_ND>(w[0].data(), nullptr, ny, nz, pitch, &offs[0], nullptr, nullptr, nullptr, nullptr, nd_out, nd_f64, scale, nctas, xb)
+#define XP(N) xpass<N, T, (N <= 512 ? WZ : WZ / 2), 1, MODE_ND>(w[0].data(), nullptr, ny, nz, pitch, &offs[0], nullptr, nullptr, nullptr, nullptr, nd_out, nd_f64, scale, nctas)
             DISPATCH_N(nx, XP)
 #undef XP
         } else {
-#define XP(N) xpass<N, T, (N <= 512 ? WZ : WZ / 2), 2, MODE_ND>(w[0].data(), w[1].data(), ny, nz, pitch, &offs[0], &offs[1], nullptr, nullptr, nullptr, nd_out, nd_f64, scale, nctas, xb)
+#define XP(N) xpass<N, T, (N <= 512 ? WZ : WZ / 2), 2, MODE_ND>(w[0].data(), w[1].data(), ny, nz, pitch, &offs[0], &offs[1], nullptr, nullptr, nullptr, nd_out, nd_f64, scale, nctas)
             DISPATCH_N(nx, XP)
 #undef XP
         }

@@ -11,12 +11,18 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=1024)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--quick", action="store_true", help="only the fp32 binned estimators")
+ap.add_argument("--cross-only", action="store_true", help="only cross_power_spectrum_1d (large cubes)")
 args = ap.parse_args()
 n = args.size
 dev = torch.device("cuda", 0)
-a = synthetic.toy_dt_cube_torch((n, n, n), seed=1, device=dev)
-b = synthetic.gaussian_cube_torch((n, n, n), seed=2, device=dev)
 L = 714.0
+if args.cross_only:         # large cubes: plain normal deviates, no temporaries
+    g = torch.Generator(device=dev).manual_seed(1)
+    a = torch.randn((n, n, n), generator=g, device=dev)
+    b = torch.randn((n, n, n), generator=g, device=dev)
+else:
+    a = synthetic.toy_dt_cube_torch((n, n, n), seed=1, device=dev)
+    b = synthetic.gaussian_cube_torch((n, n, n), seed=2, device=dev)
 
 
 def timed(fn):
@@ -33,6 +39,10 @@ def timed(fn):
 
 
 out = {"size": n, "unit": "ms per call", "dtype": "f32"}
+if args.cross_only:
+    out["cross_power_spectrum_1d"] = timed(lambda: t2c.cross_power_spectrum_1d(a, b, kbins=15, box_dims=L))
+    print(json.dumps(out))
+    sys.exit(0)
 out["power_spectrum_1d"] = timed(lambda: t2c.power_spectrum_1d(a, kbins=15, box_dims=L))
 out["cross_power_spectrum_1d"] = timed(lambda: t2c.cross_power_spectrum_1d(a, b, kbins=15, box_dims=L))
 for los in (0, 1, 2):

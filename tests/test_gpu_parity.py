@@ -93,6 +93,35 @@ def test_mixed_and_odd_shapes_against_oracle(t2c, shape):
     assert np.abs(nd - nd_o).max() <= 1e-11 * nd_o.max()
 
 
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("shape", [(16, 32, 1024), (16, 1024, 32), (1024, 16, 32), (8, 16, 2048), (2048, 8, 16), (16, 8, 4096)])
+def test_long_pencils_against_oracle(t2c, shape, dtype):
+    """The pencil lengths of the headline configurations (1024, 2048) and the longest instantiated one along
+    each axis in turn, in thin slabs the oracle finishes in seconds: three-stage plans, the Z pass's fused last
+    stage (nz = 1024), the half-width cross tiles (nx = 2048)."""
+    from oracle import ps_oracle
+    rng = np.random.default_rng(sum(shape))
+    x = rng.standard_normal(shape).astype(dtype)
+    y = (0.5 * x + rng.standard_normal(shape)).astype(dtype)
+    box = [100.0, 80.0, 120.0]
+    tol = 1e-5 if dtype == "float32" else 1e-11
+    ps, ks, nm = t2c.power_spectrum_1d(x, kbins=8, box_dims=box, return_n_modes=True)
+    ps_o, ks_o, nm_o = ps_oracle.power_spectrum_1d(x, kbins=8, box_dims=box, return_n_modes=True)
+    assert np.array_equal(nm, nm_o) and np.array_equal(ks, ks_o)
+    np.testing.assert_allclose(ps, ps_o, rtol=tol, equal_nan=True)
+    xs, _, xn = t2c.cross_power_spectrum_1d(x, y, kbins=8, box_dims=box, return_n_modes=True)
+    xs_o, _, xn_o = ps_oracle.cross_power_spectrum_1d(x, y, kbins=8, box_dims=box, return_n_modes=True)
+    assert np.array_equal(xn, xn_o)
+    np.testing.assert_allclose(xs, xs_o, rtol=tol, atol=tol * np.nanmax(np.abs(ps_o)), equal_nan=True)
+    pm, _, _, nmu = t2c.power_spectrum_mu(x, los_axis=2, mubins=4, kbins=5, box_dims=box, return_n_modes=True)
+    pm_o, _, _, nmu_o = ps_oracle.power_spectrum_mu(x, los_axis=2, mubins=4, kbins=5, box_dims=box, return_n_modes=True)
+    assert np.array_equal(nmu, nmu_o)
+    np.testing.assert_allclose(pm, pm_o, rtol=tol, equal_nan=True)
+    nd = t2c.power_spectrum_nd(x, box_dims=box)
+    nd_o = ps_oracle.power_spectrum_nd(x, box_dims=box)
+    assert np.abs(nd - nd_o).max() <= tol * nd_o.max()
+
+
 @pytest.mark.parametrize("shape", [(64, 64), (45, 64), (100,)])
 def test_low_dimensional_inputs_against_oracle(t2c, shape):
     from oracle import ps_oracle

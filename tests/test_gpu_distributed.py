@@ -87,6 +87,24 @@ def test_slab_stages_cross_and_mu_fp64():
     np.testing.assert_allclose(ps.reshape(pm_o.shape), pm_o, rtol=1e-10, equal_nan=True)
 
 
+@pytest.mark.parametrize("fused", [False, True])
+def test_slab_stages_long_x_cross_fp32(fused):
+    """nx = 2048, two fields, fp32: the half-width cross tiles of the X pass reading a y slab that is either one
+    chunk-major array (fused exchange) or P consecutive x slabs (NCCL exchange)."""
+    import torch
+    from oracle import ps_oracle
+    rng = np.random.default_rng(12)
+    a = rng.standard_normal((2048, 16, 32)).astype(np.float32)
+    b = (0.3 * a + rng.standard_normal(a.shape)).astype(np.float32)
+    box = [400.0, 30.0, 60.0]
+    spec, ps, nm = emulate_ranks([torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()], 4, dict(box=box, kbins=8),
+                                 fused=fused)
+    ps_o, _, nm_o = ps_oracle.cross_power_spectrum_1d(a, b, kbins=8, box_dims=box, return_n_modes=True)
+    auto, _ = ps_oracle.power_spectrum_1d(a, kbins=8, box_dims=box)
+    assert np.array_equal(nm, nm_o)
+    np.testing.assert_allclose(ps, ps_o, rtol=1e-5, atol=1e-5 * np.nanmax(np.abs(auto)), equal_nan=True)
+
+
 def test_sharded_nd_single_rank_equals_nd():
     """world = 1: the slab stages, the half-spectrum store and the mirror-row assembly on one GPU."""
     import torch

@@ -313,8 +313,8 @@ int t21_profile_last(float* ms_out, int cap) {
 }
 
 // ---- one cube sharded over P GPUs as x slabs --------------------------------------
-// stage 1 (local):  Z and Y passes of this rank's x slab [nx/P][ny][nz] -> w_out [nx/P][ny][pitch]
-// exchange (caller): all-to-all over NCCL re-partitions the half spectrum into y slabs [nx][ny/P][pitch]
+// stage 1 (local):  Z and Y passes of this rank's x slab [nx/P][ny][nz] -> w_out, chunk-major (nx/P planes of ny rows)
+// exchange (caller): all-to-all over NCCL re-partitions the half spectrum into y slabs (nx planes of ny/P rows)
 // stage 2 (local):  X pass + binning of this rank's y slab; the caller all-reduces sums and counts.
 int t21_slab_pitch(const t21_plan* p) { return p ? p->pitch : 0; }
 
@@ -344,7 +344,7 @@ int t21_slab_stage1(const t21_plan* p, const void* x_slab, const void* offset_or
 }
 
 // stage 1 with the exchange fused in: the Y pass stores every transformed row straight into the y-slab
-// buffer of the rank that owns it (peer_cols[s] = rank s's [nx][ny/P][pitch] buffer, peer-mapped over NVLink),
+// buffer of the rank that owns it (peer_cols[s] = rank s's chunk-major y-slab buffer, nx planes of ny/P rows, peer-mapped over NVLink),
 // so there is no send buffer and no collective; x0_global = index of this slab's first x plane in the cube.
 // The caller orders "all ranks finished stage 1" before stage 2 (a tiny all-reduce on the same stream).
 int t21_slab_stage1_p2p(const t21_plan* p, const void* x_slab, const void* offset_or_null, void* w_scratch,

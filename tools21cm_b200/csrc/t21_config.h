@@ -25,6 +25,11 @@ constexpr int emax_z(int) { return 16; }                                        
 constexpr int emax_y(int n) { return (n == 512 || n == 1024) ? T21_EMAX_Y : 16; }
 constexpr int emax_x(int n) { return (n == 512 || n == 1024) ? T21_EMAX_X : 16; }
 
+// 16*16*r pencil plans run their middle stage in place (t21_fft.cuh, Plan::kInPlace1)
+#ifndef T21_INPLACE_STAGE1
+#define T21_INPLACE_STAGE1 1
+#endif
+
 #ifndef T21_WZ_LONG
 #define T21_WZ_LONG 8
 #endif

@@ -125,6 +125,9 @@ struct Plan {
         return o;
     }
     static constexpr int TW_TOTAL = tw_off(NS);
+    // three-stage plans 16*16*r: the middle stage can run in place (one butterfly per thread, whose 16 inputs
+    // and 16 outputs are the same 16 locations), which saves the barrier between its loads and its stores
+    static constexpr bool kInPlace1 = NS == 3 && radix(0) == 16 && radix(1) == 16 && E == 16;
 };
 
 // number of twiddle entries for a run-time N (host side of t21_plan_create)
@@ -159,20 +162,30 @@ struct RowCursor {
 // ---- one stage, split into its load and its compute+store halves -------------------
 // ld(i) returns element i of this thread's pencil; st(i, v, slot) stores element i, which
 // lives in register slot `slot` (a compile-time constant after unrolling).
-template <class P, int S, typename T, class LoadFn>
+// PERM (stage 2 after an in-place stage 1, see Plan::kInPlace1): element e = jj + k*STRIDE of the Stockham
+// order was left at position 16*(e >> 8) + (e & 15) + T*((e >> 4) & 15) by the thread that produced it.
+template <class P, int S, bool PERM = false, typename T, class LoadFn>
 T21_HD void stage_load(cx<T>* v, int j, LoadFn&& ld) {
     constexpr int R = P::radix(S), NB = P::E / R, STRIDE = P::LEN / R;
+    static_assert(!PERM || (S == 2 && P::kInPlace1), "permuted loads follow the in-place stage");
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         const int jj = j + b * P::T;
 #pragma unroll
-        for (int k = 0; k < R; ++k) v[b * R + k] = ld(jj + k * STRIDE);
+        for (int k = 0; k < R; ++k) {
+            if constexpr (PERM) v[b * R + k] = ld(16 * k + (jj & 15) + P::T * (jj >> 4));   // STRIDE == 256
+            else v[b * R + k] = ld(jj + k * STRIDE);
+        }
     }
 }
 
-template <class P, int S, typename T, class StoreFn>
+// INPLACE (stage 1 only): output k goes back to where input k came from (jj + k*STRIDE) instead of to its
+// Stockham position, so the thread touches no location another thread reads or writes in this stage and its
+// loads and stores need no barrier between them; stage 2 then loads with PERM.
+template <class P, int S, bool INPLACE = false, typename T, class StoreFn>
 T21_HD void stage_compute(cx<T>* v, int j, const cx<T>* __restrict__ tw, StoreFn&& st) {
     constexpr int R = P::radix(S), NB = P::E / R, NSV = P::ns(S), OFF = P::tw_off(S);
+    static_assert(!INPLACE || (S == 1 && P::kInPlace1), "only the middle stage of a 16*16*r plan runs in place");
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         const int jj = j + b * P::T;
@@ -185,7 +198,10 @@ T21_HD void stage_compute(cx<T>* v, int j, const cx<T>* __restrict__ tw, StoreFn
         DFT<R, T>::run(v + b * R);
         const int base = (jj - m) * R + m;
 #pragma unroll
-        for (int k = 0; k < R; ++k) st(base + k * NSV, v[b * R + k], b * R + k);
+        for (int k = 0; k < R; ++k) {
+            if constexpr (INPLACE) st(jj + k * (P::LEN / R), v[b * R + k], b * R + k);
+            else st(base + k * NSV, v[b * R + k], b * R + k);
+        }
     }
 }
 

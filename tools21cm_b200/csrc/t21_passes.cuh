@@ -80,7 +80,14 @@ struct ZPass {
     static constexpr bool kFuseLast = NS >= 2 && P::radix(NS - 1) == 2 && kQ % (64 / (int)sizeof(cx<T>)) == 0 &&
                                       THREADS % ((64 / (int)sizeof(cx<T>)) * ROWS) == 0 && kGroups >= 2 &&
                                       (kQ / (64 / (int)sizeof(cx<T>))) % kGroups == 0;
-    static constexpr int NPHASE = kFuseLast ? 2 * NS - 2 : 2 * NS;
+    // ... and with a 16*16*2 plan the middle stage runs in place (Plan::kInPlace1): stage 0 | stage 1 | fused last
+    static constexpr bool kInPlace = kFuseLast && P::kInPlace1 && T21_INPLACE_STAGE1 != 0;
+    static constexpr int NPHASE = kInPlace ? 3 : (kFuseLast ? 2 * NS - 2 : 2 * NS);
+    // where the in-place middle stage left element e of its (Stockham-ordered) output
+    static T21_HD int where(int e) {
+        if constexpr (kInPlace) return 16 * (e >> 8) + (e & 15) + TP * ((e >> 4) & 15);
+        else return e;
+    }
 
     struct Params {
         const T* in;          // [nrows][NZ]
@@ -116,6 +123,9 @@ struct ZPass {
                 return cmake<T>(v.x - off, v.y - off);
             });
             stage_compute<P, 0>(r.v, j, p.tw, st_smem);
+        } else if constexpr (kInPlace && PH == 1) {
+            stage_load<P, 1>(r.v, j, ld_smem);
+            stage_compute<P, 1, true>(r.v, j, p.tw, st_smem);
         } else if constexpr (PH < NPHASE - 1) {
             constexpr int S = (PH + 1) / 2;
             if constexpr (PH % 2 == 1) stage_load<P, S>(r.v, j, ld_smem);
@@ -145,21 +155,21 @@ struct ZPass {
 #pragma unroll
                 for (int it = 0; it < (kQ / LW) / kGroups; ++it) {
                     const int k = (g + it * kGroups) * LW + l;            // 0 <= k < M/4
-                    const cx<T> a0 = ar[pad(k)], a1 = ar[pad(k + M2)];
+                    const cx<T> a0 = ar[pad(where(k))], a1 = ar[pad(where(k + M2))];
                     const cx<T> u = k ? cmul(ldg(tw2 + k), a1) : a1;
                     const cx<T> zk = cadd(a0, u), zk2 = csub(a0, u);      // Z[k], Z[k+M/2]
                     if (k == 0) {
                         untangle(0, zk, zk);                              // X[0], X[M] (M-0 wraps to 0)
                         untangle(M2, zk2, zk2);                           // the self-paired middle sample
                     } else {
-                        const cx<T> b0 = ar[pad(M2 - k)], b1 = ar[pad(M - k)];
+                        const cx<T> b0 = ar[pad(where(M2 - k))], b1 = ar[pad(where(M - k))];
                         const cx<T> v = cmul(ldg(tw2 + (M2 - k)), b1);
                         untangle(k, zk, csub(b0, v));                     // Z[M-k] = a[M/2-k] - w2^(M/2-k) a[M-k]
                         untangle(M2 - k, cadd(b0, v), zk2);               // pair (M/2-k, M/2+k)
                     }
                 }
                 if (g == 1 && l == 0) {                                   // k = M/4 pairs with 3M/4
-                    const cx<T> a0 = ar[pad(kQ)], a1 = ar[pad(kQ + M2)];
+                    const cx<T> a0 = ar[pad(where(kQ))], a1 = ar[pad(where(kQ + M2))];
                     const cx<T> u = cmul(ldg(tw2 + kQ), a1);
                     untangle(kQ, cadd(a0, u), csub(a0, u));
                 }
@@ -211,13 +221,19 @@ struct ZPass {
 // ======================================================================================
 // strided pencils: shared pieces of the Y and X passes
 // ======================================================================================
-template <int N, typename T, int WZ, int EMAX>
+// MERGE_LAST: the consumer of the last stage's outputs does not touch the exchange buffer (the Y pass stores to
+// global memory), so the last stage's loads and its compute need no barrier between them either.
+template <int N, typename T, int WZ, int EMAX, bool MERGE_LAST = false>
 struct Strided {
     using P = Plan<N, EMAX>;
     static constexpr int E = P::E, TP = P::T, NS = P::NS;
     static constexpr int THREADS = WZ * TP;
     static constexpr int SMEM_ELEMS = (NS > 1) ? N * WZ : 1;
-    static constexpr int FFT_PHASES = 2 * NS - 1;     // phases of one pencil transform
+    // 16*16*r plans run their middle stage in place (Plan::kInPlace1): phases are then
+    //   0: stage 0 (global loads, stores) | 1: stage 1 (loads, stores to the same places) | 2: stage 2 loads |
+    //   3: stage 2 compute + consumer        (2 and 3 are one phase with MERGE_LAST)
+    static constexpr bool kInPlace = P::kInPlace1 && T21_INPLACE_STAGE1 != 0;
+    static constexpr int FFT_PHASES = kInPlace ? (MERGE_LAST ? 3 : 4) : 2 * NS - 1;     // phases of one pencil transform
 
     // phase PH of one transform.  ld_g(i): load element i from global; final(i, v): consume
     // output element i (natural frequency order).
@@ -233,6 +249,14 @@ struct Strided {
             if (!loaded) stage_load<P, 0>(v, j, ld_g);
             if constexpr (NS == 1) stage_compute<P, 0>(v, j, tw, fin);
             else stage_compute<P, 0>(v, j, tw, st_smem);
+        } else if constexpr (kInPlace) {
+            if constexpr (PH == 1) {
+                stage_load<P, 1>(v, j, ld_smem);
+                stage_compute<P, 1, true>(v, j, tw, st_smem);
+            } else {
+                if constexpr (PH == 2) stage_load<P, 2, true>(v, j, ld_smem);
+                if constexpr (PH == 3 || MERGE_LAST) stage_compute<P, 2>(v, j, tw, fin);
+            }
         } else {
             constexpr int S = (PH + 1) / 2;
             if constexpr (PH % 2 == 1) {
@@ -257,7 +281,7 @@ constexpr int kMaxPeers = 16;
 
 template <int NY, typename T, int WZ, int SEND = 0>
 struct YPass {
-    using S = Strided<NY, T, WZ, emax_y(NY)>;
+    using S = Strided<NY, T, WZ, emax_y(NY), true>;
     static constexpr int THREADS = S::THREADS;
     static constexpr int SMEM_BYTES = S::SMEM_ELEMS * (int)sizeof(cx<T>);
     static constexpr int NPHASE = S::FFT_PHASES;

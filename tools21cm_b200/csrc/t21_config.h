@@ -40,7 +40,8 @@ struct WZFor {
 };
 
 // The X pass may own fewer columns per CTA than the Y pass (half a 64-byte piece): smaller CTAs, more of
-// them per SM, barriers that stall fewer warps.  The pieces' parts are consecutive tiles.
+// them per SM, barriers that stall fewer warps.  The pieces' parts are consecutive tiles.  Measured at 1024^3:
+// 4 columns 2.71 ms against 2.31 ms for 8, so the auto spectrum keeps full pieces.
 #ifndef T21_WZ_X
 #define T21_WZ_X T21_WZ_LONG
 #endif

@@ -45,14 +45,14 @@ T21_HD cx<T> rot(cx<T> v) {
         return cmake<T>(v.y, -v.x);                        // * -i
     } else if constexpr (idx == 4) {
         constexpr T h = (T)0.70710678118654752440084436210485;
-        return cmake<T>((v.x + v.y) * h, (v.y - v.x) * h);     // * (1-i)/sqrt2
+        return cscale(cadd(v, cmake<T>(v.y, -v.x)), h);        // * (1-i)/sqrt2 = ((x + y) h, (y - x) h)
     } else if constexpr (idx == 12) {
         constexpr T h = (T)0.70710678118654752440084436210485;
-        return cmake<T>((v.y - v.x) * h, -(v.x + v.y) * h);    // * (-1-i)/sqrt2
+        return cscale(csub(cmake<T>(v.y, -v.x), v), h);        // * (-1-i)/sqrt2 = ((y - x) h, -(x + y) h)
     } else {
         constexpr T c = (T)cos32(idx), s = (T)sin32(idx);
         // (x + iy)(c - is) = (xc + ys) + i(yc - xs)
-        return cmake<T>(v.x * c + v.y * s, v.y * c - v.x * s);
+        return cmul(v, cmake<T>(c, -s));
     }
 }
 

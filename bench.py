@@ -29,18 +29,11 @@ sys.path.insert(0, ROOT)
 
 BOX_MPC = 500.0 / 0.7
 KBINS = 15
-CPU_SECONDS = {128: 0.34, 256: 3.1, 512: 17.5}   # survey measurements of the reference path, 1 thread
 
 
 def algorithmic_bytes(n):
     c = 8 * n * n * (n // 2 + 1)
     return {"z": 4 * n ** 3 + c, "y": 2 * c, "x": c, "pipeline": 4 * n ** 3 + 4 * c}
-
-
-def work_units(n):
-    """N^3 log2 N^3: how CPU time of the reference path scales between cube sizes."""
-    import math
-    return n ** 3 * 3 * math.log2(n)
 
 
 def measured_peak():
@@ -104,51 +97,95 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_seconds(n, repeats=1):
-    """Wall time of the CPU oracle (same scipy.fftpack / np.histogram calls as the reference) on an n^3 cube."""
+def load_reference():
+    """The UNMODIFIED reference's power_spectrum module from baseline/_ref (installed by baseline/install_reference.sh,
+    git-ignored, shipped to the GPU box), imported through a stub package: tools21cm/__init__.py pulls in astropy /
+    scikit-image, which this image lacks and which the power-spectrum path does not need.  None when absent."""
+    import types
+    d = os.path.join(ROOT, "baseline", "_ref", "tools21cm")
+    if not os.path.isfile(os.path.join(d, "power_spectrum.py")):
+        return None
+    if "tools21cm" not in sys.modules:
+        pkg = types.ModuleType("tools21cm")
+        pkg.__path__ = [d]
+        sys.modules["tools21cm"] = pkg
+    try:
+        import tools21cm.power_spectrum as ref
+        return ref
+    except Exception:
+        return None
+
+
+def cpu_reference_run(n, cube=None):
+    """One power_spectrum_1d of the bench workload on an n^3 cube on the host: the reference itself when
+    baseline/_ref is there ("reference"), else the oracle port ("port").  The two halves of the path are timed
+    through the reference's own public functions: power_spectrum_nd (FFT, O(N^3 log N)) and radial_average
+    (k grids + two np.histogram passes, O(N^3)).  Returns (kind, seconds_fft, seconds_binning, result)."""
     import numpy as np
-    from oracle import ps_oracle          # the checker, timed as the CPU baseline -- never on the product path
     from tools21cm_b200 import synthetic
-    cube = synthetic.gaussian_cube((n, n, n), seed=1234)
-    best = None
-    for _ in range(repeats):
+    ref = load_reference()
+    kind = "reference"
+    if ref is None:
+        from oracle import ps_oracle as ref          # the checker, timed as the CPU baseline -- never on the product path
+        kind = "port"
+    if cube is None:
+        cube = synthetic.toy_dt_cube((n, n, n), seed=1235)
+    with np.errstate(all="ignore"):                   # tools21cm/__init__.py:94-95 does the same globally
         t0 = time.perf_counter()
-        with np.errstate(all="ignore"):
-            ps_oracle.power_spectrum_1d(cube, kbins=KBINS, box_dims=BOX_MPC, return_n_modes=True)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return best
+        nd = ref.power_spectrum_nd(cube, box_dims=[BOX_MPC] * 3)
+        t1 = time.perf_counter()
+        ps, ks, nm = ref.radial_average(nd, [BOX_MPC] * 3, kbins=KBINS, binning="log")
+        t2 = time.perf_counter()
+    return kind, t1 - t0, t2 - t1, (ps, ks, nm)
+
+
+def scale_to(n, sample, t_fft, t_bin):
+    """seconds for an n^3 cube from a sample^3 measurement: the FFT part scales as N^3 log N, the binning part
+    (k grids, histograms: 2/3 of the time) as N^3"""
+    import math
+    r = (n / sample) ** 3
+    return t_fft * r * math.log2(n) / math.log2(sample) + t_bin * r
+
+
+CPU_SAMPLE = 512     # ONE sample rule for both legs (the 1024^3 cube needs ~70 GB and minutes on the CPU path)
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU algorithm (oracle port; the reference is pure Python and
-    cannot travel to the GPU box) on the box's host cores.  One thread: scipy.fftpack and np.histogram
-    are single-threaded, exactly like the reference path."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores (one thread:
+    scipy.fftpack and np.histogram are single-threaded).  Each step is one power_spectrum_1d on a 512^3 sample of
+    the workload (the size is in `config` and `cpu_baseline.sample`); `value` scales it to the metric's 1024^3."""
     if rank != 0:
         return
     n = args.size
-    total = max(1, args.steps + args.warmup)
-    budget = 150.0 / total
-    sample = 128
-    for cand in (256, 512):
-        if CPU_SECONDS[cand] * 1.3 <= budget and cand <= n:
-            sample = cand
+    sample = min(CPU_SAMPLE, n)
     for _ in range(args.warmup):
-        cpu_oracle_seconds(sample)
+        cpu_reference_run(sample)
+    tf = tb = 0.0
+    kind = "port"
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_oracle_seconds(sample)
-    per_step = (time.perf_counter() - t0) / max(1, args.steps)
-    est = per_step * work_units(n) / work_units(sample)     # seconds per full-size cube
+    for _ in range(max(1, args.steps)):
+        kind, a, b, _res = cpu_reference_run(sample)
+        tf += a
+        tb += b
+    steps = max(1, args.steps)
+    wall = (time.perf_counter() - t0) / steps
+    tf /= steps
+    tb /= steps
+    est = scale_to(n, sample, tf, tb)
     value = 1.0 / est
-    desc = ("power_spectrum_1d on one %d^3 cube per step (%.2f s), scaled to %d^3 by N^3 log N"
-            % (sample, per_step, n))
+    desc = ("%s power_spectrum_1d on one %d^3 cube per step: %.2f s measured (FFT %.2f s + binning %.2f s; %.2f s with "
+            "input generation); scaled to %d^3 as FFT x N^3 log N + binning x N^3 = %.1f s"
+            % ("tools21cm v2.4.0 (baseline/_ref)" if kind == "reference" else "oracle port of tools21cm",
+               sample, tf + tb, tf, tb, wall, n, est))
+    cfg = workload_config(n)
+    cfg["reference_sample_cube"] = sample
     line = {
         "impl": "reference", "metric": "P(k) cubes/sec at %d^3 fp32" % n, "value": value, "unit": "cubes/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": est * 1e3,
+        "measured_ms_per_sample_step": (tf + tb) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(n),
-        "cpu_baseline": {"value": value, "unit": "cubes/s", "cores": 1, "kind": "port", "sample": desc,
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": "cubes/s", "cores": 1, "kind": kind, "sample": desc,
                          "host_cores": os.cpu_count()},
         "e2e": {"value": value, "unit": "cubes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -368,13 +405,23 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        sample = 512 if n >= 512 else n
-        sec = cpu_oracle_seconds(sample)
-        est = sec * work_units(n) / work_units(sample)
-        cpu = {"value": 1.0 / est, "unit": "cubes/s", "cores": 1, "kind": "port",
-               "sample": "oracle power_spectrum_1d on one %d^3 cube: %.2f s, scaled to %d^3 by N^3 log N "
-                         "(the full cube needs ~70 GB and minutes on the CPU path)" % (sample, sec, n),
-               "host_cores": os.cpu_count()}
+        # the reference on the host cores next to the GPU number, and the GPU result of the SAME cube beside it
+        sample = min(CPU_SAMPLE, n)
+        cube = synthetic.toy_dt_cube((sample,) * 3, seed=1235)
+        kind, tf, tb, (ps_c, ks_c, nm_c) = cpu_reference_run(sample, cube)
+        ps_g, ks_g, nm_g = t2c.power_spectrum_1d(cube, kbins=KBINS, box_dims=BOX_MPC, return_n_modes=True)
+        with np.errstate(all="ignore"):
+            rel = np.abs(ps_g - ps_c) / np.abs(ps_c)
+        est = scale_to(n, sample, tf, tb)
+        cpu = {"value": 1.0 / est, "unit": "cubes/s", "cores": 1, "kind": kind,
+               "sample": "%s power_spectrum_1d on one %d^3 cube: %.2f s measured (FFT %.2f s + binning %.2f s), scaled to "
+                         "%d^3 as FFT x N^3 log N + binning x N^3 = %.1f s (the full cube needs ~70 GB and minutes on the "
+                         "CPU path)" % ("tools21cm v2.4.0 (baseline/_ref)" if kind == "reference" else "oracle port",
+                                        sample, tf + tb, tf, tb, n, est),
+               "measured_seconds_at_sample": tf + tb, "sample_cube": sample, "host_cores": os.cpu_count(),
+               "parity": {"cube": sample, "n_modes_equal": bool(np.array_equal(nm_g, nm_c)),
+                          "k_centres_equal": bool(np.array_equal(ks_g, ks_c)),
+                          "max_rel_err": float(np.nanmax(rel)), "tolerance": 1e-5}}
 
     if rank == 0:
         line = {

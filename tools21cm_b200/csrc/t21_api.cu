@@ -27,24 +27,33 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// SM count of the current device, cached per device ordinal (atomics: calls may come from several host threads)
 int device_sm_count() {
-    static int cached_dev = -1, cached = 0;
+    constexpr int kMaxDev = 64;
+    static std::atomic<int> cache[kMaxDev];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (dev != cached_dev) {
-        int n = 0;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        cached = n;
-        cached_dev = dev;
+    if (dev >= 0 && dev < kMaxDev) {
+        const int hit = cache[dev].load(std::memory_order_relaxed);
+        if (hit > 0) return hit;
     }
-    return cached;
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (dev >= 0 && dev < kMaxDev) cache[dev].store(n, std::memory_order_relaxed);
+    return n;
+}
+
+// T21_PENCIL32=0 keeps the round-1 CTA-per-tile kernels everywhere (A/B runs); read once
+static bool use_pencil32() {
+    static const bool on = [] { const char* e = getenv("T21_PENCIL32"); return !(e && e[0] == '0'); }();
+    return on;
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ---- optional per-pass timing (bench.py's roofline block) ------------------------------
-// When enabled, every public call records a CUDA event on the caller's stream after each
-// pass; t21_profile_last() turns them into per-slot durations.  Off by default.
+// When enabled (per host thread), every public call of that thread records a CUDA event on the caller's stream
+// after each pass; t21_profile_last() turns them into per-slot durations.  Off by default.
 enum { SLOT_MEAN = 0, SLOT_Z, SLOT_Y, SLOT_X, SLOT_REDUCE, SLOT_COUNT };
 struct Prof {
     bool on = false;
@@ -54,7 +63,7 @@ struct Prof {
     int n = 0;          // segments recorded in the last call
     bool made = false;
 };
-static Prof g_prof;
+static thread_local Prof g_prof;   // per host thread: concurrent callers do not share event slots
 
 static void prof_begin(cudaStream_t st) {
     if (!g_prof.on) return;
@@ -83,6 +92,7 @@ struct t21_plan {
     int fast[3];          // axis handled by the Stockham kernels
     void* tw[3];          // stage twiddles per axis (z: for nz/2), device
     void* twr;            // exp(-2 pi i k / nz), k = 0..nz/2, device
+    void* tw32[3];        // Plan<n, 32> stage twiddles of the warp-per-pencil kernels (fp32, n = 1024), or null
     int max_grid;         // capacity (in CTAs) of the partial-histogram buffers
 };
 
@@ -124,6 +134,10 @@ static int build_tables(t21_plan* p) {
             if (int rc = upload<T>(build_roots<T>(p->n[d], p->n[d]), &p->tw[d])) return rc;   // generic pass
         }
     }
+    if (sizeof(T) == 4 && use_pencil32())
+        for (int d = 0; d < 2; ++d)
+            if (p->n[d] == 1024)
+                if (int rc = upload<T>(build_stage_twiddles<T>(1024, 32), &p->tw32[d])) return rc;
     if (p->fast[2]) {
         if (int rc = upload<T>(build_roots<T>(p->n[2], p->n[2] / 2 + 1), &p->twr)) return rc;
     } else {
@@ -167,6 +181,7 @@ int t21_plan_create(t21_plan** out, int nx, int ny, int nz, int dtype, int devic
 int t21_plan_destroy(t21_plan* p) {
     if (!p) return T21_OK;
     for (int d = 0; d < 3; ++d) if (p->tw[d]) cudaFree(p->tw[d]);
+    for (int d = 0; d < 3; ++d) if (p->tw32[d]) cudaFree(p->tw32[d]);
     if (p->twr) cudaFree(p->twr);
     delete p;
     return T21_OK;
@@ -237,7 +252,7 @@ int t21_ps_binned(const t21_plan* p, const void* x1, const void* x2, int subtrac
     a.w[1] = nf == 2 ? ws + L.w[1] : nullptr;
     a.nf = nf;
     a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch; a.xs_log2 = -1;
-    a.tw = p->tw[0];
+    a.tw = p->tw[0]; a.tw32 = p->tw32[0];
     a.offset[0] = offs[0]; a.offset[1] = offs[1];
     a.ntot = (double)p->n[0] * p->n[1] * p->n[2];
     a.bins = spec;
@@ -281,7 +296,7 @@ int t21_ps_nd(const t21_plan* p, const void* x1, const void* x2, int subtract_me
     a.w[1] = nf == 2 ? ws + L.w[1] : nullptr;
     a.nf = nf;
     a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch; a.xs_log2 = -1;
-    a.tw = p->tw[0];
+    a.tw = p->tw[0]; a.tw32 = p->tw32[0];
     a.offset[0] = offs[0]; a.offset[1] = offs[1];
     a.ntot = (double)p->n[0] * p->n[1] * p->n[2];
     a.nd_out = out; a.nd_f64 = out_dtype == T21_F64; a.scale = scale;
@@ -423,7 +438,7 @@ int t21_slab_stage2(const t21_plan* p, const void* w1, const void* w2, int n_xsl
     memset(&a, 0, sizeof(a));
     a.w[0] = w1; a.w[1] = w2; a.nf = nf;
     a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch; a.xs_log2 = xs_log2; a.iy0 = iy0;
-    a.tw = p->tw[0];
+    a.tw = p->tw[0]; a.tw32 = p->tw32[0];
     a.offset[0] = offset1; a.offset[1] = offset2;
     a.ntot = (double)p->n[0] * ny_global * p->n[2];
     a.bins = spec; a.nbins = nbins;
@@ -463,7 +478,7 @@ int t21_slab_stage2_nd(const t21_plan* p, const void* w1, const void* w2, int n_
     memset(&a, 0, sizeof(a));
     a.w[0] = w1; a.w[1] = w2; a.nf = w2 ? 2 : 1;
     a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch; a.xs_log2 = xs_log2; a.iy0 = iy0;
-    a.tw = p->tw[0];
+    a.tw = p->tw[0]; a.tw32 = p->tw32[0];
     a.offset[0] = offset1; a.offset[1] = offset2;
     a.ntot = (double)p->n[0] * ny_global * p->n[2];
     a.nd_out = out_half; a.nd_f64 = out_dtype == T21_F64; a.nd_half = 1; a.scale = scale;

@@ -105,14 +105,19 @@ __device__ __forceinline__ void advance_coords(int ix0, int iy0, int iz0, int d,
 }
 
 template <typename T, int HK, class BinOf>
-__device__ __forceinline__ void bin_array(const T* __restrict__ p, int n0, int n1, int n2, int nbins,
+__device__ __forceinline__ void bin_array(const T* __restrict__ p, int n0, int n1, int n2, int nbins, int warp_private,
                                           double* __restrict__ part_sum, unsigned* __restrict__ part_cnt, double* gsum,
                                           unsigned long long* gcnt, BinOf&& bin_of) {
+    // HK == 0: CTA histogram in shared memory -- one copy per warp when that fits (only lane 0 of the owning warp
+    // writes it, in program order; warps, then CTAs, are summed in a fixed order => bit-reproducible run to run),
+    // otherwise one copy updated with atomics
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NW = kBinThreads / 32;
+    const int copies = (HK == 0 && warp_private) ? NW : 1;
     double* hs = reinterpret_cast<double*>(smem_raw);
-    unsigned* hc = reinterpret_cast<unsigned*>(hs + nbins);
+    unsigned* hc = reinterpret_cast<unsigned*>(hs + (size_t)copies * nbins);
     if (HK == 0) {
-        for (int b = threadIdx.x; b < nbins; b += kBinThreads) { hs[b] = 0.0; hc[b] = 0u; }
+        for (int b = threadIdx.x; b < copies * nbins; b += kBinThreads) { hs[b] = 0.0; hc[b] = 0u; }
         __syncthreads();
     }
     const long long total = (long long)n0 * n1 * n2;
@@ -123,6 +128,7 @@ __device__ __forceinline__ void bin_array(const T* __restrict__ p, int n0, int n
     WarpBinCache acc;
     wbc_init(acc);
     SmemHist sh{hs, hc};
+    WarpPrivHist wh{hs + (size_t)(threadIdx.x >> 5) * nbins, hc + (size_t)(threadIdx.x >> 5) * nbins};
     GlobalHist gh{gsum, gcnt};
     for (long long o0 = warp0 * span; o0 < total; o0 += nwarps * span) {     // warp-uniform trip count
         const long long t = o0 / n2;                                         // one 64-bit division per 128 samples
@@ -140,16 +146,20 @@ __device__ __forceinline__ void bin_array(const T* __restrict__ p, int n0, int n
             int ix, iy, iz, w = 1;
             advance_coords(ix0, iy0, iz0, u * 32 + lane, n1, n2, ix, iy, iz);
             const int bin = o < total ? bin_of(ix, iy, iz, w) : -1;
-            if (HK == 0) wbc_add(acc, sh, bin, (double)v[u], (unsigned)w);
+            if (HK == 0 && warp_private) wbc_add(acc, wh, bin, (double)v[u], (unsigned)w);
+            else if (HK == 0) wbc_add(acc, sh, bin, (double)v[u], (unsigned)w);
             else wbc_add(acc, gh, bin, (double)v[u], (unsigned)w);
         }
     }
     if (HK == 0) {
-        wbc_flush(acc, sh);
+        if (warp_private) wbc_flush(acc, wh); else wbc_flush(acc, sh);
         __syncthreads();
         for (int b = threadIdx.x; b < nbins; b += kBinThreads) {
-            part_sum[(size_t)blockIdx.x * nbins + b] = hs[b];
-            part_cnt[(size_t)blockIdx.x * nbins + b] = hc[b];
+            double sacc = 0.0;
+            unsigned cacc = 0u;
+            for (int w = 0; w < copies; ++w) { sacc += hs[(size_t)w * nbins + b]; cacc += hc[(size_t)w * nbins + b]; }
+            part_sum[(size_t)blockIdx.x * nbins + b] = sacc;
+            part_cnt[(size_t)blockIdx.x * nbins + b] = cacc;
         }
     } else {
         wbc_flush(acc, gh);
@@ -158,10 +168,10 @@ __device__ __forceinline__ void bin_array(const T* __restrict__ p, int n0, int n
 
 template <typename T, int HK>
 __global__ void __launch_bounds__(kBinThreads)
-bin_only_kernel(const T* __restrict__ p, const __grid_constant__ t21_binspec B, int nbins,
+bin_only_kernel(const T* __restrict__ p, const __grid_constant__ t21_binspec B, int nbins, int warp_private,
                 double* __restrict__ part_sum, unsigned* __restrict__ part_cnt, double* gsum,
                 unsigned long long* gcnt) {
-    bin_array<T, HK>(p, B.n[0], B.n[1], B.n[2], nbins, part_sum, part_cnt, gsum, gcnt,
+    bin_array<T, HK>(p, B.n[0], B.n[1], B.n[2], nbins, warp_private, part_sum, part_cnt, gsum, gcnt,
                      [&](int ix, int iy, int iz, int& w) {
                          const ModeBins mb = classify(B, ix, iy, iz, false);
                          w = mb.own_w;
@@ -177,10 +187,10 @@ bin_only_kernel(const T* __restrict__ p, const __grid_constant__ t21_binspec B, 
 template <typename T, int HK>
 __global__ void __launch_bounds__(kBinThreads)
 bin_cyl_kernel(const T* __restrict__ p, int n0, int n1, int n2, int nu_axis, const int* __restrict__ perp_tab,
-               const int* __restrict__ par_tab, int npar, int nbins, double* __restrict__ part_sum,
+               const int* __restrict__ par_tab, int npar, int nbins, int warp_private, double* __restrict__ part_sum,
                unsigned* __restrict__ part_cnt, double* gsum, unsigned long long* gcnt) {
     const int nb_perp_inner = nu_axis == 2 ? n1 : n2;      // length of the second perpendicular axis
-    bin_array<T, HK>(p, n0, n1, n2, nbins, part_sum, part_cnt, gsum, gcnt,
+    bin_array<T, HK>(p, n0, n1, n2, nbins, warp_private, part_sum, part_cnt, gsum, gcnt,
                      [&](int ix, int iy, int iz, int& w) {
                          const int inu = nu_axis == 0 ? ix : (nu_axis == 1 ? iy : iz);
                          const int ia = nu_axis == 0 ? iy : ix;
@@ -204,14 +214,16 @@ int launch_bin_cyl(const void* p, int dtype, int n0, int n1, int n2, int nu_axis
     if (g > cap) g = cap;
     if (!global && g > max_grid) g = max_grid;
     if (g < 1) g = 1;
-    const size_t smem = global ? 0 : (size_t)nbins * (sizeof(double) + sizeof(unsigned));
+    // per-warp histogram copies (deterministic sums) while they fit the default 48 KB of dynamic shared memory
+    const int wp = (!global && (size_t)(kBinThreads / 32) * nbins * 12 <= 48 * 1024) ? 1 : 0;
+    const size_t smem = global ? 0 : (size_t)(wp ? kBinThreads / 32 : 1) * nbins * (sizeof(double) + sizeof(unsigned));
     unsigned long long* gc = reinterpret_cast<unsigned long long*>(gcnt);
     if (dtype == T21_F32) {
-        if (global) bin_cyl_kernel<float, 1><<<(int)g, kBinThreads, smem, st>>>((const float*)p, n0, n1, n2, nu_axis, perp_tab, par_tab, npar, nbins, nullptr, nullptr, gsum, gc);
-        else bin_cyl_kernel<float, 0><<<(int)g, kBinThreads, smem, st>>>((const float*)p, n0, n1, n2, nu_axis, perp_tab, par_tab, npar, nbins, part_sum, part_cnt, nullptr, nullptr);
+        if (global) bin_cyl_kernel<float, 1><<<(int)g, kBinThreads, smem, st>>>((const float*)p, n0, n1, n2, nu_axis, perp_tab, par_tab, npar, nbins, 0, nullptr, nullptr, gsum, gc);
+        else bin_cyl_kernel<float, 0><<<(int)g, kBinThreads, smem, st>>>((const float*)p, n0, n1, n2, nu_axis, perp_tab, par_tab, npar, nbins, wp, part_sum, part_cnt, nullptr, nullptr);
     } else {
-        if (global) bin_cyl_kernel<double, 1><<<(int)g, kBinThreads, smem, st>>>((const double*)p, n0, n1, n2, nu_axis, perp_tab, par_tab, npar, nbins, nullptr, nullptr, gsum, gc);
-        else bin_cyl_kernel<double, 0><<<(int)g, kBinThreads, smem, st>>>((const double*)p, n0, n1, n2, nu_axis, perp_tab, par_tab, npar, nbins, part_sum, part_cnt, nullptr, nullptr);
+        if (global) bin_cyl_kernel<double, 1><<<(int)g, kBinThreads, smem, st>>>((const double*)p, n0, n1, n2, nu_axis, perp_tab, par_tab, npar, nbins, 0, nullptr, nullptr, gsum, gc);
+        else bin_cyl_kernel<double, 0><<<(int)g, kBinThreads, smem, st>>>((const double*)p, n0, n1, n2, nu_axis, perp_tab, par_tab, npar, nbins, wp, part_sum, part_cnt, nullptr, nullptr);
     }
     count_launch();
     T21_CUDA_OK(cudaGetLastError());
@@ -230,14 +242,16 @@ int launch_bin_only(const void* p, int dtype, const t21_binspec& spec, double* p
     if (g > cap) g = cap;
     if (!global && g > max_grid) g = max_grid;
     if (g < 1) g = 1;
-    const size_t smem = global ? 0 : (size_t)nbins * (sizeof(double) + sizeof(unsigned));
+    // per-warp histogram copies (deterministic sums) while they fit the default 48 KB of dynamic shared memory
+    const int wp = (!global && (size_t)(kBinThreads / 32) * nbins * 12 <= 48 * 1024) ? 1 : 0;
+    const size_t smem = global ? 0 : (size_t)(wp ? kBinThreads / 32 : 1) * nbins * (sizeof(double) + sizeof(unsigned));
     unsigned long long* gc = reinterpret_cast<unsigned long long*>(gcnt);
     if (dtype == T21_F32) {
-        if (global) bin_only_kernel<float, 1><<<(int)g, kBinThreads, smem, st>>>((const float*)p, spec, nbins, nullptr, nullptr, gsum, gc);
-        else bin_only_kernel<float, 0><<<(int)g, kBinThreads, smem, st>>>((const float*)p, spec, nbins, part_sum, part_cnt, nullptr, nullptr);
+        if (global) bin_only_kernel<float, 1><<<(int)g, kBinThreads, smem, st>>>((const float*)p, spec, nbins, 0, nullptr, nullptr, gsum, gc);
+        else bin_only_kernel<float, 0><<<(int)g, kBinThreads, smem, st>>>((const float*)p, spec, nbins, wp, part_sum, part_cnt, nullptr, nullptr);
     } else {
-        if (global) bin_only_kernel<double, 1><<<(int)g, kBinThreads, smem, st>>>((const double*)p, spec, nbins, nullptr, nullptr, gsum, gc);
-        else bin_only_kernel<double, 0><<<(int)g, kBinThreads, smem, st>>>((const double*)p, spec, nbins, part_sum, part_cnt, nullptr, nullptr);
+        if (global) bin_only_kernel<double, 1><<<(int)g, kBinThreads, smem, st>>>((const double*)p, spec, nbins, 0, nullptr, nullptr, gsum, gc);
+        else bin_only_kernel<double, 0><<<(int)g, kBinThreads, smem, st>>>((const double*)p, spec, nbins, wp, part_sum, part_cnt, nullptr, nullptr);
     }
     count_launch();
     T21_CUDA_OK(cudaGetLastError());

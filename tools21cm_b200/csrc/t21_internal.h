@@ -19,6 +19,7 @@ struct YArgs {
 struct XArgs {
     const void* w[2]; int nf; int nx, ny, nz, nzh, pitch; int xs_log2; int iy0;   // xs_log2: log2(x planes per slab), <0 = one slab
     const void* tw; const void* offset[2]; double ntot;
+    const void* tw32;                        // Plan<nx, 32> stage twiddles (warp-per-pencil kernels) or null
     const t21_binspec* bins;                 // MODE_BIN
     void* nd_out; int nd_f64; int nd_half; double scale;  // MODE_ND
     // histogram plumbing (MODE_BIN)
@@ -39,7 +40,12 @@ int launch_xpass_f64_bin_mu1(XArgs& a, cudaStream_t st);
 int launch_xpass_f64_bin_mu2(XArgs& a, cudaStream_t st);
 int launch_xpass_f32_nd(XArgs& a, cudaStream_t st);
 int launch_xpass_f64_nd(XArgs& a, cudaStream_t st);
+// t21_xpass32.cu: warp-per-pencil X pass (fp32, nx = 1024, one field), TMA-staged
+bool xpass32_applicable(int dtype, const XArgs& a);
+int launch_xpass32_bin(XArgs& a, cudaStream_t st);
+
 inline int launch_xpass_bin(int dtype, XArgs& a, cudaStream_t st) {
+    if (xpass32_applicable(dtype, a)) return launch_xpass32_bin(a, st);
     const int mu = (a.bins && a.bins->nmu > 0) ? (a.bins->absolute_mus ? 1 : 2) : 0;
     if (dtype == T21_F32)
         return mu == 0 ? launch_xpass_f32_bin_mu0(a, st) : (mu == 1 ? launch_xpass_f32_bin_mu1(a, st) : launch_xpass_f32_bin_mu2(a, st));

@@ -124,7 +124,6 @@ inline int launch_tiles(const typename K::Params& p, long long nctas, cudaStream
     if (nctas <= 0) return 0;
     if (nctas > 2147483647LL) { set_error("grid too large"); return T21_EINVAL; }
     size_t smem = K::SMEM_BYTES;
-    if (const char* e = getenv("T21_PAD_SMEM")) smem += (size_t)atoi(e);   // experiments: lower the occupancy
     auto kern = tile_kernel<K, T>;
     if (int rc = ensure_smem(kern, smem)) return rc;
     kern<<<(unsigned)nctas, K::THREADS, smem, st>>>(p);
@@ -160,7 +159,6 @@ inline int launch_x(XArgs& a, cudaStream_t st) {
     const int warp_private = (hk == 0 && K::THREADS % 32 == 0 &&
                               (size_t)NW * a.nbins * (sizeof(double) + sizeof(unsigned)) <= 16 * 1024) ? 1 : 0;
     if (hk == 0) smem += (size_t)(warp_private ? NW : 1) * a.nbins * (sizeof(double) + sizeof(unsigned));
-    if (const char* e = getenv("T21_PAD_SMEM")) smem += (size_t)atoi(e);   // experiments: lower the occupancy
     int occ = 0, grid = 0;
 #define T21_LAUNCH_HK(HKV)                                                                              \
     {                                                                                                   \

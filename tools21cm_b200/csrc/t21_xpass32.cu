@@ -1,0 +1,542 @@
+// X pass, warp-per-pencil form (fp32, nx = 1024): TMA-landed tiles, radix-32 x radix-32 in registers with packed
+// f32x2 butterflies, binning straight from the registers.
+//
+// Why (profiles/r01_ncu_final_xf_summary.txt): the 512-thread X pass of round 1 spent 33 % of its stall samples at
+// CTA-wide barriers (five per tile, 16 values per thread, three stages) and had nothing in flight while a tile's
+// global loads landed.  Here
+//   * a tile (all 1024 x of the 8 columns of one 64-byte piece, one ky) is fetched by TMA (cp.async.bulk.tensor, four
+//     boxes of 256 rows x 64 B) into shared memory under an mbarrier, issued as soon as the previous tile's data has
+//     left the buffer -- the copy overlaps the second half of the previous tile's work and no register holds it;
+//   * a thread holds 32 values: 1024 = 32 * 32 needs ONE exchange.  Stage 0 runs with lanes across the 8 columns
+//     (conflict-free reads of the landed [x][8] tile) and stores transposed, pencil-major and padded
+//     (i + i/32, pitch = 2 mod 16: conflict-free both ways); stage 1 then has one WARP per pencil, so nothing after
+//     the exchange needs a CTA barrier;
+//   * after stage 1 lane l holds kx = l + 32 k (k = 0..31) of its pencil: a step covers 32 consecutive kx at one
+//     (ky, kz), so `c_yz = ky^2 + kz^2` is warp-uniform and the interval tests of the bin cache are made on
+//     warp-uniform values for a whole pencil, or for the two steps that cover |kx| in [32k, 32k+32] -- no power
+//     tile, no re-deal, no barrier;
+//   * CTAs are 256 threads (8 pencils), two per SM; three 256-thread barriers per tile.
+// Mode counts are decided exactly as in XPass (t21_passes.cuh): guard intervals first, classify() otherwise.
+#include <string.h>
+#include "t21_launch.cuh"
+#include "t21_tma.cuh"
+
+namespace t21 {
+
+namespace x32 {
+
+constexpr int NX = 1024;
+constexpr int WZ = 8;                               // columns per tile = one 64-byte piece
+constexpr int THREADS = 256;
+constexpr int PITCH = NX + NX / 32 + 2;             // padded pencil, = 2 (mod 16): see the header comment
+constexpr int BUF_BYTES = WZ * PITCH * 8;           // 67 712 >= the landed tile (65 536)
+constexpr int BAR_OFF = (BUF_BYTES + 127) / 128 * 128;
+constexpr int STAGE_OFF = BAR_OFF + 128;           // per-warp strips of 32 x 32 powers (shells epilogue)
+constexpr int HIST_OFF = STAGE_OFF + (THREADS / 32) * 32 * 32 * 4;
+using P = Plan<NX, 32>;
+static_assert(P::NS == 2 && P::T == 32 && P::E == 32, "one warp per pencil");
+
+struct Params {
+    int ny, nz, nzh, nchunks;
+    long long ntiles;
+    int iy0;
+    int box_rows;          // x planes per TMA box
+    int xs_log2;           // log2(x planes per slab)
+    const cx<float>* tw;   // Plan<1024, 32> stage twiddles
+    const float* offset;   // mean offset (device scalar) or null
+    double ntot;
+    t21_binspec bins;
+};
+
+#if T21_DEVICE_CODE   // (WarpBins has its device members only in the device pass)
+
+template <int MU>
+struct Accs {
+    WarpBins<(MU != 0)> a[MU == 2 ? 2 : 1];
+};
+
+// exact bin of one mode for accumulator `which` (see XPass::exact_bin)
+__device__ __forceinline__ int exact_bin(const t21_binspec& B, int ix, int iy, int iz, bool has_twin, int which, float sh, int& weight) {
+    const ModeBins mb = classify(B, ix, iy, iz, has_twin);
+    int bin = which == 0 ? mb.own : mb.twin;
+    weight = which == 0 ? mb.own_w : 1;
+    if (bin < 0) {
+        const int nb = B.nk * (B.nmu > 0 ? B.nmu : 1);
+        weight = 1;
+        if (sh < ldg(B.k_hi_f + B.nk)) bin = nb;
+        else if (sh >= ldg(B.k_lo_f + B.nk + 1)) bin = nb + 1;
+    }
+    return bin;
+}
+
+template <int MU, class Hist>
+__device__ __forceinline__ void epilogue(const Params& p, const cx<float>* v, int lane, int iy, int iz, Accs<MU>& accs, Hist& hist) {
+    const t21_binspec& B = p.bins;
+    const bool has_twin = (iz != 0) && (iz != p.nz - iz);
+    const int nb = B.nk * (MU ? B.nmu : 1);
+    const float* sfx = B.tab_sf[0];
+    const float c_yz = ldg(B.tab_sf[1] + iy) + ldg(B.tab_sf[2] + iz);
+    const unsigned wt = (has_twin && MU != 2) ? 2u : 1u;
+    const float wf = (float)wt;
+
+    float pw[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) pw[k] = v[k].x * v[k].x + v[k].y * v[k].y;
+    if (iy == 0 && iz == 0 && lane == 0) {
+        // DC of (x - c) plus c*N: the only sample the mean offset changes.  It stays in the flow with power 0 (so
+        // that it is counted like any other mode); its true power goes to the histogram here, with count 0.
+        const double c0 = p.offset ? (double)ldg(p.offset) : 0.0;
+        const double ra = (double)v[0].x + c0 * p.ntot;
+        const double dc = ra * ra + (double)v[0].y * (double)v[0].y;
+        pw[0] = 0.f;
+        const ModeBins mb = classify(B, 0, 0, 0, false);
+        if (mb.own >= 0) hist.add(mb.own, dc, 0u);
+    }
+
+    unsigned slow0 = 0u, slow1 = 0u;     // steps that need the exact classification (warp-uniform masks)
+    if constexpr (MU == 0) {
+        WarpBins<false>& acc = accs.a[0];
+        // the whole pencil inside one cached interval?  s^ grows with |kx| (fp32 addition is monotonic)
+        const float t_lo = c_yz + ldg(sfx), t_hi = c_yz + ldg(sfx + NX / 2);
+        const bool w0 = t_lo >= acc.slo[0] && t_hi < acc.shi[0];
+        const bool w1 = t_lo >= acc.slo[1] && t_hi < acc.shi[1];
+        if (w0 || w1) {
+            float g[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                g[q] = ((pw[8 * q] + pw[8 * q + 1]) + (pw[8 * q + 2] + pw[8 * q + 3])) +
+                       ((pw[8 * q + 4] + pw[8 * q + 5]) + (pw[8 * q + 6] + pw[8 * q + 7]));
+            const double d = ((double)(g[0] * wf) + (double)(g[1] * wf)) + ((double)(g[2] * wf) + (double)(g[3] * wf));
+            if (w0) { acc.sum[0] += d; acc.cnt[0] += 32u * wt; }
+            else { acc.sum[1] += d; acc.cnt[1] += 32u * wt; }
+            return;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            // steps k (kx = 32k + l) and 31-k (kx - NX = -(32k + 32 - l)) cover |kx| in [32k, 32k + 32]
+            const float a_lo = c_yz + ldg(sfx + 32 * k), a_hi = c_yz + ldg(sfx + 32 * k + 32);
+            const bool u0 = a_lo >= acc.slo[0] && a_hi < acc.shi[0];
+            const bool u1 = a_lo >= acc.slo[1] && a_hi < acc.shi[1];
+            if (u0 || u1) {
+                const double d = (double)((pw[k] + pw[31 - k]) * wf);
+                if (u0) { acc.sum[0] += d; acc.cnt[0] += 2u * wt; }
+                else { acc.sum[1] += d; acc.cnt[1] += 2u * wt; }
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int kk = h ? 31 - k : k;
+                    const float sh = ldg(sfx + lane + 32 * kk) + c_yz;
+                    if (!warpbins_fast<false>(acc, sh, 0.f, (double)(pw[kk] * wf), wt, true)) slow0 |= 1u << kk;
+                }
+            }
+        }
+    } else {
+        const int los = B.los_axis;
+        const int zx = B.zero_idx[0], nyx = B.nyq_idx[0];
+        // k_perp = 0 line (power_spectrum.py:563-575): the part of the test that is fixed for this pencil
+        bool line_fixed = false;
+        if (B.exclude_zero)
+            line_fixed = los == 0 ? (iy == B.zero_idx[1] && iz == B.zero_idx[2])
+                                  : (los == 1 ? iz == B.zero_idx[2] : iy == B.zero_idx[1]);
+        float klos_c = 0.f;
+        bool nyq_c = false;
+        if (los != 0) {
+            const int il = los == 1 ? iy : iz;
+            klos_c = ldg(B.tab_losf + il);
+            nyq_c = il == B.nyq_idx[los];
+        }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const int ix = lane + 32 * k;
+            const bool valid = !(line_fixed && (los == 0 || ix == zx));
+            const float sh = ldg(sfx + ix) + c_yz;
+            const float muh = (los == 0 ? ldg(B.tab_losf + ix) : klos_c) * fast_rsqrt(sh);
+            const float m_own = MU == 1 ? fabsf(muh) : muh;
+            if (!warpbins_fast<true>(accs.a[0], sh, m_own, (double)(pw[k] * wf), wt, valid)) slow0 |= 1u << k;
+            if constexpr (MU == 2) {                      // the twin goes to the mirrored mu bin
+                const bool nyq = los == 0 ? ix == nyx : nyq_c;
+                if (!warpbins_fast<true>(accs.a[1], sh, nyq ? muh : -muh, (double)pw[k], 1u, valid && has_twin)) slow1 |= 1u << k;
+            }
+        }
+    }
+    if ((slow0 | slow1) == 0u) return;
+
+    // rare: some lane sits in a guard band or in a bin that is not cached.  The powers go through a local array
+    // so that this loop is rolled (one copy of the exact path in the code).
+    float spill[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) spill[k] = pw[k];
+    const int los = MU ? B.los_axis : -1;
+    bool line_fixed = false;
+    if (MU && B.exclude_zero)
+        line_fixed = los == 0 ? (iy == B.zero_idx[1] && iz == B.zero_idx[2])
+                              : (los == 1 ? iz == B.zero_idx[2] : iy == B.zero_idx[1]);
+#pragma unroll 1
+    for (unsigned todo = slow0 | slow1; todo; todo &= todo - 1) {
+        const int k = __ffs(todo) - 1;
+        const int ix = lane + 32 * k;
+        const float pk = spill[k];
+        const float sh = ldg(sfx + ix) + c_yz;
+        bool valid = true;
+        if (MU) valid = !(line_fixed && (los == 0 || ix == B.zero_idx[0]));
+        if ((slow0 >> k) & 1u) {
+            int w1 = 1;
+            const int bin = valid ? exact_bin(B, ix, iy, iz, has_twin, 0, sh, w1) : -1;
+            warpbins_slow(accs.a[0], hist, B, nb, bin, w1 == (int)wt ? (double)(pk * wf) : (double)pk, (unsigned)w1, valid);
+        }
+        if constexpr (MU == 2) {
+            if ((slow1 >> k) & 1u) {
+                const bool tv = valid && has_twin;
+                int w1 = 1;
+                const int bin = tv ? exact_bin(B, ix, iy, iz, has_twin, 1, sh, w1) : -1;
+                warpbins_slow(accs.a[1], hist, B, nb, bin, (double)pk, 1u, tv);
+            }
+        }
+    }
+}
+
+// ---- shells (MU = 0): exact bin boundaries along the pencil -----------------------------------------------
+// Along a pencil s = (kx^2 + ky^2) + kz^2 only grows with |kx| (rounding is monotonic), so bin b is the index range
+// m_b <= |kx| < m_{b+1} with m_e = #{f : s(f) < thr[e]}.  Lane e finds m_e for edge e by bisection with the
+// reference's own float64 sequence (10 probes of tab_s[0]); no fp32 estimate, no guard band, no look-up table.
+// The pencil is then walked in steps of 64 modes (|kx| in [32k, 32k + 32]): steps no boundary falls into add
+// their powers to an fp32 run; the others (a bit mask built with one warp reduction) give every lane its bin
+// from the boundaries inside the step.  Sums leave the lanes through the two-entry warp cache (WarpBinCache).
+template <class Hist>
+__device__ __forceinline__ void wbc_add_uniform(WarpBinCache& a, Hist& h, int bin, double v, unsigned w) {
+    if (bin == a.bin[0]) { a.sum[0] += v; a.cnt[0] += w; a.lru = 1; }
+    else if (bin == a.bin[1]) { a.sum[1] += v; a.cnt[1] += w; a.lru = 0; }
+    else if (a.lru == 0) {
+        if (a.bin[0] >= 0) wbc_evict(a, h, 0);
+        a.bin[0] = bin; a.sum[0] = v; a.cnt[0] = w; a.lru = 1;
+    } else {
+        if (a.bin[1] >= 0) wbc_evict(a, h, 1);
+        a.bin[1] = bin; a.sum[1] = v; a.cnt[1] = w; a.lru = 0;
+    }
+}
+
+// exact s of |kx| = f on this pencil: the reference's float64 sequence (kx^2 + ky^2) + kz^2 (power_spectrum.py:477)
+__device__ __forceinline__ double s_exact(const double* __restrict__ t0, int f, double t1, double t2) {
+    return dadd_rn(dadd_rn(ldg(t0 + f), t1), t2);
+}
+
+// m = min{ f in [0, NX/2] : s(f) >= thr }, NX/2 + 1 if there is none.  A closed-form fp32 guess (the k grid is
+// uniform: kx^2 = f^2 * d) is verified -- and stepped, if it is off -- with the exact float64 values on both sides
+// of the boundary; whatever has not settled after a few steps is bisected.  Every lane searches its own edge.
+__device__ __forceinline__ int boundary_of(const double* __restrict__ t0, double t1, double t2, double thr, float inv_d) {
+    const double x = thr - (t1 + t2);
+    int g = 0;
+    if (x > 0.0) {
+        const float q = sqrtf((float)x * inv_d);
+        g = q < (float)(NX / 2 + 1) ? (int)ceilf(q) : NX / 2 + 1;     // (NaN compares false: NX/2 + 1)
+    }
+    bool done = false;
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+        if (!done) {
+            const bool hi_ok = g > NX / 2 || s_exact(t0, g, t1, t2) >= thr;
+            const bool lo_ok = g == 0 || s_exact(t0, g - 1, t1, t2) < thr;
+            if (!hi_ok) ++g; else if (!lo_ok) --g; else done = true;
+        }
+        if (__all_sync(0xffffffffu, done)) return g;
+    }
+    if (!done) {
+        int lo = 0, hi = NX / 2 + 1;
+#pragma unroll 1
+        for (int it = 0; it < 10; ++it) {
+            const int mid = (lo + hi) >> 1;
+            const bool ge = s_exact(t0, mid, t1, t2) >= thr;
+            if (lo < hi) { if (ge) hi = mid; else lo = mid + 1; }
+        }
+        g = lo;
+    }
+    return g;
+}
+
+template <class Hist>
+__device__ __forceinline__ void epilogue_shells(const Params& p, const cx<float>* v, int lane, int iy, int iz, float* stage,
+                                                WarpBinCache& c, Hist& hist) {
+    const t21_binspec& B = p.bins;
+    const int nk = B.nk;
+    const bool has_twin = (iz != 0) && (iz != p.nz - iz);
+    const unsigned wt = has_twin ? 2u : 1u;
+    const float wf = (float)wt;
+    constexpr unsigned kNone = 0xffffffffu;
+
+    // boundaries: lane e <= nk owns edge e
+    const float inv_d = 1.0f / (float)ldg(B.tab_s[0] + 1);               // 1 / (kx spacing)^2, for the boundary guess
+    const int mm = boundary_of(B.tab_s[0], ldg(B.tab_s[1] + iy), ldg(B.tab_s[2] + iz), ldg(B.thr + (lane <= nk ? lane : nk)), inv_d);
+    const int m = lane <= nk ? mm : (1 << 20);
+    const int n0 = __popc(__ballot_sync(0xffffffffu, m <= 0));           // edges at or below |kx| = 0: bin = n0 - 1
+    // distinct boundary positions inside the pencil, in order (warp-uniform)
+    const unsigned inb = (m >= 1 && m <= NX / 2) ? (unsigned)m : kNone;
+    const unsigned M1 = __reduce_min_sync(0xffffffffu, inb);
+    const unsigned M2 = __reduce_min_sync(0xffffffffu, (M1 != kNone && inb > M1) ? inb : kNone);
+    const unsigned M3 = __reduce_min_sync(0xffffffffu, (M2 != kNone && inb > M2) ? inb : kNone);
+
+    float pw[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) pw[k] = v[k].x * v[k].x + v[k].y * v[k].y;
+    if (iy == 0 && iz == 0 && lane == 0) {
+        // DC of (x - c) plus c*N: the only sample the mean offset changes.  It stays in the flow with power 0 (so
+        // that it is counted like any other mode); its true power goes to the histogram here, with count 0.
+        const double c0 = p.offset ? (double)ldg(p.offset) : 0.0;
+        const double ra = (double)v[0].x + c0 * p.ntot;
+        const double dc = ra * ra + (double)v[0].y * (double)v[0].y;
+        pw[0] = 0.f;
+        if (n0 >= 1 && n0 <= nk) hist.add(n0 - 1, dc, 0u);
+    }
+
+    if (M3 == kNone) {
+        // At most two boundaries cross the pencil (nearly always): three segments A | B | C of |kx|, summed in lane
+        // registers.  A step of 64 modes (|kx| in [32k, 32k + 32]) no boundary falls into goes to one segment as a
+        // whole (warp-uniform choice); in the one or two steps that hold a boundary every lane compares its own |kx|.
+        const int K1 = M1 != kNone ? (int)((M1 - 1u) >> 5) : 99, K2 = M2 != kNone ? (int)((M2 - 1u) >> 5) : 99;
+        float sA = 0.f, sB = 0.f, sC = 0.f;
+        unsigned cA = 0u, cB = 0u, cC = 0u;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (k != K1 && k != K2) {
+                const float pp = pw[k] + pw[31 - k];
+                if (k < K1) { sA += pp; cA += 2u; }
+                else if (k < K2) { sB += pp; cB += 2u; }
+                else { sC += pp; cC += 2u; }
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const unsigned f = h ? 32u * k + 32u - lane : 32u * k + lane;      // |kx| of this lane's mode
+                    const float pv = h ? pw[31 - k] : pw[k];
+                    if (f < M1) { sA += pv; cA += 1u; }
+                    else if (f < M2) { sB += pv; cB += 1u; }
+                    else { sC += pv; cC += 1u; }
+                }
+            }
+        }
+        if (n0 >= 1 && n0 <= nk) wbc_add_uniform(c, hist, n0 - 1, (double)(sA * wf), cA * wt);
+        if (M1 != kNone) {
+            const int n1 = __popc(__ballot_sync(0xffffffffu, m <= (int)M1));
+            if (n1 >= 1 && n1 <= nk) wbc_add_uniform(c, hist, n1 - 1, (double)(sB * wf), cB * wt);
+        }
+        if (M2 != kNone) {
+            const int n2 = __popc(__ballot_sync(0xffffffffu, m <= (int)M2));
+            if (n2 >= 1 && n2 <= nk) wbc_add_uniform(c, hist, n2 - 1, (double)(sC * wf), cC * wt);
+        }
+        return;
+    }
+
+    // Three or more boundaries (pencils close to the kx axis): the powers go through a warp-private strip of shared
+    // memory so that the walk is a rolled loop (an unrolled walk with its mixed-step branches was 50 000
+    // instructions and starved the instruction cache).
+    const unsigned mixed = __reduce_or_sync(0xffffffffu, inb != kNone ? 1u << ((inb - 1u) >> 5) : 0u);
+#pragma unroll
+    for (int q = 0; q < 32; ++q) stage[q * 32 + lane] = pw[q];
+    __syncwarp();
+    int nle = n0;
+    float run = 0.f;
+    unsigned runc = 0u;
+#pragma unroll 1
+    for (int k = 0; k <= 16; ++k) {
+        if (k < 16 && !((mixed >> k) & 1u)) {
+            run += stage[k * 32 + lane] + stage[(31 - k) * 32 + lane];
+            runc += 2u;
+            continue;
+        }
+        if (runc && nle >= 1 && nle <= nk) wbc_add_uniform(c, hist, nle - 1, (double)(run * wf), runc * wt);
+        run = 0.f; runc = 0u;
+        if (k == 16) break;
+        const int nhi = __popc(__ballot_sync(0xffffffffu, m <= 32 * k + 32));
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const int kk = h ? 31 - k : k;
+            const int f = h ? 32 * k + 32 - lane : 32 * k + lane;
+            int ne = nle;
+            for (int e = nle; e < nhi; ++e) ne += f >= __shfl_sync(0xffffffffu, m, e) ? 1 : 0;
+            wbc_add(c, hist, (ne >= 1 && ne <= nk) ? ne - 1 : -1, (double)(stage[kk * 32 + lane] * wf), wt);
+        }
+        nle = nhi;
+    }
+    __syncwarp();
+}
+
+template <int MU, class Hist>
+__device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& p, unsigned char* smem_raw, Hist& hist, int nbins) {
+    cx<float>* buf = reinterpret_cast<cx<float>*>(smem_raw);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + BAR_OFF);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int zl0 = tid & (WZ - 1), j0 = tid >> 3;          // stage 0: lanes across the columns
+
+    Accs<MU> accs;
+    WarpBinCache wbc;
+    if constexpr (MU == 0) wbc_init(wbc);
+    else {
+#pragma unroll
+        for (int c = 0; c < (MU == 2 ? 2 : 1); ++c) acc_init(accs.a[c]);
+    }
+
+    auto issue = [&](long long tile) {
+        const unsigned chunk = (unsigned)tile / (unsigned)p.ny;
+        const int iy_loc = (int)((unsigned)tile - chunk * (unsigned)p.ny);
+        mbar_expect_tx(bar, NX * WZ * 8);
+        for (int x = 0; x < NX; x += p.box_rows)
+            tma_load_5d(smem_raw + (size_t)x * (WZ * 8), map, bar, 0, iy_loc, x & ((1 << p.xs_log2) - 1), (int)chunk, x >> p.xs_log2);
+    };
+
+    // Tiles are dealt to the CTAs in batches of kBatch consecutive tiles (ky runs fastest): consecutive pencils of a
+    // warp then cross nearly the same bins, so the warp's cached bins survive from one pencil to the next, while the
+    // expensive tiles (pencils near the kx axis cross many bin edges) are spread over all CTAs.  (One contiguous
+    // range per CTA left the SMs idle 41 % of the time: profiles/r02_x32_imbalance.txt.)
+    constexpr int kBatch = 8;
+    auto tile_at = [&](long long i) { return ((i / kBatch) * gridDim.x + blockIdx.x) * kBatch + (i % kBatch); };
+    long long it = 0;
+    long long tile = tile_at(0);
+    if (tid == 0 && tile < p.ntiles) issue(tile);
+    unsigned parity = 0;
+    for (; tile < p.ntiles; tile = tile_at(++it)) {
+        const unsigned chunk = (unsigned)tile / (unsigned)p.ny;
+        const int iy = (int)((unsigned)tile - chunk * (unsigned)p.ny) + p.iy0;
+        cx<float> v[32];
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        // stage 0: rows j0 + 32 k of column zl0 from the landed [x][8] tile
+        stage_load<P, 0>(v, j0, [&](int i) { return buf[i * WZ + zl0]; });
+        DFT<32, float>::run(v);
+        __syncthreads();                                   // every thread has its inputs: the tile may be overwritten
+        {
+            cx<float>* dst = buf + zl0 * PITCH + 33 * j0;  // outputs 32 j0 + k, padded
+#pragma unroll
+            for (int k = 0; k < 32; ++k) dst[k] = v[k];
+        }
+        __syncthreads();
+        // stage 1: warp = pencil, lane = butterfly; inputs lane + 32 k
+        {
+            const cx<float>* src = buf + warp * PITCH + lane;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = src[33 * k];
+        }
+        // The buffer is free once every warp has its inputs: only the issuing warp waits for that (bar.sync), the
+        // others just say so (bar.arrive) and go on; the next tile lands under the rest of this one.
+        fence_proxy_async();                               // (generic-proxy accesses above, async-proxy writes below)
+        if (warp == 0) {
+            named_sync(1, THREADS);
+            const long long next = tile_at(it + 1);
+            if (lane == 0 && next < p.ntiles) issue(next);
+        } else {
+            named_arrive(1, THREADS);
+        }
+#pragma unroll
+        for (int k = 1; k < 32; ++k) v[k] = cmul(v[k], ldg(p.tw + (k - 1) * 32 + lane));
+        DFT<32, float>::run(v);                            // v[k] = X[lane + 32 k]
+        const int iz = (int)chunk * WZ + warp;
+        if (iz < p.nzh) {
+            if constexpr (MU == 0) epilogue_shells(p, v, lane, iy, iz, reinterpret_cast<float*>(smem_raw + STAGE_OFF) + warp * 1024, wbc, hist);
+            else epilogue<MU>(p, v, lane, iy, iz, accs, hist);
+        }
+    }
+    if constexpr (MU == 0) wbc_flush(wbc, hist);
+    else {
+#pragma unroll
+        for (int c = 0; c < (MU == 2 ? 2 : 1); ++c) acc_flush(accs.a[c], hist, nbins);
+    }
+}
+
+#endif  // T21_DEVICE_CODE
+
+// HK = 0: histogram in shared memory (per-warp copies when small), HK = 1: global atomics
+template <int MU, int HK>
+__global__ void __launch_bounds__(THREADS, 2)
+xpass32_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ Params p, int nbins, int warp_private,
+               double* __restrict__ part_sum, unsigned* __restrict__ part_cnt, double* gsum, unsigned long long* gcnt) {
+#if T21_DEVICE_CODE
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(smem_raw + BAR_OFF, 1);
+        mbar_init_fence();
+    }
+    if constexpr (HK == 0) {
+        constexpr int NW = THREADS / 32;
+        const int copies = warp_private ? NW : 1;
+        double* hs = reinterpret_cast<double*>(smem_raw + HIST_OFF);
+        unsigned* hc = reinterpret_cast<unsigned*>(hs + (size_t)copies * nbins);
+        for (int b = tid; b < copies * nbins; b += THREADS) { hs[b] = 0.0; hc[b] = 0u; }
+        __syncthreads();
+        if (warp_private) {
+            WarpPrivHist hist{hs + (size_t)(tid >> 5) * nbins, hc + (size_t)(tid >> 5) * nbins};
+            run_tiles<MU>(&map, p, smem_raw, hist, nbins);
+        } else {
+            SmemHist hist{hs, hc};
+            run_tiles<MU>(&map, p, smem_raw, hist, nbins);
+        }
+        __syncthreads();
+        for (int b = tid; b < nbins; b += THREADS) {
+            double s = 0.0;
+            unsigned c = 0;
+            for (int w = 0; w < copies; ++w) { s += hs[(size_t)w * nbins + b]; c += hc[(size_t)w * nbins + b]; }
+            part_sum[(size_t)blockIdx.x * nbins + b] = s;
+            part_cnt[(size_t)blockIdx.x * nbins + b] = c;
+        }
+    } else {
+        __syncthreads();
+        GlobalHist hist{gsum, gcnt};
+        run_tiles<MU>(&map, p, smem_raw, hist, nbins);
+    }
+#endif
+}
+
+template <int MU>
+static int launch(XArgs& a, cudaStream_t st) {
+    Params p;
+    memset(&p, 0, sizeof(p));
+    p.ny = a.ny; p.nz = a.nz; p.nzh = a.nzh; p.iy0 = a.iy0;
+    p.nchunks = (a.nzh + WZ - 1) / WZ;
+    p.ntiles = (long long)a.ny * p.nchunks;
+    p.xs_log2 = a.xs_log2 >= 0 ? a.xs_log2 : 10;
+    const int nxs = 1 << p.xs_log2;
+    p.box_rows = nxs < 256 ? nxs : 256;
+    p.tw = (const cx<float>*)a.tw32;
+    p.offset = (const float*)a.offset[0];
+    p.ntot = a.ntot;
+    p.bins = *a.bins;
+    CUtensorMap map;
+    if (int rc = make_wmap_f32(&map, a.w[0], nxs, a.ny, a.pitch / WZ, NX / nxs, p.box_rows)) return rc;
+
+    const int hk = a.hist_global ? 1 : 0;
+    constexpr int NW = THREADS / 32;
+    const int warp_private = (hk == 0 && (size_t)NW * a.nbins * 12 <= 16 * 1024) ? 1 : 0;
+    size_t smem = HIST_OFF;
+    if (hk == 0) smem += (size_t)(warp_private ? NW : 1) * a.nbins * 12;
+    int occ = 0, grid = 0;
+#define T21_LAUNCH32(HKV)                                                                                     \
+    {                                                                                                         \
+        auto kern = xpass32_kernel<MU, HKV>;                                                                  \
+        if (int rc = ensure_smem(kern, smem)) return rc;                                                      \
+        T21_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));                \
+        if (occ < 1) { set_error("x pass (warp per pencil) does not fit on an SM (smem %zu)", smem); return T21_EINVAL; } \
+        long long g = (long long)occ * device_sm_count();                                                     \
+        if (g > p.ntiles) g = p.ntiles;                                                                       \
+        if (HKV == 0 && g > a.max_grid) g = a.max_grid;                                                       \
+        grid = (int)g;                                                                                        \
+        kern<<<grid, THREADS, smem, st>>>(map, p, a.nbins, warp_private, a.part_sum, a.part_cnt, a.gsum, a.gcnt); \
+    }
+    if (hk == 0) T21_LAUNCH32(0) else T21_LAUNCH32(1)
+#undef T21_LAUNCH32
+    count_launch();
+    T21_CUDA_OK(cudaGetLastError());
+    a.grid_used = grid;
+    return 0;
+}
+
+}  // namespace x32
+
+bool xpass32_applicable(int dtype, const XArgs& a) {
+    // shells only for now, one lane per bin edge; everything else keeps the CTA-per-tile kernel
+    return dtype == T21_F32 && a.nx == x32::NX && a.nf == 1 && a.bins != nullptr && a.tw32 != nullptr && a.pitch % x32::WZ == 0 &&
+           a.bins->nmu == 0 && a.bins->nk <= 31;
+}
+
+int launch_xpass32_bin(XArgs& a, cudaStream_t st) {
+    const int mu = a.bins->nmu > 0 ? (a.bins->absolute_mus ? 1 : 2) : 0;
+    return mu == 0 ? x32::launch<0>(a, st) : (mu == 1 ? x32::launch<1>(a, st) : x32::launch<2>(a, st));
+}
+
+}  // namespace t21

@@ -122,6 +122,33 @@ def test_long_pencils_against_oracle(t2c, shape, dtype):
     assert np.abs(nd - nd_o).max() <= tol * nd_o.max()
 
 
+@pytest.mark.parametrize("shape", [(1024, 16, 32), (1024, 32, 16)])
+@pytest.mark.parametrize("los", [0, 1, 2])
+@pytest.mark.parametrize("absmu", [True, False])
+def test_warp_per_pencil_x_pass_mu_modes_against_oracle(t2c, shape, los, absmu):
+    """nx = 1024 fp32 takes the warp-per-pencil X pass (t21_xpass32.cu): every line of sight, |mu| and signed mu
+    (twins binned separately), the excluded k_perp = 0 line, against the oracle; kx runs over the full 1024 samples."""
+    from oracle import ps_oracle
+    rng = np.random.default_rng(7 + los)
+    x = (rng.standard_normal(shape) + 3.0).astype(np.float32)
+    box = [300.0, 40.0, 60.0]
+    for excl in (True, False):
+        kw = dict(los_axis=los, mubins=6, kbins=7, box_dims=box, return_n_modes=True, absolute_mus=absmu, exclude_zero_modes=excl)
+        pm, _, _, nmu = t2c.power_spectrum_mu(x, **kw)
+        pm_o, _, _, nmu_o = ps_oracle.power_spectrum_mu(x, **kw)
+        assert np.array_equal(nmu, nmu_o)
+        np.testing.assert_allclose(pm, pm_o, rtol=1e-5, equal_nan=True)
+    ps, ks, nm = t2c.power_spectrum_1d(x, kbins=31, box_dims=box, return_n_modes=True)          # 32 edges: one per lane
+    ps_o, ks_o, nm_o = ps_oracle.power_spectrum_1d(x, kbins=31, box_dims=box, return_n_modes=True)
+    assert np.array_equal(nm, nm_o)
+    np.testing.assert_allclose(ps, ps_o, rtol=1e-5, equal_nan=True)
+    e = np.array([0.0, 0.05, 0.3, 0.31, 0.31, 2.0, 9.0])                                           # zero edge, empty bin
+    ps, ks, nm = t2c.power_spectrum_1d(x, kbins=e, box_dims=box, return_n_modes=True)
+    ps_o, ks_o, nm_o = ps_oracle.power_spectrum_1d(x, kbins=e, box_dims=box, return_n_modes=True)
+    assert np.array_equal(nm, nm_o)
+    np.testing.assert_allclose(ps, ps_o, rtol=1e-5, equal_nan=True)
+
+
 @pytest.mark.parametrize("shape", [(64, 64), (45, 64), (100,)])
 def test_low_dimensional_inputs_against_oracle(t2c, shape):
     from oracle import ps_oracle

@@ -48,152 +48,7 @@ struct Params {
     t21_binspec bins;
 };
 
-#if T21_DEVICE_CODE   // (WarpBins has its device members only in the device pass)
-
-template <int MU>
-struct Accs {
-    WarpBins<(MU != 0)> a[MU == 2 ? 2 : 1];
-};
-
-// exact bin of one mode for accumulator `which` (see XPass::exact_bin)
-__device__ __forceinline__ int exact_bin(const t21_binspec& B, int ix, int iy, int iz, bool has_twin, int which, float sh, int& weight) {
-    const ModeBins mb = classify(B, ix, iy, iz, has_twin);
-    int bin = which == 0 ? mb.own : mb.twin;
-    weight = which == 0 ? mb.own_w : 1;
-    if (bin < 0) {
-        const int nb = B.nk * (B.nmu > 0 ? B.nmu : 1);
-        weight = 1;
-        if (sh < ldg(B.k_hi_f + B.nk)) bin = nb;
-        else if (sh >= ldg(B.k_lo_f + B.nk + 1)) bin = nb + 1;
-    }
-    return bin;
-}
-
-template <int MU, class Hist>
-__device__ __forceinline__ void epilogue(const Params& p, const cx<float>* v, int lane, int iy, int iz, Accs<MU>& accs, Hist& hist) {
-    const t21_binspec& B = p.bins;
-    const bool has_twin = (iz != 0) && (iz != p.nz - iz);
-    const int nb = B.nk * (MU ? B.nmu : 1);
-    const float* sfx = B.tab_sf[0];
-    const float c_yz = ldg(B.tab_sf[1] + iy) + ldg(B.tab_sf[2] + iz);
-    const unsigned wt = (has_twin && MU != 2) ? 2u : 1u;
-    const float wf = (float)wt;
-
-    float pw[32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) pw[k] = v[k].x * v[k].x + v[k].y * v[k].y;
-    if (iy == 0 && iz == 0 && lane == 0) {
-        // DC of (x - c) plus c*N: the only sample the mean offset changes.  It stays in the flow with power 0 (so
-        // that it is counted like any other mode); its true power goes to the histogram here, with count 0.
-        const double c0 = p.offset ? (double)ldg(p.offset) : 0.0;
-        const double ra = (double)v[0].x + c0 * p.ntot;
-        const double dc = ra * ra + (double)v[0].y * (double)v[0].y;
-        pw[0] = 0.f;
-        const ModeBins mb = classify(B, 0, 0, 0, false);
-        if (mb.own >= 0) hist.add(mb.own, dc, 0u);
-    }
-
-    unsigned slow0 = 0u, slow1 = 0u;     // steps that need the exact classification (warp-uniform masks)
-    if constexpr (MU == 0) {
-        WarpBins<false>& acc = accs.a[0];
-        // the whole pencil inside one cached interval?  s^ grows with |kx| (fp32 addition is monotonic)
-        const float t_lo = c_yz + ldg(sfx), t_hi = c_yz + ldg(sfx + NX / 2);
-        const bool w0 = t_lo >= acc.slo[0] && t_hi < acc.shi[0];
-        const bool w1 = t_lo >= acc.slo[1] && t_hi < acc.shi[1];
-        if (w0 || w1) {
-            float g[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                g[q] = ((pw[8 * q] + pw[8 * q + 1]) + (pw[8 * q + 2] + pw[8 * q + 3])) +
-                       ((pw[8 * q + 4] + pw[8 * q + 5]) + (pw[8 * q + 6] + pw[8 * q + 7]));
-            const double d = ((double)(g[0] * wf) + (double)(g[1] * wf)) + ((double)(g[2] * wf) + (double)(g[3] * wf));
-            if (w0) { acc.sum[0] += d; acc.cnt[0] += 32u * wt; }
-            else { acc.sum[1] += d; acc.cnt[1] += 32u * wt; }
-            return;
-        }
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            // steps k (kx = 32k + l) and 31-k (kx - NX = -(32k + 32 - l)) cover |kx| in [32k, 32k + 32]
-            const float a_lo = c_yz + ldg(sfx + 32 * k), a_hi = c_yz + ldg(sfx + 32 * k + 32);
-            const bool u0 = a_lo >= acc.slo[0] && a_hi < acc.shi[0];
-            const bool u1 = a_lo >= acc.slo[1] && a_hi < acc.shi[1];
-            if (u0 || u1) {
-                const double d = (double)((pw[k] + pw[31 - k]) * wf);
-                if (u0) { acc.sum[0] += d; acc.cnt[0] += 2u * wt; }
-                else { acc.sum[1] += d; acc.cnt[1] += 2u * wt; }
-            } else {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int kk = h ? 31 - k : k;
-                    const float sh = ldg(sfx + lane + 32 * kk) + c_yz;
-                    if (!warpbins_fast<false>(acc, sh, 0.f, (double)(pw[kk] * wf), wt, true)) slow0 |= 1u << kk;
-                }
-            }
-        }
-    } else {
-        const int los = B.los_axis;
-        const int zx = B.zero_idx[0], nyx = B.nyq_idx[0];
-        // k_perp = 0 line (power_spectrum.py:563-575): the part of the test that is fixed for this pencil
-        bool line_fixed = false;
-        if (B.exclude_zero)
-            line_fixed = los == 0 ? (iy == B.zero_idx[1] && iz == B.zero_idx[2])
-                                  : (los == 1 ? iz == B.zero_idx[2] : iy == B.zero_idx[1]);
-        float klos_c = 0.f;
-        bool nyq_c = false;
-        if (los != 0) {
-            const int il = los == 1 ? iy : iz;
-            klos_c = ldg(B.tab_losf + il);
-            nyq_c = il == B.nyq_idx[los];
-        }
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            const int ix = lane + 32 * k;
-            const bool valid = !(line_fixed && (los == 0 || ix == zx));
-            const float sh = ldg(sfx + ix) + c_yz;
-            const float muh = (los == 0 ? ldg(B.tab_losf + ix) : klos_c) * fast_rsqrt(sh);
-            const float m_own = MU == 1 ? fabsf(muh) : muh;
-            if (!warpbins_fast<true>(accs.a[0], sh, m_own, (double)(pw[k] * wf), wt, valid)) slow0 |= 1u << k;
-            if constexpr (MU == 2) {                      // the twin goes to the mirrored mu bin
-                const bool nyq = los == 0 ? ix == nyx : nyq_c;
-                if (!warpbins_fast<true>(accs.a[1], sh, nyq ? muh : -muh, (double)pw[k], 1u, valid && has_twin)) slow1 |= 1u << k;
-            }
-        }
-    }
-    if ((slow0 | slow1) == 0u) return;
-
-    // rare: some lane sits in a guard band or in a bin that is not cached.  The powers go through a local array
-    // so that this loop is rolled (one copy of the exact path in the code).
-    float spill[32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) spill[k] = pw[k];
-    const int los = MU ? B.los_axis : -1;
-    bool line_fixed = false;
-    if (MU && B.exclude_zero)
-        line_fixed = los == 0 ? (iy == B.zero_idx[1] && iz == B.zero_idx[2])
-                              : (los == 1 ? iz == B.zero_idx[2] : iy == B.zero_idx[1]);
-#pragma unroll 1
-    for (unsigned todo = slow0 | slow1; todo; todo &= todo - 1) {
-        const int k = __ffs(todo) - 1;
-        const int ix = lane + 32 * k;
-        const float pk = spill[k];
-        const float sh = ldg(sfx + ix) + c_yz;
-        bool valid = true;
-        if (MU) valid = !(line_fixed && (los == 0 || ix == B.zero_idx[0]));
-        if ((slow0 >> k) & 1u) {
-            int w1 = 1;
-            const int bin = valid ? exact_bin(B, ix, iy, iz, has_twin, 0, sh, w1) : -1;
-            warpbins_slow(accs.a[0], hist, B, nb, bin, w1 == (int)wt ? (double)(pk * wf) : (double)pk, (unsigned)w1, valid);
-        }
-        if constexpr (MU == 2) {
-            if ((slow1 >> k) & 1u) {
-                const bool tv = valid && has_twin;
-                int w1 = 1;
-                const int bin = tv ? exact_bin(B, ix, iy, iz, has_twin, 1, sh, w1) : -1;
-                warpbins_slow(accs.a[1], hist, B, nb, bin, (double)pk, 1u, tv);
-            }
-        }
-    }
-}
+#if T21_DEVICE_CODE
 
 // ---- shells (MU = 0): exact bin boundaries along the pencil -----------------------------------------------
 // Along a pencil s = (kx^2 + ky^2) + kz^2 only grows with |kx| (rounding is monotonic), so bin b is the index range
@@ -358,20 +213,15 @@ __device__ __forceinline__ void epilogue_shells(const Params& p, const cx<float>
     __syncwarp();
 }
 
-template <int MU, class Hist>
+template <class Hist>
 __device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& p, unsigned char* smem_raw, Hist& hist, int nbins) {
     cx<float>* buf = reinterpret_cast<cx<float>*>(smem_raw);
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + BAR_OFF);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int zl0 = tid & (WZ - 1), j0 = tid >> 3;          // stage 0: lanes across the columns
 
-    Accs<MU> accs;
     WarpBinCache wbc;
-    if constexpr (MU == 0) wbc_init(wbc);
-    else {
-#pragma unroll
-        for (int c = 0; c < (MU == 2 ? 2 : 1); ++c) acc_init(accs.a[c]);
-    }
+    wbc_init(wbc);
 
     auto issue = [&](long long tile) {
         const unsigned chunk = (unsigned)tile / (unsigned)p.ny;
@@ -427,25 +277,19 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& 
         for (int k = 1; k < 32; ++k) v[k] = cmul(v[k], ldg(p.tw + (k - 1) * 32 + lane));
         DFT<32, float>::run(v);                            // v[k] = X[lane + 32 k]
         const int iz = (int)chunk * WZ + warp;
-        if (iz < p.nzh) {
-            if constexpr (MU == 0) epilogue_shells(p, v, lane, iy, iz, reinterpret_cast<float*>(smem_raw + STAGE_OFF) + warp * 1024, wbc, hist);
-            else epilogue<MU>(p, v, lane, iy, iz, accs, hist);
-        }
+        if (iz < p.nzh) epilogue_shells(p, v, lane, iy, iz, reinterpret_cast<float*>(smem_raw + STAGE_OFF) + warp * 1024, wbc, hist);
     }
-    if constexpr (MU == 0) wbc_flush(wbc, hist);
-    else {
-#pragma unroll
-        for (int c = 0; c < (MU == 2 ? 2 : 1); ++c) acc_flush(accs.a[c], hist, nbins);
-    }
+    wbc_flush(wbc, hist);
 }
 
 #endif  // T21_DEVICE_CODE
 
-// HK = 0: histogram in shared memory (per-warp copies when small), HK = 1: global atomics
-template <int MU, int HK>
+// The histogram (at most 31 bins) lives in shared memory, one copy per warp: only lane 0 of the owning warp writes
+// it, in program order; warps are summed in order here and CTAs in order by reduce_partials_kernel, so the result
+// is bit-reproducible run to run.
 __global__ void __launch_bounds__(THREADS, 2)
-xpass32_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ Params p, int nbins, int warp_private,
-               double* __restrict__ part_sum, unsigned* __restrict__ part_cnt, double* gsum, unsigned long long* gcnt) {
+xpass32_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ Params p, int nbins,
+               double* __restrict__ part_sum, unsigned* __restrict__ part_cnt) {
 #if T21_DEVICE_CODE
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int tid = threadIdx.x;
@@ -453,37 +297,24 @@ xpass32_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ 
         mbar_init(smem_raw + BAR_OFF, 1);
         mbar_init_fence();
     }
-    if constexpr (HK == 0) {
-        constexpr int NW = THREADS / 32;
-        const int copies = warp_private ? NW : 1;
-        double* hs = reinterpret_cast<double*>(smem_raw + HIST_OFF);
-        unsigned* hc = reinterpret_cast<unsigned*>(hs + (size_t)copies * nbins);
-        for (int b = tid; b < copies * nbins; b += THREADS) { hs[b] = 0.0; hc[b] = 0u; }
-        __syncthreads();
-        if (warp_private) {
-            WarpPrivHist hist{hs + (size_t)(tid >> 5) * nbins, hc + (size_t)(tid >> 5) * nbins};
-            run_tiles<MU>(&map, p, smem_raw, hist, nbins);
-        } else {
-            SmemHist hist{hs, hc};
-            run_tiles<MU>(&map, p, smem_raw, hist, nbins);
-        }
-        __syncthreads();
-        for (int b = tid; b < nbins; b += THREADS) {
-            double s = 0.0;
-            unsigned c = 0;
-            for (int w = 0; w < copies; ++w) { s += hs[(size_t)w * nbins + b]; c += hc[(size_t)w * nbins + b]; }
-            part_sum[(size_t)blockIdx.x * nbins + b] = s;
-            part_cnt[(size_t)blockIdx.x * nbins + b] = c;
-        }
-    } else {
-        __syncthreads();
-        GlobalHist hist{gsum, gcnt};
-        run_tiles<MU>(&map, p, smem_raw, hist, nbins);
+    constexpr int NW = THREADS / 32;
+    double* hs = reinterpret_cast<double*>(smem_raw + HIST_OFF);
+    unsigned* hc = reinterpret_cast<unsigned*>(hs + (size_t)NW * nbins);
+    for (int b = tid; b < NW * nbins; b += THREADS) { hs[b] = 0.0; hc[b] = 0u; }
+    __syncthreads();
+    WarpPrivHist hist{hs + (size_t)(tid >> 5) * nbins, hc + (size_t)(tid >> 5) * nbins};
+    run_tiles(&map, p, smem_raw, hist, nbins);
+    __syncthreads();
+    for (int b = tid; b < nbins; b += THREADS) {
+        double s = 0.0;
+        unsigned c = 0;
+        for (int w = 0; w < NW; ++w) { s += hs[(size_t)w * nbins + b]; c += hc[(size_t)w * nbins + b]; }
+        part_sum[(size_t)blockIdx.x * nbins + b] = s;
+        part_cnt[(size_t)blockIdx.x * nbins + b] = c;
     }
 #endif
 }
 
-template <int MU>
 static int launch(XArgs& a, cudaStream_t st) {
     Params p;
     memset(&p, 0, sizeof(p));
@@ -500,43 +331,35 @@ static int launch(XArgs& a, cudaStream_t st) {
     CUtensorMap map;
     if (int rc = make_wmap_f32(&map, a.w[0], nxs, a.ny, a.pitch / WZ, NX / nxs, p.box_rows)) return rc;
 
-    const int hk = a.hist_global ? 1 : 0;
-    constexpr int NW = THREADS / 32;
-    const int warp_private = (hk == 0 && (size_t)NW * a.nbins * 12 <= 16 * 1024) ? 1 : 0;
-    size_t smem = HIST_OFF;
-    if (hk == 0) smem += (size_t)(warp_private ? NW : 1) * a.nbins * 12;
-    int occ = 0, grid = 0;
-#define T21_LAUNCH32(HKV)                                                                                     \
-    {                                                                                                         \
-        auto kern = xpass32_kernel<MU, HKV>;                                                                  \
-        if (int rc = ensure_smem(kern, smem)) return rc;                                                      \
-        T21_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));                \
-        if (occ < 1) { set_error("x pass (warp per pencil) does not fit on an SM (smem %zu)", smem); return T21_EINVAL; } \
-        long long g = (long long)occ * device_sm_count();                                                     \
-        if (g > p.ntiles) g = p.ntiles;                                                                       \
-        if (HKV == 0 && g > a.max_grid) g = a.max_grid;                                                       \
-        grid = (int)g;                                                                                        \
-        kern<<<grid, THREADS, smem, st>>>(map, p, a.nbins, warp_private, a.part_sum, a.part_cnt, a.gsum, a.gcnt); \
-    }
-    if (hk == 0) T21_LAUNCH32(0) else T21_LAUNCH32(1)
-#undef T21_LAUNCH32
+    const size_t smem = HIST_OFF + (size_t)(THREADS / 32) * a.nbins * 12;
+    auto kern = xpass32_kernel;
+    if (int rc = ensure_smem(kern, smem)) return rc;
+    int occ = 0;
+    T21_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+    if (occ < 1) { set_error("x pass (warp per pencil) does not fit on an SM (smem %zu)", smem); return T21_EINVAL; }
+    long long g = (long long)occ * device_sm_count();
+    if (g > p.ntiles) g = p.ntiles;
+    if (g > a.max_grid) g = a.max_grid;
+    kern<<<(int)g, THREADS, smem, st>>>(map, p, a.nbins, a.part_sum, a.part_cnt);
     count_launch();
     T21_CUDA_OK(cudaGetLastError());
-    a.grid_used = grid;
+    a.grid_used = (int)g;
     return 0;
 }
 
 }  // namespace x32
 
 bool xpass32_applicable(int dtype, const XArgs& a) {
-    // shells only for now, one lane per bin edge; everything else keeps the CTA-per-tile kernel
+    // One field, spherical shells, one lane per bin edge; everything else keeps the CTA-per-tile kernel.  ((k, mu)
+    // bins were tried here with the guard-interval cache of XPass: a warp that walks a whole pencil crosses ~7
+    // (k, mu) bins per pencil and a two-entry cache thrashes -- 9.1 ms against 6.0 ms at 1024^3; it needs the
+    // boundary form with host-built mu thresholds, which is not written.)
     return dtype == T21_F32 && a.nx == x32::NX && a.nf == 1 && a.bins != nullptr && a.tw32 != nullptr && a.pitch % x32::WZ == 0 &&
-           a.bins->nmu == 0 && a.bins->nk <= 31;
+           a.bins->nmu == 0 && a.bins->nk <= 31 && !a.hist_global;
 }
 
 int launch_xpass32_bin(XArgs& a, cudaStream_t st) {
-    const int mu = a.bins->nmu > 0 ? (a.bins->absolute_mus ? 1 : 2) : 0;
-    return mu == 0 ? x32::launch<0>(a, st) : (mu == 1 ? x32::launch<1>(a, st) : x32::launch<2>(a, st));
+    return x32::launch(a, st);
 }
 
 }  // namespace t21

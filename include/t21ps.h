@@ -124,6 +124,8 @@ T21_API int t21_ps_nd(const t21_plan* plan, const void* x1, const void* x2_or_nu
  * the X pass fused with the binning for rows iy0 .. iy0+ny/P of the global cube; the caller
  * all-reduces sums_out / counts_out.  t21_workspace_bytes(plan, 0, nbins) sizes stage2's workspace. */
 T21_API int t21_slab_pitch(const t21_plan* plan);
+/* row length (elements) of the half-spectrum power arrays of t21_ps_half / t21_slab_stage2_nd: nz/2+1 rounded up to 8 */
+T21_API int t21_half_pitch(const t21_plan* plan);
 T21_API int t21_slab_stage1(const t21_plan* plan_slab, const void* x_slab, const void* offset_or_null,
                             void* w_out, void* send_out_or_null, int nranks, void* stream);
 /* stage 1 with the re-partition FUSED into the Y pass: every transformed row is stored straight into the
@@ -146,7 +148,7 @@ T21_API int t21_slab_stage2(const t21_plan* plan_cols, const void* w1, const voi
                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* power_spectrum_nd / cross_power_spectrum_nd of a slab-sharded cube: the scaled power of this rank's
- * rows as the computed HALF spectrum in FFT order, out_half[nx][ny/P][nz/2+1].  The caller assembles
+ * rows as the computed HALF spectrum in FFT order, out_half[nx][ny/P][t21_half_pitch(plan)].  The caller assembles
  * the fftshifted rows: the kz < 0 half of row ky is the mirrored half of row -ky, held by another rank. */
 T21_API int t21_slab_stage2_nd(const t21_plan* plan_cols, const void* w1, const void* w2_or_null, int n_xslabs,
                                int iy0, int ny_global, const void* offset1, const void* offset2, double scale,
@@ -172,6 +174,26 @@ T21_API int t21_bin_cyl(const void* p_shifted, int dtype, int n0, int n1, int n2
                         const int* perp_tab, const int* par_tab, int nperp, int npar, double* sums_out,
                         long long* counts_out, void* workspace, size_t workspace_bytes, void* stream);
 T21_API size_t t21_bin_cyl_workspace_bytes(int nperp, int npar);
+
+/* The scaled power of the computed HALF spectrum only, FFT order: out_half[nx][ny][t21_half_pitch(plan)] (columns >= nz/2+1 are padding; a quarter of the bytes
+ * of the full float64 array of t21_ps_nd, no Hermitian-twin stores).  It feeds the estimators whose bins are not
+ * (k, mu) boxes, so that power_spectrum_2d (power_spectrum.py:177-254) and power_spectrum_multipoles
+ * (power_legendre.py:4-90) never materialise the fftshifted float64 cube the reference builds (:45-46). */
+T21_API int t21_ps_half(const t21_plan* plan, const void* x1, const void* x2_or_null, int subtract_mean, double scale,
+                        void* out_half, int out_dtype, void* workspace, size_t workspace_bytes, void* stream);
+/* t21_bin_cyl on that half spectrum (rows of `row_pitch` elements): perp_tab / par_tab in FFT index order and over
+ * the full axes; a mode whose Hermitian twin is not stored stands for both (weight 2).  sums_out only: the mode
+ * counts of separable bins are a product of two table histograms and are formed on the host. */
+T21_API int t21_bin_cyl_half(const void* p_half, int dtype, int nx, int ny, int nz, int row_pitch, int nu_axis,
+                             const int* perp_tab, const int* par_tab, int nperp, int npar, double* sums_out,
+                             void* workspace, size_t workspace_bytes, void* stream);
+/* power_spectrum_multipoles (power_legendre.py:55-87): per k bin of `spec` (shells, FFT order, half-open last bin,
+ * tab_los / tab_losf filled for los_axis) sums_out[nk][5] = sum P, sum P L2, sum P L4, sum L2^2, sum L4^2 over the
+ * modes of the bin (twins included) and counts_out[nk] = number of modes. */
+T21_API int t21_bin_multipoles_half(const void* p_half, int dtype, int row_pitch, const t21_binspec* spec, int los_axis,
+                                    int exclude_zero, double* sums_out, long long* counts_out, void* workspace,
+                                    size_t workspace_bytes, void* stream);
+T21_API size_t t21_bin_multipoles_workspace_bytes(int nk);
 
 T21_API const char* t21_last_error(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */

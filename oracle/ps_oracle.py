@@ -330,3 +330,40 @@ def dimensionless_ps(data, kbins=100, box_dims=None, binning="log", factor=10):
     else:
         knew = np.linspace(ks[1], ks[-1], kbins)
     return f(knew), knew
+
+
+def power_spectrum_multipoles(input_array, kbins=10, box_dims=None, los_axis=0,
+                              output=['P0', 'P2', 'P4', 'nmodes'], exclude_zero_modes=False):
+    """Reference ``power_legendre.py:4-90`` with the two lines that stop it from running repaired and nothing else:
+    ``_get_mu`` gets its fourth argument (``:47`` passes three; only even powers of mu are used, so
+    ``absolute_mus`` is immaterial) and the all-pass mask of ``exclude_zero_modes=False`` is boolean (``:51`` builds a
+    float array, which ``idx *= good_idx`` at ``:79`` cannot cast).  ``nmodes`` stays ``len(np.nonzero(idx))``
+    (``:80``): the number of dimensions, as the reference returns it; the mode count is added as ``n_modes``."""
+    assert (los_axis >= 0 and los_axis <= len(input_array.shape))
+    box_dims = box_lengths(box_dims, input_array.shape)
+    ps = power_spectrum_nd(input_array, box_dims)
+    kc, k = k_magnitude(input_array.shape, box_dims)
+    edges = k_edges(kbins, box_dims, k.max())                       # binning='log' default of _get_kbins (:45)
+    dk = (edges[1:] - edges[:-1]) / 2.
+    mu = mu_of(kc, k, los_axis, True)
+    good_idx = kperp_nonzero(ps.shape, los_axis) if exclude_zero_modes else np.ones(ps.shape, dtype=bool)
+    P2 = 0.5 * (3. * mu ** 2 - 1.)
+    P4 = 4.375 * (mu ** 2 - 0.115587) * (mu ** 2 - 0.741556)
+    n_kbins = len(edges) - 1
+    multipoles = {key: np.zeros(n_kbins) for key in ('P0', 'P2', 'P4') if key in output}
+    nmodes = np.zeros(n_kbins)
+    count = np.zeros(n_kbins)
+    for i in range(n_kbins):
+        idx = (k >= edges[i]) & (k < edges[i + 1])
+        idx = idx * good_idx
+        nmodes[i] = len(np.nonzero(idx))
+        count[i] = np.count_nonzero(idx)
+        if 'P0' in output:
+            multipoles['P0'][i] = np.sum(ps[idx]) / np.sum(np.ones_like(mu)[idx] ** 2)
+        if 'P2' in output:
+            multipoles['P2'][i] = np.sum(ps[idx] * P2[idx]) / np.sum(P2[idx] ** 2)
+        if 'P4' in output:
+            multipoles['P4'][i] = np.sum(ps[idx] * P4[idx]) / np.sum(P4[idx] ** 2)
+    multipoles['nmodes'] = nmodes
+    multipoles['n_modes'] = count
+    return multipoles, edges[:-1] + dk

@@ -91,6 +91,16 @@ CASES = [
        return_modes=True),
     _c("ps2d_edges", "power_spectrum_2d", (32,) * 3, seed=65, dtype="float64",
        kbins=["edges:0,0.2,0.5,1.0,2.0", "edges:0,0.3,0.9,2.0"], box_dims=100.0, return_modes=True),
+    # ---- multipoles; the reference runs only with its _get_mu call repaired and with
+    # exclude_zero_modes=True (make_golden.py), so these are the cases it can pin
+    _c("mpoles_64_los0", "power_spectrum_multipoles", (64,) * 3, field="toy", seed=71, kbins=8, box_dims=200.0, los_axis=0,
+       exclude_zero_modes=True),
+    _c("mpoles_64_los2_f64", "power_spectrum_multipoles", (64,) * 3, seed=72, dtype="float64", kbins=10, box_dims=244 / H,
+       los_axis=2, exclude_zero_modes=True),
+    _c("mpoles_noncubic_los1", "power_spectrum_multipoles", (32, 64, 16), seed=73, kbins=6, box_dims=[80.0, 100.0, 40.0],
+       los_axis=1, exclude_zero_modes=True),
+    _c("mpoles_33_odd", "power_spectrum_multipoles", (33,) * 3, seed=74, dtype="float64", kbins=5, box_dims=50.0, los_axis=0,
+       exclude_zero_modes=True),
     # ---- stand-alone binning of caller-supplied fftshifted arrays ----------
     _c("ravg_3d", "radial_average", (32,) * 3, field="positive", seed=51, box_dims=[200.0] * 3, kbins=8),
     _c("ravg_3d_lin", "radial_average", (33, 32, 16), field="positive", seed=52, box_dims=[100.0, 90.0, 40.0],

@@ -57,6 +57,16 @@ def test_api_matches_reference_golden(t2c, case, golden):
     if not isinstance(res, tuple):
         res = (res,)
     want = golden_outputs(golden, case["id"])
+    if case["fn"] == "power_spectrum_multipoles":
+        mp, kc = res
+        single = case["dtype"] == "float32"
+        assert np.array_equal(kc, want[4]) and np.array_equal(mp["nmodes"], want[3])
+        np.testing.assert_allclose(mp["P0"], want[0], rtol=1e-5 if single else 1e-12)
+        # P2 / P4 are signed sums that nearly cancel for an isotropic field: bounded relative to the monopole
+        atol = (2e-5 if single else 1e-11) * float(np.max(np.abs(want[0])))
+        np.testing.assert_allclose(mp["P2"], want[1], rtol=1e-5 if single else 1e-10, atol=atol)
+        np.testing.assert_allclose(mp["P4"], want[2], rtol=1e-5 if single else 1e-10, atol=atol)
+        return
     assert len(res) == len(want)
     for got, ref in zip(res, want):
         assert np.asarray(got).shape == ref.shape
@@ -147,6 +157,25 @@ def test_warp_per_pencil_x_pass_mu_modes_against_oracle(t2c, shape, los, absmu):
     ps_o, ks_o, nm_o = ps_oracle.power_spectrum_1d(x, kbins=e, box_dims=box, return_n_modes=True)
     assert np.array_equal(nm, nm_o)
     np.testing.assert_allclose(ps, ps_o, rtol=1e-5, equal_nan=True)
+
+
+@pytest.mark.parametrize("shape,los", [((64, 64, 64), 0), ((48, 40, 72), 1), ((33, 33, 33), 2), ((128, 16, 32), 2)])
+def test_multipoles_against_oracle(t2c, shape, los):
+    """power_spectrum_multipoles with and without the k_perp = 0 line, explicit edges (a bin that holds DC: mu = NaN
+    there, so P2 / P4 of that bin are NaN like the oracle's), mode counts against the oracle's count."""
+    from oracle import ps_oracle
+    x = np.random.default_rng(sum(shape)).standard_normal(shape) + 1.5
+    box = [120.0, 100.0, 180.0]
+    for kb, excl in ((7, True), (7, False), (np.array([0.0, 0.2, 0.5, 1.0, 2.5]), False)):
+        got, kc = t2c.power_spectrum_multipoles(x, kbins=kb, box_dims=box, los_axis=los, exclude_zero_modes=excl)
+        with np.errstate(all="ignore"):
+            want, kc_o = ps_oracle.power_spectrum_multipoles(x, kbins=kb, box_dims=box, los_axis=los, exclude_zero_modes=excl)
+        assert np.array_equal(kc, kc_o)
+        assert np.array_equal(got["n_modes"], want["n_modes"]) and np.array_equal(got["nmodes"], want["nmodes"])
+        np.testing.assert_allclose(got["P0"], want["P0"], rtol=1e-11, equal_nan=True)
+        atol = 1e-10 * float(np.nanmax(np.abs(want["P0"])))
+        np.testing.assert_allclose(got["P2"], want["P2"], rtol=1e-6, atol=atol, equal_nan=True)
+        np.testing.assert_allclose(got["P4"], want["P4"], rtol=1e-6, atol=atol, equal_nan=True)
 
 
 @pytest.mark.parametrize("shape", [(64, 64), (45, 64), (100,)])

@@ -22,6 +22,8 @@ def test_oracle_matches_reference_golden(case, golden):
     res = fn(*build_inputs(case), **kw)
     if not isinstance(res, tuple):
         res = (res,)
+    if case["fn"] == "power_spectrum_multipoles":      # (dict, k) -> P0, P2, P4, nmodes, k as make_golden.py stores them
+        res = (res[0]["P0"], res[0]["P2"], res[0]["P4"], res[0]["nmodes"], res[1])
     want = golden_outputs(golden, case["id"])
     assert len(res) == len(want)
     for got, ref in zip(res, want):

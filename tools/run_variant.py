@@ -18,6 +18,7 @@ V = {
     "k100": lambda: t2c.power_spectrum_1d(a, kbins=100, box_dims=L),
     "nd": lambda: t2c.power_spectrum_nd(a, box_dims=L),
     "2d": lambda: t2c.power_spectrum_2d(a, kbins=10, box_dims=L),
+    "mp0": lambda: t2c.power_spectrum_multipoles(a, kbins=15, box_dims=L, los_axis=0),
 }
 for _ in range(reps):
     V[name]()

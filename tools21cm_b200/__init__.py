@@ -14,4 +14,6 @@ from .power_spectrum import (  # noqa: F401
     _get_k, _get_mu, _get_kbins, _get_dims, _get_nonzero_idx,
 )
 
-__version__ = "0.1.0"
+from .power_legendre import power_spectrum_multipoles  # noqa: F401  (src/tools21cm/__init__.py:38)
+
+__version__ = "0.2.0"

@@ -165,6 +165,16 @@ def load():
     lib.t21_bin_cyl.restype = i32
     lib.t21_bin_cyl_workspace_bytes.argtypes = [i32, i32]
     lib.t21_bin_cyl_workspace_bytes.restype = sz
+    lib.t21_ps_half.argtypes = [vp, vp, vp, i32, dbl, vp, i32, vp, sz, vp]
+    lib.t21_ps_half.restype = i32
+    lib.t21_half_pitch.argtypes = [vp]
+    lib.t21_half_pitch.restype = i32
+    lib.t21_bin_cyl_half.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp, sz, vp]
+    lib.t21_bin_cyl_half.restype = i32
+    lib.t21_bin_multipoles_half.argtypes = [vp, i32, i32, C.POINTER(BinSpecC), i32, i32, vp, vp, vp, sz, vp]
+    lib.t21_bin_multipoles_half.restype = i32
+    lib.t21_bin_multipoles_workspace_bytes.argtypes = [i32]
+    lib.t21_bin_multipoles_workspace_bytes.restype = sz
     lib.t21_profile.argtypes = [i32]
     lib.t21_profile.restype = i32
     lib.t21_profile_last.argtypes = [C.POINTER(C.c_float), i32]

@@ -251,11 +251,13 @@ def _guard_intervals(thr, mu_edges, s_nan):
 
 
 def build_binspec(shape, box_dims, kbins, *, binning="log", breakpoint=0.1, mubins=None, los_axis=0,
-                  absolute_mus=True, exclude_zero_modes=True, last_bin_closed=True, order="fft"):
+                  absolute_mus=True, exclude_zero_modes=True, last_bin_closed=True, order="fft", shells_with_los=False):
     """Assemble a BinSpec for an array of ``shape`` (1-, 2- or 3-D).
 
     ``last_bin_closed`` is True for ``radial_average`` (np.histogram closes the last bin)
     and False for ``mu_binning`` (``k < kmax`` strictly, power_spectrum.py:424).
+    ``shells_with_los``: shell bins (``mubins`` None) that still carry the signed k along ``los_axis`` and the
+    mu = NaN threshold -- what ``power_spectrum_multipoles`` weights its modes with (power_legendre.py:47,55-61).
     """
     ndim = len(shape)
     if ndim not in (1, 2, 3):
@@ -316,6 +318,12 @@ def build_binspec(shape, box_dims, kbins, *, binning="log", breakpoint=0.1, mubi
         s_nan = sqrt_threshold(MU_NAN_K)
         extra_flags = (s_nan,)
 
+    elif shells_with_los:
+        if ndim != 3 or los_axis not in (0, 1, 2):
+            raise ValueError("the line of sight must be one of the three axes of a 3-D array")
+        tab_los = kaxes_o[los_axis].copy()
+        s_nan = sqrt_threshold(MU_NAN_K)
+
     # pad to three axes (front) so one kernel signature serves 1-, 2- and 3-D inputs
     pad = 3 - ndim
     shape3 = (1,) * pad + tuple(int(n) for n in shape)
@@ -360,8 +368,17 @@ class CylSpec:
     kpar_mid: np.ndarray
     nu_axis: int
 
+    def counts(self):
+        """Modes per (k_perp, k_par) bin, float64 like scipy's 'count' statistic: the bins are separable, so the count is
+        (index pairs whose k_perp falls in the perp bin) x (indices whose |k_par| falls in the par bin), exactly."""
+        if getattr(self, "_counts", None) is None:
+            nperp = np.bincount(self.perp_tab[self.perp_tab >= 0].ravel(), minlength=self.nperp).astype(np.float64)
+            npar = np.bincount(self.par_tab[self.par_tab >= 0].ravel(), minlength=self.npar).astype(np.float64)
+            self._counts = nperp[:, None] * npar[None, :]
+        return self._counts.copy()
 
-def build_cyl_tables(shape, box_dims, kbins, binning="log", nu_axis=2):
+
+def build_cyl_tables(shape, box_dims, kbins, binning="log", nu_axis=2, order="shifted"):
     """Bin tables of the reference's power_spectrum_2d (power_spectrum.py:209-254).
 
     A mode's bin is separable, so the reference's digitisation (scipy.stats.binned_statistic_2d, i.e.
@@ -409,5 +426,10 @@ def build_cyl_tables(shape, box_dims, kbins, binning="log", nu_axis=2):
     else:
         kper_mid = (kper[:-1] + kper[1:]) / 2.0
         kpar_mid = (kpar[:-1] + kpar[1:]) / 2.0
+    if order == "fft":        # tables indexed by FFT index m: fftshift index i = (m + n//2) % n along every axis
+        ia = (np.arange(perp_tab.shape[0]) + perp_tab.shape[0] // 2) % perp_tab.shape[0]
+        ib = (np.arange(perp_tab.shape[1]) + perp_tab.shape[1] // 2) % perp_tab.shape[1]
+        perp_tab = perp_tab[np.ix_(ia, ib)]
+        par_tab = to_fft_order(par_tab)
     return CylSpec(nperp=nperp, npar=npar, perp_tab=np.ascontiguousarray(perp_tab),
                    par_tab=np.ascontiguousarray(par_tab), kper_mid=kper_mid, kpar_mid=kpar_mid, nu_axis=nu_axis)

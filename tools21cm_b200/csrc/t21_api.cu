@@ -276,8 +276,24 @@ int t21_ps_binned(const t21_plan* p, const void* x1, const void* x2, int subtrac
     return rc;
 }
 
+static int ps_nd_impl(const t21_plan* p, const void* x1, const void* x2, int subtract_mean, double scale, void* out,
+                      int out_dtype, int half, void* workspace, size_t workspace_bytes, void* stream);
+
 int t21_ps_nd(const t21_plan* p, const void* x1, const void* x2, int subtract_mean, double scale, void* out,
               int out_dtype, void* workspace, size_t workspace_bytes, void* stream) {
+    return ps_nd_impl(p, x1, x2, subtract_mean, scale, out, out_dtype, 0, workspace, workspace_bytes, stream);
+}
+
+// The scaled power of the computed half spectrum only, FFT order: out[nx][ny][nz/2+1].  It is what the estimators
+// that bin on something other than (k, mu) boxes read back (t21_bin_cyl_half, t21_bin_multipoles_half): a quarter
+// of the bytes of the full fftshifted float64 array, and no Hermitian-twin stores.  Rows are t21_half_pitch(plan) long.
+int t21_ps_half(const t21_plan* p, const void* x1, const void* x2, int subtract_mean, double scale, void* out_half,
+                int out_dtype, void* workspace, size_t workspace_bytes, void* stream) {
+    return ps_nd_impl(p, x1, x2, subtract_mean, scale, out_half, out_dtype, 1, workspace, workspace_bytes, stream);
+}
+
+static int ps_nd_impl(const t21_plan* p, const void* x1, const void* x2, int subtract_mean, double scale, void* out,
+                      int out_dtype, int half, void* workspace, size_t workspace_bytes, void* stream) {
     if (!out) { set_error("null output"); return T21_EINVAL; }
     if (out_dtype != T21_F32 && out_dtype != T21_F64) { set_error("bad output dtype"); return T21_EINVAL; }
     const int nf = x2 ? 2 : 1;
@@ -299,7 +315,7 @@ int t21_ps_nd(const t21_plan* p, const void* x1, const void* x2, int subtract_me
     a.tw = p->tw[0]; a.tw32 = p->tw32[0];
     a.offset[0] = offs[0]; a.offset[1] = offs[1];
     a.ntot = (double)p->n[0] * p->n[1] * p->n[2];
-    a.nd_out = out; a.nd_f64 = out_dtype == T21_F64; a.scale = scale;
+    a.nd_out = out; a.nd_f64 = out_dtype == T21_F64; a.scale = scale; a.nd_half = half ? t21_half_pitch(p) : 0;
     a.max_grid = p->max_grid;
     const int rc = !p->fast[0] ? launch_xpass_generic(p->dtype, a, st)
                                : (p->dtype == T21_F32 ? launch_xpass_f32_nd(a, st) : launch_xpass_f64_nd(a, st));
@@ -332,6 +348,9 @@ int t21_profile_last(float* ms_out, int cap) {
 // exchange (caller): all-to-all over NCCL re-partitions the half spectrum into y slabs (nx planes of ny/P rows)
 // stage 2 (local):  X pass + binning of this rank's y slab; the caller all-reduces sums and counts.
 int t21_slab_pitch(const t21_plan* p) { return p ? p->pitch : 0; }
+// row length (elements) of the half-spectrum power arrays: nz/2+1 rounded up to 8, so that the 8-column runs the
+// X pass stores are whole 32-byte sectors (an odd row length made every run straddle two: +100 % DRAM traffic)
+int t21_half_pitch(const t21_plan* p) { return p ? (p->nzh + 7) / 8 * 8 : 0; }
 
 int t21_slab_stage1(const t21_plan* p, const void* x_slab, const void* offset_or_null, void* w_out, void* send_out,
                     int nranks, void* stream) {
@@ -481,7 +500,7 @@ int t21_slab_stage2_nd(const t21_plan* p, const void* w1, const void* w2, int n_
     a.tw = p->tw[0]; a.tw32 = p->tw32[0];
     a.offset[0] = offset1; a.offset[1] = offset2;
     a.ntot = (double)p->n[0] * ny_global * p->n[2];
-    a.nd_out = out_half; a.nd_f64 = out_dtype == T21_F64; a.nd_half = 1; a.scale = scale;
+    a.nd_out = out_half; a.nd_f64 = out_dtype == T21_F64; a.nd_half = t21_half_pitch(p); a.scale = scale;
     a.max_grid = p->max_grid;
     const int rc = p->dtype == T21_F32 ? launch_xpass_f32_nd(a, st) : launch_xpass_f64_nd(a, st);
     prof_mark(st, SLOT_X);
@@ -548,6 +567,48 @@ int t21_bin_cyl(const void* p_shifted, int dtype, int n0, int n1, int n2, int nu
         return rc;
     if (!global) return launch_reduce_partials(part_sum, part_cnt, grid, nbins, sums_out, counts_out, st);
     return T21_OK;
+}
+
+// the same SUMS from the computed half spectrum of t21_ps_half ([nx][ny][row_pitch], FFT order; tables in FFT order
+// over the full axes).  Mode counts of separable bins are formed on the host from the two tables.
+int t21_bin_cyl_half(const void* p_half, int dtype, int nx, int ny, int nz, int row_pitch, int nu_axis, const int* perp_tab,
+                     const int* par_tab, int nperp, int npar, double* sums_out, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+    if (!p_half || !perp_tab || !par_tab || !sums_out || !workspace) { set_error("null argument"); return T21_EINVAL; }
+    if (dtype != T21_F32 && dtype != T21_F64) { set_error("bad dtype %d", dtype); return T21_EINVAL; }
+    if (nu_axis < 0 || nu_axis > 2 || nx < 1 || ny < 1 || nz < 1 || nperp < 1 || npar < 1 || row_pitch < nz / 2 + 1) {
+        set_error("bad geometry"); return T21_EINVAL;
+    }
+    const size_t need = t21_bin_cyl_workspace_bytes(nperp, npar);
+    if (workspace_bytes < need) { set_error("workspace too small: %zu < %zu bytes", workspace_bytes, need); return T21_ENOMEM; }
+    return launch_cyl_rows(p_half, dtype, nx, ny, nz, row_pitch, nu_axis, perp_tab, par_tab, nperp, npar, (double*)workspace,
+                           device_sm_count() * 8, sums_out, (cudaStream_t)stream);
+}
+
+size_t t21_bin_multipoles_workspace_bytes(int nk) {
+    if (nk < 1) return 0;
+    const size_t g = (size_t)device_sm_count() * 4;
+    return align_up(g * nk * 5 * sizeof(double), 256) + align_up(g * nk * sizeof(unsigned), 256);
+}
+
+int t21_bin_multipoles_half(const void* p_half, int dtype, int row_pitch, const t21_binspec* spec, int los_axis, int exclude_zero,
+                            double* sums_out, long long* counts_out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!p_half || !spec || !sums_out || !counts_out || !workspace) { set_error("null argument"); return T21_EINVAL; }
+    if (dtype != T21_F32 && dtype != T21_F64) { set_error("bad dtype %d", dtype); return T21_EINVAL; }
+    if (spec->nmu != 0 || spec->nk < 1 || los_axis < 0 || los_axis > 2 || !spec->tab_losf) {
+        set_error("multipoles need a shell bin spec that carries the line-of-sight table"); return T21_EINVAL;
+    }
+    const size_t need = t21_bin_multipoles_workspace_bytes(spec->nk);
+    if (workspace_bytes < need) { set_error("workspace too small: %zu < %zu bytes", workspace_bytes, need); return T21_ENOMEM; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int max_grid = device_sm_count() * 4;
+    double* part_sum = (double*)workspace;
+    unsigned* part_cnt = (unsigned*)((unsigned char*)workspace + align_up((size_t)max_grid * spec->nk * 5 * sizeof(double), 256));
+    int grid = 0;
+    if (row_pitch < spec->n[2] / 2 + 1) { set_error("row pitch %d is shorter than nz/2+1", row_pitch); return T21_EINVAL; }
+    if (int rc = launch_bin_multipoles(p_half, dtype, *spec, row_pitch, los_axis, exclude_zero, part_sum, part_cnt, max_grid, &grid, st))
+        return rc;
+    return launch_reduce_moments(part_sum, part_cnt, grid, spec->nk, sums_out, counts_out, st);
 }
 
 }  // extern "C"

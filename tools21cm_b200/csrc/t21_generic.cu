@@ -95,7 +95,7 @@ gen_xpass_kernel(const cx<T>* __restrict__ w0, const cx<T>* __restrict__ w1, int
                  int pitch, const cx<T>* __restrict__ roots, const T* off0, const T* off1, double ntot,
                  const __grid_constant__ t21_binspec B, int nbins, double* __restrict__ part_sum,
                  unsigned* __restrict__ part_cnt, double* gsum, unsigned long long* gcnt, void* nd_out, int nd_f64,
-                 double scale) {
+                 int nd_half, double scale) {
     constexpr int WZ = GenWZ<T>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<T>* tile0 = reinterpret_cast<cx<T>*>(smem_raw);                 // [nx][WZ]
@@ -154,6 +154,11 @@ gen_xpass_kernel(const cx<T>* __restrict__ w0, const cx<T>* __restrict__ w1, int
             const bool has_twin = (iz != 0) && (iz != nz - iz);
             if (HK == 2) {
                 const double val = pw * scale;
+                if (nd_half) {                  // the computed half spectrum, FFT order: [nx][ny][nd_half >= nz/2+1]
+                    const long long oh = ((long long)ix * ny + iy) * nd_half + iz;
+                    if (nd_f64) ((double*)nd_out)[oh] = val; else ((float*)nd_out)[oh] = (float)val;
+                    continue;
+                }
                 const int hx = nx / 2, hy = ny / 2, hz = nz / 2;
                 const int sx = (ix + hx) % nx, sy = (iy + hy) % ny, sz = (iz + hz) % nz;
                 const long long o = ((long long)sx * ny + sy) * nz + sz;
@@ -248,7 +253,7 @@ static int gen_x(XArgs& a, cudaStream_t st) {
         if (int rc = ensure_smem(kern, smem)) return rc;                                                        \
         kern<<<(unsigned)g, kGenThreads, smem, st>>>((const cx<T>*)a.w[0], (const cx<T>*)a.w[1], a.nx, a.ny, a.nz,  \
             a.nzh, a.pitch, (const cx<T>*)a.tw, (const T*)a.offset[0], (const T*)a.offset[1], a.ntot, B,        \
-            a.nbins, a.part_sum, a.part_cnt, a.gsum, a.gcnt, a.nd_out, a.nd_f64, a.scale);                      \
+            a.nbins, a.part_sum, a.part_cnt, a.gsum, a.gcnt, a.nd_out, a.nd_f64, a.nd_half, a.scale);                      \
     }
     if (hk == 0) T21_GEN_X(0) else if (hk == 1) T21_GEN_X(1) else T21_GEN_X(2)
 #undef T21_GEN_X

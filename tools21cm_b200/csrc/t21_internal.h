@@ -69,6 +69,13 @@ int launch_bin_cyl(const void* p, int dtype, int n0, int n1, int n2, int nu_axis
                    const int* par_tab, int nperp, int npar, double* part_sum, unsigned* part_cnt, int max_grid,
                    double* gsum, long long* gcnt, int* grid_used, cudaStream_t st);
 
+int launch_cyl_rows(const void* p, int dtype, int n0, int n1, int nz, int pitch, int nu_axis, const int* perp_tab, const int* par_tab,
+                    int nperp, int npar, double* part_sum, int max_grid, double* sums_out, cudaStream_t st);
+int launch_bin_multipoles(const void* p, int dtype, const t21_binspec& spec, int pitch, int los, int exclude_zero,
+                          double* part_sum, unsigned* part_cnt, int max_grid, int* grid_used, cudaStream_t st);
+int launch_reduce_moments(const double* part_sum, const unsigned* part_cnt, int nparts, int nk, double* sums_out,
+                          long long* counts_out, cudaStream_t st);
+
 // error plumbing (t21_api.cu)
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);

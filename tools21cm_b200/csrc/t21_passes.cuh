@@ -407,7 +407,8 @@ struct XPass {
         t21_binspec bins;     // MODE_BIN
         void* nd_out;         // MODE_ND: [NX][ny][nz] fftshifted, or [NX][ny][nz/2+1] in FFT order (nd_half)
         int nd_f64;           // MODE_ND: output dtype
-        int nd_half;          // MODE_ND: store only the computed half spectrum, unshifted (slab-sharded cubes)
+        int nd_half;          // MODE_ND: > 0 = store only the computed half spectrum, unshifted, rows of nd_half elements
+                              // (a multiple of 8 keeps every 32-byte run of a tile inside one DRAM sector)
         double scale;         // MODE_ND
     };
     struct Regs {
@@ -730,7 +731,7 @@ struct XPass {
             if ((ix | iy | iz) == 0) pw = *dc_slot(smem);
             const double val = pw * p.scale;
             if (p.nd_half) {
-                const long long oh = ((long long)ix * p.ny + iy_loc) * p.nzh + iz;
+                const long long oh = ((long long)ix * p.ny + iy_loc) * p.nd_half + iz;
                 if (p.nd_f64) ((double*)p.nd_out)[oh] = val; else ((float*)p.nd_out)[oh] = (float)val;
                 continue;
             }

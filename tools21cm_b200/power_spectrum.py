@@ -226,6 +226,28 @@ def _fused_nd(fields, scale, out_dtype):
     return out
 
 
+def _fused_half(fields, scale, out_dtype):
+    """t21_ps_half: the scaled power of the computed half spectrum, FFT order, [nx][ny][row pitch >= nz//2+1] (device
+    tensor; the columns past nz//2 are padding that keeps the rows sector-aligned)."""
+    torch = _torch()
+    x = fields[0]
+    if x.dim() != 3:
+        raise NotImplementedError("this estimator handles 3-dimensional cubes; got %d-D" % x.dim())
+    dev = _device(x.device.index)
+    with torch.cuda.device(x.device):
+        lib = _lib.load()
+        code = _dtype_code(x)
+        plan = dev.plan(tuple(x.shape), code)
+        ws = dev.workspace(lib.t21_workspace_bytes(plan, len(fields), 0))
+        out = torch.empty((x.shape[0], x.shape[1], lib.t21_half_pitch(plan)), dtype=out_dtype, device=x.device)
+        x2 = fields[1].data_ptr() if len(fields) == 2 else None
+        rc = lib.t21_ps_half(plan, x.data_ptr(), x2, 1 if code == T21_F32 else 0, float(scale), out.data_ptr(),
+                             T21_F32 if out_dtype == torch.float32 else T21_F64, ws.data_ptr(), ws.numel(),
+                             _stream_ptr(torch, x.device.index))
+        _lib.check(rc, "t21_ps_half")
+    return out
+
+
 def _bin_only(arr_t, spec_key, spec_builder):
     torch = _torch()
     dev = _device(arr_t.device.index)
@@ -541,22 +563,26 @@ def power_spectrum_2d(input_array, kbins=10, binning="log", box_dims=244 / .7, r
     x, _ = _stage(input_array)
     torch = _torch()
     shape = tuple(x.shape)
-    power = _fused_nd([x], _bs.volume_scale(shape, box_dims), torch.float64)
+    if len(shape) != 3:
+        raise ValueError("power_spectrum_2d needs a 3-D array")
+    # the power of the computed half spectrum in the transform's own precision (a quarter of the reference's
+    # fftshifted float64 cube, :229), then the separable (k_perp, k_par) tables applied to it
+    power = _fused_half([x], _bs.volume_scale(shape, box_dims), x.dtype)
     dev = _device(x.device.index)
     cyl, perp, par = dev.cyl((shape, _freeze(list(box_dims)), _freeze(kbins), binning, int(nu_axis)),
-                             lambda: _bs.build_cyl_tables(shape, box_dims, kbins, binning=binning, nu_axis=nu_axis))
+                             lambda: _bs.build_cyl_tables(shape, box_dims, kbins, binning=binning, nu_axis=nu_axis,
+                                                          order="fft"))
     with torch.cuda.device(x.device):
         lib = _lib.load()
         nb = cyl.nperp * cyl.npar
         ws = dev.workspace(lib.t21_bin_cyl_workspace_bytes(cyl.nperp, cyl.npar))
         sums = torch.empty(nb, dtype=torch.float64, device=x.device)
-        counts = torch.empty(nb, dtype=torch.int64, device=x.device)
-        rc = lib.t21_bin_cyl(power.data_ptr(), T21_F64, shape[0], shape[1], shape[2], int(nu_axis), perp.data_ptr(),
-                             par.data_ptr(), cyl.nperp, cyl.npar, sums.data_ptr(), counts.data_ptr(), ws.data_ptr(),
-                             ws.numel(), _stream_ptr(torch, x.device.index))
-        _lib.check(rc, "t21_bin_cyl")
+        rc = lib.t21_bin_cyl_half(power.data_ptr(), _dtype_code(power), shape[0], shape[1], shape[2], int(power.shape[2]),
+                                  int(nu_axis), perp.data_ptr(), par.data_ptr(), cyl.nperp, cyl.npar, sums.data_ptr(),
+                                  ws.data_ptr(), ws.numel(), _stream_ptr(torch, x.device.index))
+        _lib.check(rc, "t21_bin_cyl_half")
         s = sums.cpu().numpy().reshape(cyl.nperp, cyl.npar)
-        n = counts.cpu().numpy().astype("float").reshape(cyl.nperp, cyl.npar)
+        n = cyl.counts()          # separable bins: (index pairs in the perp bin) x (indices in the par bin), exact
     ps = _finish(s, n, 1.0)
     if return_modes:
         return ps, cyl.kper_mid, cyl.kpar_mid, n

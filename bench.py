@@ -192,6 +192,243 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def nccl_summary():
+    """What NCCL logged at init (NCCL_DEBUG_FILE of this process): communicator size and whether NVLS is in use."""
+    import glob, re
+    out = {"nranks": None, "nvls": None, "log": None}
+    pat = os.environ.get("NCCL_DEBUG_FILE", "").replace("%h", "*").replace("%p", str(os.getpid()))
+    for path in glob.glob(pat):
+        try:
+            txt = open(path, errors="replace").read()
+        except OSError:
+            continue
+        out["log"] = path
+        m = re.findall(r"nranks (\d+)", txt)
+        if m:
+            out["nranks"] = max(int(v) for v in m)
+        out["nvls"] = bool(re.search(r"NVLS", txt))
+        for ln in txt.splitlines():
+            if "nranks" in ln or "NVLS" in ln or "NCCL version" in ln:
+                print(ln, file=sys.stderr)
+    return out
+
+
+def gather_slabs(slab, dist, world, rank):
+    """The full cube on rank 0 from the ranks' x slabs (for the parity figures of the sharded legs)."""
+    import torch
+    parts = [torch.empty_like(slab) for _ in range(world)] if rank == 0 else None
+    dist.gather(slab, parts, dst=0)
+    return torch.cat(parts, dim=0) if rank == 0 else None
+
+
+def sharded_leg(args, D, t2c, lib, synthetic, dist, dev, rank, world, barrier, e0, e1):
+    import ctypes as C
+    import numpy as np
+    import torch
+    ns = args.slab_size or args.size
+    nxl = ns // world
+    slabs = [synthetic.toy_dt_cube_torch((nxl, ns, ns), seed=4000 + rank, device=dev)]
+    cross = args.slab_cross or args.slab_nd
+    if cross:
+        slabs.append(synthetic.gaussian_cube_torch((nxl, ns, ns), seed=5000 + rank, device=dev))
+
+    def slab_step():
+        if args.slab_nd:
+            rows, yidx = D.sharded_cross_power_spectrum_nd(slabs[0], slabs[1], BOX_MPC, copy=False)
+            return None, None, np.array([float(rows.numel())])
+        if cross:
+            return D.sharded_cross_power_spectrum_1d(slabs[0], slabs[1], kbins=KBINS, box_dims=BOX_MPC, return_n_modes=True)
+        return D.sharded_power_spectrum_1d(slabs[0], kbins=KBINS, box_dims=BOX_MPC, return_n_modes=True)
+
+    def timed(n_steps):
+        for _ in range(3):
+            r = slab_step()
+        barrier()
+        e0.record()
+        for _ in range(n_steps):
+            r = slab_step()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n_steps, r
+
+    nf = 2 if cross else 1
+    cbytes = 8 * ns * ns * (ns // 2 + 1)
+    a_bytes = (world - 1) / world ** 2 * cbytes * nf           # per GPU and direction, all fields (SURVEY.md 8d)
+    out = {"workload": "%s of ONE %d^3 fp32 cube held as %d x slabs" %
+                       ("cross_power_spectrum_nd (output sharded by y rows)" if args.slab_nd else
+                        "cross_power_spectrum_1d" if cross else "power_spectrum_1d", ns, world),
+           "unit": "cubes/s", "scaling": "strong", "nvlink_bytes_per_gpu_per_direction": a_bytes}
+    results = {}
+    for mode in ("p2p", "nccl"):
+        os.environ["T21_EXCHANGE"] = mode
+        ms, res = timed(args.steps)
+        results[mode] = res
+        entry = {"ms_per_step": ms, "value": 1e3 / ms}
+        if mode == "p2p":
+            # stage 1 of the fused path alone: Z pass + Y pass whose stores ARE the exchange (CUDA events of the library)
+            buf = (C.c_float * 5)()
+            if True:
+                lib.t21_profile(1)
+                acc = np.zeros(5)
+                for _ in range(3):
+                    slab_step()
+                    lib.t21_profile_last(buf, 5)
+                    acc += np.array(list(buf))
+                lib.t21_profile(0)
+                acc /= 3.0
+                t = torch.tensor(acc, device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                acc = t.cpu().numpy()
+                if True:
+                    gbs1 = a_bytes / nf / 1e9 / (acc[2] / 1e3) if acc[2] > 0 else None      # (the profile holds the last field)
+                    entry["fused_y_pass"] = {
+                        "ms_per_field": float(acc[2]), "z_ms_per_field": float(acc[1]), "achieved_gbs": gbs1,
+                        "frac_of_770_measured_peer": gbs1 / 770.0 if gbs1 else None,
+                        "frac_of_900_nominal": gbs1 / 900.0 if gbs1 else None,
+                        "what": "Y pass with SEND=2 (its stores go straight to the owners' y slabs over NVLink), one field, "
+                                "CUDA events of the library around the pass; bytes = A(N,P) of SURVEY.md 8d per field"}
+                    entry["x_pass_ms"] = float(acc[3])
+        elif mode == "nccl":
+            # the NCCL exchange alone (one field, no overlap with compute)
+            be = D.CudaBackend()
+            send = be.stage1(slabs[0], None, send_world=world)
+            for _ in range(2):
+                D.all_to_all_packed(send)
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                D.all_to_all_packed(send)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            a2a = float(t.item())
+            del send
+            gbs = a_bytes / nf / 1e9 / (a2a / 1e3)
+            entry["all_to_all_alone"] = {"ms": a2a, "achieved_gbs": gbs, "frac_of_770_measured_peer": gbs / 770.0,
+                                         "frac_of_900_nominal": gbs / 900.0,
+                                         "what": "all_to_all_single over NCCL of ONE field's packed send buffer, timed alone"}
+        out[mode] = entry
+    os.environ["T21_EXCHANGE"] = "p2p"
+    out["value"] = out["p2p"]["value"]
+    out["ms_per_step"] = out["p2p"]["ms_per_step"]
+    # parity: the same cube on ONE GPU (rank 0 gathers the slabs) against both exchanges
+    if not args.slab_nd and ns <= 1024:
+        full = [gather_slabs(sl, dist, world, rank) for sl in slabs]
+        if rank == 0:
+            if cross:
+                ref = t2c.cross_power_spectrum_1d(full[0], full[1], kbins=KBINS, box_dims=BOX_MPC, return_n_modes=True)
+            else:
+                ref = t2c.power_spectrum_1d(full[0], kbins=KBINS, box_dims=BOX_MPC, return_n_modes=True)
+            par = {}
+            for mode in ("p2p", "nccl"):
+                got = results[mode]
+                with np.errstate(all="ignore"):
+                    rel = np.abs(got[0] - ref[0]) / np.abs(ref[0])
+                par[mode] = {"n_modes_equal": bool(np.array_equal(got[2], ref[2])), "max_rel": float(np.nanmax(rel))}
+            out["parity"] = dict(par, against="the single-GPU estimator on the gathered cube (rank 0)")
+        del full
+    elif not args.slab_nd:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import lattice                                   # exact per-bin mode counts without an FFT (a checker)
+        want = lattice.shell_counts((ns,) * 3, [BOX_MPC] * 3, lattice.reference_edges((ns,) * 3, [BOX_MPC] * 3, KBINS))
+        out["parity"] = {m: {"n_modes_equal": bool(np.array_equal(results[m][2], want))} for m in ("p2p", "nccl")}
+        out["parity"]["against"] = "exact lattice mode counts (tests/lattice.py); the cube is too large to gather"
+    out["n_modes_total"] = float(np.sum(results["p2p"][2]))
+    return out
+
+
+def config3_leg(args, D, t2c, synthetic, dist, dev, rank, world, barrier):
+    """BASELINE config 3: cross_power_spectrum_1d of 64 pairs of 512^3 (density, xfrac) cubes, dealt to the ranks."""
+    import numpy as np
+    import torch
+    npairs, n = 64, 512
+    mine = D.partition(npairs, world, rank)
+    pairs = {}
+    for i in mine:
+        g = torch.Generator(device=dev).manual_seed(2000 + i)
+        delta = 0.3 * torch.randn((n, n, n), generator=g, device=dev)
+        xf = (torch.rand((n, n, n), generator=g, device=dev) < 0.3).to(torch.float32)
+        pairs[i] = ((1.0 + delta), xf)
+
+    def fn(i):
+        a, b = pairs[i]
+        return t2c.cross_power_spectrum_1d(a, b, kbins=KBINS, box_dims=244 / 0.7, return_n_modes=True)
+    D.batched(fn, list(range(npairs)))
+    barrier()
+    t0 = time.perf_counter()
+    res = D.batched(fn, list(range(npairs)))
+    torch.cuda.synchronize()
+    barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    b_pair = 2 * (4 * n ** 3 + 4 * 8 * n * n * (n // 2 + 1))
+    return {"workload": "cross_power_spectrum_1d, 64 pairs of 512^3 fp32 (1+delta, mask) cubes, pair i on rank i mod %d, "
+                        "results gathered on every rank" % world,
+            "pairs_per_s": npairs / dt, "ms_total": dt * 1e3, "ms_per_pair_per_gpu": dt * 1e3 / (npairs / world),
+            "hbm_gbs_per_gpu": b_pair * (npairs / world) / dt / 1e9,
+            "n_modes_total_pair0": float(np.sum(res[0][2])), "timing": "wall clock around the whole batch, max over ranks"}
+
+
+def config5_leg(args, D, lib, synthetic, dist, dev, rank, world, barrier):
+    """BASELINE config 5: cross_power_spectrum_nd of a 2048^3 pair held as x slabs, output left sharded by y rows."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    n = args.c5_size
+    nxl = n // world
+    free, _ = torch.cuda.mem_get_info()
+    need = 2 * nxl * n * n * 4 * 6
+    if free < need:
+        return {"skipped": "needs %.0f GB per GPU, %.0f free" % (need / 2 ** 30, free / 2 ** 30)}
+    g = torch.Generator(device=dev).manual_seed(7000 + rank)
+    a = torch.randn((nxl, n, n), generator=g, device=dev)
+    b = torch.randn((nxl, n, n), generator=g, device=dev)
+    out = {"workload": "cross_power_spectrum_nd, one pair of %d^3 fp32 cubes as %d x slabs, fftshifted fp32 output left sharded "
+                       "by rows of y" % (n, world)}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cbytes = 8 * n * n * (n // 2 + 1)
+    a_bytes = 2 * (world - 1) / world ** 2 * cbytes
+    for mode in ("p2p", "nccl"):
+        os.environ["T21_EXCHANGE"] = mode
+        try:
+            for _ in range(2):
+                rows, yidx = D.sharded_cross_power_spectrum_nd(a, b, 714.0, copy=False)
+            barrier()
+            e0.record()
+            reps = 3
+            for _ in range(reps):
+                rows, yidx = D.sharded_cross_power_spectrum_nd(a, b, 714.0, copy=False)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            # Parseval over the sharded output: sum of the fftshifted power == N^3 * sum(a * b) * scale
+            s = rows.double().sum().reshape(1)
+            dot = (a.double() * b.double()).sum().reshape(1)
+            dist.all_reduce(s)
+            dist.all_reduce(dot)
+            scale = (714.0 ** 3 / n ** 3) ** 2 / 714.0 ** 3
+            expect = float(dot.item()) * n ** 3 * scale
+            ref = float((a.double() ** 2).sum().item()) * world * n ** 3 * scale       # auto-power level
+            out[mode] = {"ms_per_pair": ms, "pairs_per_s": 1e3 / ms,
+                         "parseval_rel_err_vs_auto_level": abs(float(s.item()) - expect) / ref,
+                         "rows_shape": list(rows.shape)}
+            del rows
+        except Exception as exc:                       # keep the bench line alive; say what failed
+            out[mode] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+        torch.cuda.empty_cache()
+    os.environ["T21_EXCHANGE"] = "p2p"
+    out["nvlink_bytes_per_gpu_per_direction"] = a_bytes
+    out["target"] = "all-to-all phase <= %.1f ms for 50 %% of 900 GB/s (SURVEY.md 8d)" % (a_bytes / 1e9 / 0.45)
+    return out
+
+
 def workload_config(n):
     return {"workload": "power_spectrum_1d, %d^3 fp32 toy-ionised dT cube, box_dims=500/0.7 cMpc, "
                         "15 log kbins, return_n_modes" % n,
@@ -213,12 +450,20 @@ def main():
     ap.add_argument("--slab-cross", action="store_true", help="slab-sharded leg: cross spectrum of two cubes")
     ap.add_argument("--slab-nd", action="store_true",
                     help="slab-sharded leg: cross_power_spectrum_nd, output left sharded (BASELINE.json config 5)")
+    ap.add_argument("--configs35", action="store_true", help="run the config 3 / config 5 legs with fewer than 8 ranks too")
+    ap.add_argument("--c5-size", type=int, default=2048, help="cube size of the config 5 leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and args.impl == "ours":
+        # NCCL's log goes to a file per rank (stdout carries the JSON line), set before torch loads NCCL; rank 0
+        # echoes the communicator lines to stderr at the end and reports nranks / NVLS in the line
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(os.environ.get("TMPDIR", "/tmp"), "t21_nccl_%h_%p.log"))
 
     if args.impl == "reference":
         run_reference(args, rank)
@@ -236,7 +481,6 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.pop("NCCL_DEBUG", None)     # its version banner goes to stdout, which carries the JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -340,7 +584,7 @@ def main():
                "h2d_bytes_per_step": 4 * n ** 3, "d2h_bytes_per_step": 2 * KBINS * 8,
                "ms_per_step": ms_e / args.steps}
 
-    # ---- one cube sharded over all ranks as x slabs: NCCL all-to-all between the Y and X passes ----
+    # ---- one cube sharded over all ranks as x slabs (BASELINE config 4 "1 vs 2/4/8 B200 slab-sharded") ----
     sharded = None
     if world > 1 and not args.no_slab:
         from tools21cm_b200 import distributed as D
@@ -348,60 +592,21 @@ def main():
             del host
         except NameError:
             pass
+        try:
+            del x
+        except NameError:
+            pass
         torch.cuda.empty_cache()
-        ns = args.slab_size or n
-        nxl = ns // world
-        slabs = [synthetic.toy_dt_cube_torch((nxl, ns, ns), seed=4000 + rank, device=dev)]
-        if args.slab_cross or args.slab_nd:
-            slabs.append(synthetic.gaussian_cube_torch((nxl, ns, ns), seed=5000 + rank, device=dev))
+        sharded = sharded_leg(args, D, t2c, lib, synthetic, dist, dev, rank, world, barrier, e0, e1)
 
-        def slab_step():
-            if args.slab_nd:
-                rows, yidx = D.sharded_cross_power_spectrum_nd(slabs[0], slabs[1], BOX_MPC)
-                return None, None, np.array([float(rows.numel())])
-            if args.slab_cross:
-                return D.sharded_cross_power_spectrum_1d(slabs[0], slabs[1], kbins=KBINS, box_dims=BOX_MPC,
-                                                         return_n_modes=True)
-            return D.sharded_power_spectrum_1d(slabs[0], kbins=KBINS, box_dims=BOX_MPC, return_n_modes=True)
-        for _ in range(3):
-            slab_step()
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            sres = slab_step()
-        e1.record()
-        torch.cuda.synchronize()
-        ms_s = e0.elapsed_time(e1)
-        # the exchange alone (no overlap with compute), for the NVLink roofline
-        be = D.CudaBackend()
-        send = be.stage1(slabs[0], None, send_world=world)
-        for _ in range(2):
-            D.all_to_all_packed(send)
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            D.all_to_all_packed(send)
-        e1.record()
-        torch.cuda.synchronize()
-        a2a = e0.elapsed_time(e1) / args.steps
-        del send
-        t = torch.tensor([ms_s, a2a], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_s, a2a = float(t[0].item()), float(t[1].item())
-        nf = 2 if args.slab_cross else 1
-        cbytes = 8 * ns * ns * (ns // 2 + 1)
-        a_bytes = (world - 1) / world ** 2 * cbytes               # per field, per GPU, per direction
-        gbs = a_bytes / 1e9 / (a2a / 1e3) if a2a > 0 else 0.0
-        sharded = {"workload": "%s of ONE %d^3 fp32 cube held as %d x slabs" %
-                               ("cross_power_spectrum_nd (output sharded by y rows)" if args.slab_nd else
-                                "cross_power_spectrum_1d" if args.slab_cross else "power_spectrum_1d", ns, world),
-                   "value": args.steps / (ms_s / 1e3), "unit": "cubes/s", "scaling": "strong",
-                   "ms_per_step": ms_s / args.steps,
-                   "all_to_all": {"ms": a2a, "bytes_per_gpu_per_direction": a_bytes, "achieved_gbs": gbs,
-                                  "includes": "all_to_all_single over NCCL of one field, timed alone; inside a step it "
-                                              "runs in 4 pieces overlapped with the Z/Y passes, pack fused into the Y store",
-                                  "frac_of_770_measured_peer": gbs / 770.0, "frac_of_900_nominal": gbs / 900.0},
-                   "n_modes_total": float(np.sum(sres[2]))}
+    # ---- BASELINE configs 3 and 5 (only with 8 ranks, or when asked for) ----
+    config3 = config5 = None
+    if world > 1 and (world == 8 or args.configs35) and not args.no_slab:
+        from tools21cm_b200 import distributed as D
+        torch.cuda.empty_cache()
+        config3 = config3_leg(args, D, t2c, synthetic, dist, dev, rank, world, barrier)
+        torch.cuda.empty_cache()
+        config5 = config5_leg(args, D, lib, synthetic, dist, dev, rank, world, barrier)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -430,6 +635,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(n), "clocks": clocks, "gpu_launches": int(launches),
             "roofline": roofline, "passes": passes, "e2e": e2e, "cpu_baseline": cpu, "sharded": sharded,
+            "config3": config3, "config5": config5, "nccl": nccl_summary() if world > 1 else None,
             "n_modes_total": float(np.sum(res[2])),
         }
         print(json.dumps(line), flush=True)

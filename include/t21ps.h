@@ -139,6 +139,27 @@ T21_API int t21_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
 T21_API int t21_peer_open(const unsigned char* handle64, void** ptr);
 T21_API int t21_peer_close(void* ptr);
 T21_API int t21_peer_free(void* ptr);
+/* A few-KB all-gather over peer-mapped memory that doubles as a barrier (no collective library): every rank owns a
+ * buffer of t21_peer_comm_bytes() made with t21_peer_alloc (zero it once) and maps the others'.  t21_peer_signal
+ * copies this rank's payload into slot (epoch & 1, rank) of every rank's mail area and then raises its flag there;
+ * t21_peer_wait returns (on the stream) once all nranks payloads of `epoch` have landed in the caller's own buffer at
+ * mail_offset + ((epoch & 1) * nranks + r) * slot_bytes.  Epochs start at 1 and grow by 1 per exchange on every rank.
+ * peers_dev is a DEVICE array of the nranks mapped buffer addresses (own one included).  Work queued on the stream
+ * before the signal (the Y pass's peer stores) is visible to every rank that has passed the matching wait. */
+T21_API size_t t21_peer_comm_bytes(int nranks, int slot_bytes);
+T21_API size_t t21_peer_comm_mail_offset(void);
+T21_API int t21_peer_signal(void* const* peers_dev, int nranks, int rank, unsigned long long epoch, const void* payload_dev,
+                            int nbytes, int slot_bytes, void* stream);
+T21_API int t21_peer_wait(const void* my_buf, int nranks, unsigned long long epoch, int* timed_out_dev, double timeout_s,
+                          void* stream);
+/* Assembles the fftshifted n-D power of a slab-sharded cube from every rank's half spectrum (t21_slab_stage2_nd):
+ * half[nx][ny/P][row_pitch] -> outs_dev[r] = rank r's output [nx][ny/P][nz] (peer-mapped; a DEVICE array of nranks
+ * addresses).  A rank writes the kz >= 0 part of its own rows and stores the mirrored kz < 0 part straight into the
+ * output of the rank that owns row -ky.  Follow it with a barrier (t21_peer_signal / t21_peer_wait) before reading. */
+T21_API int t21_nd_assemble(const void* half, int dtype, int nx, int nyl, int nz, int row_pitch, int iy0, int ny_global,
+                            void* const* outs_dev, int nranks, int rank, void* stream);
+/* c ~ mean(x) of n elements from a strided sample, written to a device scalar of x's type (the offset of the passes) */
+T21_API int t21_mean_estimate(const void* x, long long n, int dtype, void* out_dev, void* stream);
 T21_API int t21_slab_stage1_p2p(const t21_plan* plan_slab, const void* x_slab, const void* offset_or_null,
                                 void* w_scratch, void* const* peer_cols, int nranks, long long x0_global,
                                 void* stream);

@@ -151,6 +151,18 @@ def load():
     lib.t21_peer_close.restype = i32
     lib.t21_peer_free.argtypes = [vp]
     lib.t21_peer_free.restype = i32
+    lib.t21_peer_comm_bytes.argtypes = [i32, i32]
+    lib.t21_peer_comm_bytes.restype = sz
+    lib.t21_peer_comm_mail_offset.argtypes = []
+    lib.t21_peer_comm_mail_offset.restype = sz
+    lib.t21_peer_signal.argtypes = [vp, i32, i32, C.c_ulonglong, vp, i32, i32, vp]
+    lib.t21_peer_signal.restype = i32
+    lib.t21_peer_wait.argtypes = [vp, i32, C.c_ulonglong, vp, dbl, vp]
+    lib.t21_peer_wait.restype = i32
+    lib.t21_nd_assemble.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, i32, vp]
+    lib.t21_nd_assemble.restype = i32
+    lib.t21_mean_estimate.argtypes = [vp, C.c_longlong, i32, vp, vp]
+    lib.t21_mean_estimate.restype = i32
     lib.t21_slab_stage1_p2p.argtypes = [vp, vp, vp, vp, C.POINTER(vp), i32, C.c_longlong, vp]
     lib.t21_slab_stage1_p2p.restype = i32
     lib.t21_slab_stage2.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, C.POINTER(BinSpecC), vp, vp, vp, sz, vp]

@@ -217,6 +217,14 @@ static int forward_zy(const t21_plan* p, const void* const x[2], int nf, int sub
     return 0;
 }
 
+// the current device must be the plan's (the slab entry points take raw buffers, so this is their only guard)
+static int check_device(const t21_plan* p) {
+    int cur = 0;
+    T21_CUDA_OK(cudaGetDevice(&cur));
+    if (cur != p->device) { set_error("plan was made for device %d, current device is %d", p->device, cur); return T21_EINVAL; }
+    return 0;
+}
+
 static int check_common(const t21_plan* p, const void* x1, void* ws, size_t need, size_t have) {
     if (!p || !x1 || !ws) { set_error("null plan, input or workspace"); return T21_EINVAL; }
     if (have < need) { set_error("workspace too small: %zu < %zu bytes", have, need); return T21_ENOMEM; }
@@ -347,6 +355,11 @@ int t21_profile_last(float* ms_out, int cap) {
 // stage 1 (local):  Z and Y passes of this rank's x slab [nx/P][ny][nz] -> w_out, chunk-major (nx/P planes of ny rows)
 // exchange (caller): all-to-all over NCCL re-partitions the half spectrum into y slabs (nx planes of ny/P rows)
 // stage 2 (local):  X pass + binning of this rank's y slab; the caller all-reduces sums and counts.
+int t21_mean_estimate(const void* x, long long n, int dtype, void* out_dev, void* stream) {
+    if (!x || !out_dev || n < 1 || (dtype != T21_F32 && dtype != T21_F64)) { set_error("bad argument to t21_mean_estimate"); return T21_EINVAL; }
+    return launch_mean_estimate(dtype, x, n, out_dev, (cudaStream_t)stream);
+}
+
 int t21_slab_pitch(const t21_plan* p) { return p ? p->pitch : 0; }
 // row length (elements) of the half-spectrum power arrays: nz/2+1 rounded up to 8, so that the 8-column runs the
 // X pass stores are whole 32-byte sectors (an odd row length made every run straddle two: +100 % DRAM traffic)
@@ -355,6 +368,7 @@ int t21_half_pitch(const t21_plan* p) { return p ? (p->nzh + 7) / 8 * 8 : 0; }
 int t21_slab_stage1(const t21_plan* p, const void* x_slab, const void* offset_or_null, void* w_out, void* send_out,
                     int nranks, void* stream) {
     if (!p || !x_slab || !w_out) { set_error("null argument"); return T21_EINVAL; }
+    if (int rc = check_device(p)) return rc;
     if (!(p->fast[1] && p->fast[2])) { set_error("slab mode needs power-of-two y and z axes"); return T21_EINVAL; }
     if (((uintptr_t)x_slab & 15) || ((uintptr_t)w_out & 15) || ((uintptr_t)send_out & 15)) {
         set_error("buffers must be 16-byte aligned"); return T21_EINVAL;
@@ -384,6 +398,8 @@ int t21_slab_stage1(const t21_plan* p, const void* x_slab, const void* offset_or
 int t21_slab_stage1_p2p(const t21_plan* p, const void* x_slab, const void* offset_or_null, void* w_scratch,
                         void* const* peer_cols, int nranks, long long x0_global, void* stream) {
     if (!p || !x_slab || !w_scratch || !peer_cols) { set_error("null argument"); return T21_EINVAL; }
+    if (int rc = check_device(p)) return rc;
+    if (((uintptr_t)x_slab & 15) || ((uintptr_t)w_scratch & 15)) { set_error("buffers must be 16-byte aligned"); return T21_EINVAL; }
     if (!(p->fast[1] && p->fast[2])) { set_error("slab mode needs power-of-two y and z axes"); return T21_EINVAL; }
     if (nranks < 1 || nranks > 16 || (nranks & (nranks - 1)) || p->n[1] % nranks) {
         set_error("rank count %d must be a power of two <= 16 dividing ny = %d", nranks, p->n[1]); return T21_EINVAL;
@@ -440,6 +456,10 @@ int t21_slab_stage2(const t21_plan* p, const void* w1, const void* w2, int n_xsl
                     const void* offset1, const void* offset2, const t21_binspec* spec, double* sums_out, long long* counts_out,
                     void* workspace, size_t workspace_bytes, void* stream) {
     if (!p || !w1 || !spec || !sums_out || !counts_out || !workspace) { set_error("null argument"); return T21_EINVAL; }
+    if (int rc = check_device(p)) return rc;
+    if (((uintptr_t)w1 & 63) || ((uintptr_t)w2 & 63) || ((uintptr_t)workspace & 255)) {
+        set_error("y slabs must be 64-byte and the workspace 256-byte aligned"); return T21_EINVAL;
+    }
     if (!p->fast[0]) { set_error("slab mode needs a power-of-two x axis"); return T21_EINVAL; }
     if (spec->n[0] != p->n[0] || spec->n[2] != p->n[2] || spec->n[1] != ny_global || iy0 < 0 || iy0 + p->n[1] > ny_global) {
         set_error("bin spec / slab geometry mismatch"); return T21_EINVAL;
@@ -486,6 +506,7 @@ int t21_slab_stage2_nd(const t21_plan* p, const void* w1, const void* w2, int n_
                        const void* offset1, const void* offset2, double scale, void* out_half, int out_dtype,
                        void* stream) {
     if (!p || !w1 || !out_half) { set_error("null argument"); return T21_EINVAL; }
+    if (int rc = check_device(p)) return rc;
     if (n_xslabs < 1 || (n_xslabs & (n_xslabs - 1)) || p->n[0] % n_xslabs) { set_error("bad x slab count %d", n_xslabs); return T21_EINVAL; }
     int xs_log2 = 0;
     while ((p->n[0] / n_xslabs) >> (xs_log2 + 1)) ++xs_log2;

@@ -54,7 +54,8 @@ class _Device:
         self.plans = {}
         self.specs = OrderedDict()
         self.cyls = OrderedDict()
-        self.ws = None
+        self.ws = {}
+        self._scratch = {}
 
     def plan(self, shape, dtype):
         key = (tuple(shape), dtype)
@@ -68,11 +69,27 @@ class _Device:
         return p
 
     def workspace(self, nbytes):
+        """The scratch buffer of the calls issued on the CURRENT stream: one per stream, so that estimators running on
+        different streams (or host threads with their own streams) never share half spectra or partial histograms."""
         torch = _torch()
-        if self.ws is None or self.ws.numel() < nbytes:
-            self.ws = None
-            self.ws = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda:%d" % self.index)
-        return self.ws
+        key = torch.cuda.current_stream(self.index).cuda_stream
+        ws = self.ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            self.ws.pop(key, None)
+            ws = self.ws[key] = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda:%d" % self.index)
+        return ws
+
+    def scratch(self, shape, dtype):
+        """A reusable per-stream tensor for stage outputs nobody reads after the call (the Y pass's in-place copy of a
+        slab whose result goes to the peers)."""
+        torch = _torch()
+        key = (torch.cuda.current_stream(self.index).cuda_stream, dtype)
+        n = int(np.prod(shape))
+        t = self._scratch.get(key)
+        if t is None or t.numel() < n:
+            self._scratch.pop(key, None)
+            t = self._scratch[key] = torch.empty(n, dtype=dtype, device="cuda:%d" % self.index)
+        return t[:n].view(shape)
 
     def spec(self, key, builder):
         hit = self.specs.get(key)

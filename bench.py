@@ -197,7 +197,10 @@ def nccl_summary():
     import glob, re
     out = {"nranks": None, "nvls": None, "log": None}
     pat = os.environ.get("NCCL_DEBUG_FILE", "").replace("%h", "*").replace("%p", str(os.getpid()))
-    for path in glob.glob(pat):
+    found = glob.glob(pat)
+    if not found:
+        print("no NCCL log at %s (NCCL_DEBUG=%s)" % (pat, os.environ.get("NCCL_DEBUG")), file=sys.stderr)
+    for path in found:
         try:
             txt = open(path, errors="replace").read()
         except OSError:
@@ -461,9 +464,10 @@ def main():
     if world > 1 and args.impl == "ours":
         # NCCL's log goes to a file per rank (stdout carries the JSON line), set before torch loads NCCL; rank 0
         # echoes the communicator lines to stderr at the end and reports nranks / NVLS in the line
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(os.environ.get("TMPDIR", "/tmp"), "t21_nccl_%h_%p.log"))
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "INFO"             # the communicator lines (nranks, NVLS) are INFO level
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/t21_nccl_%p.log")
 
     if args.impl == "reference":
         run_reference(args, rank)

@@ -106,6 +106,15 @@ T21_API int t21_ps_binned(const t21_plan* plan, const void* x1, const void* x2_o
                   const t21_binspec* spec, double* sums_out, long long* counts_out,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* The batch behind integrated_bispectrum / power_spectrum_response (position_dependent_power_spectrum.py:45-88): the
+ * binned auto power spectrum of `nwindows` cubically masked copies of one cube, `cube * W_L` (:65-77,90-103), with the
+ * mask fused into the first pass's load -- no masked cube is written, only the window's samples are read, and one
+ * call queues every launch.  windows: HOST array [nwindows][6] = {x0, x1, y0, y1, z0, z1}; sums_out[nwindows][nbins];
+ * counts_out[nbins] (the same for every window).  Power-of-two axes, at most 2048 bins, no mean offset. */
+T21_API int t21_ps_binned_windows(const t21_plan* plan, const void* x1, const int* windows, int nwindows,
+                                  const t21_binspec* spec, double* sums_out, long long* counts_out, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+
 /* power_spectrum_nd / cross_power_spectrum_nd (power_spectrum.py:24-54, 57-95): the full
  * fftshifted power array, multiplied by `scale`, written as out_dtype (T21_F32/T21_F64). */
 T21_API int t21_ps_nd(const t21_plan* plan, const void* x1, const void* x2_or_null, int subtract_mean,

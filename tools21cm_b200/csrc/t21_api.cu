@@ -194,7 +194,7 @@ size_t t21_workspace_bytes(const t21_plan* p, int n_fields, int nbins) {
 
 // z and y passes of every field; leaves the half spectra in the workspace
 static int forward_zy(const t21_plan* p, const void* const x[2], int nf, int subtract_mean, unsigned char* ws,
-                      const WsLayout& L, const void* offs[2], cudaStream_t st) {
+                      const WsLayout& L, const void* offs[2], cudaStream_t st, const int* window = nullptr) {
     const size_t rsz = p->dtype == T21_F32 ? 4 : 8;
     const long long ntot = (long long)p->n[0] * p->n[1] * p->n[2];
     for (int f = 0; f < nf; ++f) {
@@ -207,7 +207,7 @@ static int forward_zy(const t21_plan* p, const void* const x[2], int nf, int sub
         }
         // (Running Z and Y slab by slab to keep the half spectrum in L2 between them was measured and
         // is slower: neither pass is DRAM-bandwidth bound and every extra launch costs ~5 us.)
-        ZArgs z{x[f], ws + L.w[f], (long long)p->n[0] * p->n[1], p->n[2], p->pitch, p->n[1], (long long)p->n[0], offs[f], p->tw[2], p->twr};
+        ZArgs z{x[f], ws + L.w[f], (long long)p->n[0] * p->n[1], p->n[2], p->pitch, p->n[1], (long long)p->n[0], offs[f], p->tw[2], p->twr, window};
         if (int rc = p->fast[2] ? launch_zpass(p->dtype, z, st) : launch_zpass_generic(p->dtype, z, st)) return rc;
         prof_mark(st, SLOT_Z);
         YArgs y{ws + L.w[f], (long long)p->n[0], p->n[1], p->nzh, p->pitch, p->tw[1], nullptr, 0, nullptr, 0, 0, 0};
@@ -282,6 +282,60 @@ int t21_ps_binned(const t21_plan* p, const void* x1, const void* x2, int subtrac
         prof_mark(st, SLOT_REDUCE);
     }
     return rc;
+}
+
+static int binned_windowed(const t21_plan* p, const void* x1, const int* window, const t21_binspec* spec, double* sums_out,
+                           long long* counts_out, unsigned char* ws, const WsLayout& L, cudaStream_t st);
+
+// power_spectrum_1d of `nwindows` cubically masked copies of ONE cube (position_dependent_power_spectrum.py:65-77:
+// `c1 = cube1 * _W_L(...)` then power_spectrum_1d(c1), once per sub-box): the mask is fused into the Z pass's load, so
+// no masked cube is ever written and only the window's samples are read; the launches of all windows are queued by
+// this one call.  windows[i] = {x0, x1, y0, y1, z0, z1} (host array); sums_out[nwindows][nbins]; the mode counts do
+// not depend on the window and are written once.  The FFT sees the raw samples (no mean offset: a masked cube's mean
+// is dominated by the mask).
+int t21_ps_binned_windows(const t21_plan* p, const void* x1, const int* windows, int nwindows, const t21_binspec* spec,
+                          double* sums_out, long long* counts_out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!spec || !sums_out || !counts_out || !windows || nwindows < 1) { set_error("null or empty argument"); return T21_EINVAL; }
+    if (!p || !(p->fast[0] && p->fast[1] && p->fast[2])) { set_error("windowed batches need power-of-two axes"); return T21_EINVAL; }
+    const int nbins = spec->nk * (spec->nmu > 0 ? spec->nmu : 1);
+    if (nbins < 1 || nbins > kSmemHistMaxBins) { set_error("windowed batches take 1..%d bins", kSmemHistMaxBins); return T21_EINVAL; }
+    if (spec->n[0] != p->n[0] || spec->n[1] != p->n[1] || spec->n[2] != p->n[2]) { set_error("bin spec shape does not match the plan"); return T21_EINVAL; }
+    const WsLayout L = ws_layout(p, 1, nbins);
+    if (int rc = check_common(p, x1, workspace, L.total, workspace_bytes)) return rc;
+    for (int i = 0; i < nwindows; ++i)
+        for (int d = 0; d < 3; ++d)
+            if (windows[6 * i + 2 * d] < 0 || windows[6 * i + 2 * d + 1] > p->n[d] || windows[6 * i + 2 * d] > windows[6 * i + 2 * d + 1]) {
+                set_error("window %d is outside the cube", i); return T21_EINVAL;
+            }
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < nwindows; ++i)
+        if (int rc = binned_windowed(p, x1, windows + 6 * i, spec, sums_out + (size_t)i * nbins, counts_out, (unsigned char*)workspace, L, st))
+            return rc;
+    return T21_OK;
+}
+
+static int binned_windowed(const t21_plan* p, const void* x1, const int* window, const t21_binspec* spec, double* sums_out,
+                           long long* counts_out, unsigned char* ws, const WsLayout& L, cudaStream_t st) {
+    const void* x[2] = {x1, nullptr};
+    const void* offs[2] = {nullptr, nullptr};
+    if (int rc = forward_zy(p, x, 1, 0, ws, L, offs, st, window)) return rc;
+    const int nbins = spec->nk * (spec->nmu > 0 ? spec->nmu : 1);
+    XArgs a;
+    memset(&a, 0, sizeof(a));
+    a.w[0] = ws + L.w[0];
+    a.nf = 1;
+    a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch; a.xs_log2 = -1;
+    a.tw = p->tw[0]; a.tw32 = p->tw32[0];
+    a.ntot = (double)p->n[0] * p->n[1] * p->n[2];
+    a.bins = spec;
+    a.nbins = nbins;
+    a.part_sum = (double*)(ws + L.part_sum);
+    a.part_cnt = (unsigned*)(ws + L.part_cnt);
+    a.gsum = sums_out;
+    a.gcnt = (unsigned long long*)counts_out;
+    a.max_grid = p->max_grid;
+    if (int rc = launch_xpass_bin(p->dtype, a, st)) return rc;
+    return launch_reduce_partials(a.part_sum, a.part_cnt, a.grid_used, nbins, sums_out, counts_out, st);
 }
 
 static int ps_nd_impl(const t21_plan* p, const void* x1, const void* x2, int subtract_mean, double scale, void* out,
@@ -382,7 +436,7 @@ int t21_slab_stage1(const t21_plan* p, const void* x_slab, const void* offset_or
     }
     cudaStream_t st = (cudaStream_t)stream;
     prof_begin(st);
-    ZArgs z{x_slab, w_out, (long long)p->n[0] * p->n[1], p->n[2], p->pitch, p->n[1], (long long)p->n[0], offset_or_null, p->tw[2], p->twr};
+    ZArgs z{x_slab, w_out, (long long)p->n[0] * p->n[1], p->n[2], p->pitch, p->n[1], (long long)p->n[0], offset_or_null, p->tw[2], p->twr, nullptr};
     if (int rc = launch_zpass(p->dtype, z, st)) return rc;
     prof_mark(st, SLOT_Z);
     YArgs y{w_out, (long long)p->n[0], p->n[1], p->nzh, p->pitch, p->tw[1], send_out, nyl_log2, nullptr, 0, 0, 0};
@@ -410,7 +464,7 @@ int t21_slab_stage1_p2p(const t21_plan* p, const void* x_slab, const void* offse
     while ((p->n[1] / nranks) >> (nyl_log2 + 1)) ++nyl_log2;
     cudaStream_t st = (cudaStream_t)stream;
     prof_begin(st);
-    ZArgs z{x_slab, w_scratch, (long long)p->n[0] * p->n[1], p->n[2], p->pitch, p->n[1], (long long)p->n[0], offset_or_null, p->tw[2], p->twr};
+    ZArgs z{x_slab, w_scratch, (long long)p->n[0] * p->n[1], p->n[2], p->pitch, p->n[1], (long long)p->n[0], offset_or_null, p->tw[2], p->twr, nullptr};
     if (int rc = launch_zpass(p->dtype, z, st)) return rc;
     prof_mark(st, SLOT_Z);
     YArgs y{w_scratch, (long long)p->n[0], p->n[1], p->nzh, p->pitch, p->tw[1], nullptr, nyl_log2, peer_cols, nranks, x0_global,

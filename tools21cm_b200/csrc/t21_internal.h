@@ -10,6 +10,7 @@ namespace t21 {
 struct ZArgs {
     const void* in; void* out; long long nrows; int nz; int pitch; int ny; long long nxa;   // nxa: x planes in `out`
     const void* offset; const void* tw; const void* twr;
+    const int* window;    // null, or {x0, x1, y0, y1, z0, z1}: samples outside are read as zero (mask fused into the load)
 };
 struct YArgs {
     void* w; long long nouter; int ny; int nzh; int pitch; const void* tw;

@@ -99,6 +99,10 @@ struct ZPass {
         const T* offset;      // device scalar subtracted from every sample, or null
         const cx<T>* tw;      // Plan<M> stage twiddles
         const cx<T>* twr;     // exp(-2 pi i k / NZ), k = 0..M
+        // Cubical window fused into the load (position_dependent_power_spectrum.py:65-68,90-103: cube * W_L): samples
+        // outside [win_lo, win_hi) along any axis are read as zero -- and not read at all.  win_on = 0: no window.
+        int win_on;
+        int win_lo[3], win_hi[3];
     };
     struct Regs {
         cx<T> v[E];
@@ -118,10 +122,28 @@ struct ZPass {
         if constexpr (PH == 0) {
             const T off = p.offset ? ldg(p.offset) : (T)0;
             const cx<T>* src = reinterpret_cast<const cx<T>*>(p.in + (active ? row : 0) * NZ);
-            stage_load<P, 0>(r.v, j, [&](int i) {
-                cx<T> v = active ? src[i] : cmake<T>(0, 0);
-                return cmake<T>(v.x - off, v.y - off);
-            });
+            if (p.win_on) {
+                // (rows fit 32 bits with a window: the launcher checks; one division per thread, only on this path)
+                const unsigned xr = (unsigned)row / (unsigned)p.ny, yr = (unsigned)row - xr * (unsigned)p.ny;
+                const bool row_in = active && (int)xr >= p.win_lo[0] && (int)xr < p.win_hi[0] && (int)yr >= p.win_lo[1] &&
+                                    (int)yr < p.win_hi[1];
+                const int z0 = p.win_lo[2], z1 = p.win_hi[2];
+                stage_load<P, 0>(r.v, j, [&](int i) {
+                    const int z = 2 * i;
+                    cx<T> v = cmake<T>(0, 0);
+                    if (row_in && z + 1 >= z0 && z < z1) {
+                        v = src[i];
+                        if (z < z0) v.x = (T)0;
+                        if (z + 1 >= z1) v.y = (T)0;
+                    }
+                    return v;
+                });
+            } else {
+                stage_load<P, 0>(r.v, j, [&](int i) {
+                    cx<T> v = active ? src[i] : cmake<T>(0, 0);
+                    return cmake<T>(v.x - off, v.y - off);
+                });
+            }
             stage_compute<P, 0>(r.v, j, p.tw, st_smem);
         } else if constexpr (kInPlace && PH == 1) {
             stage_load<P, 1>(r.v, j, ld_smem);

@@ -367,3 +367,48 @@ def power_spectrum_multipoles(input_array, kbins=10, box_dims=None, los_axis=0,
     multipoles['nmodes'] = nmodes
     multipoles['n_modes'] = count
     return multipoles, edges[:-1] + dk
+
+
+def integrated_bispectrum_cross(cube1, cube2, Ncuts=4, kbins=15, box_dims=244 / .7, binning='log', normalize=False,
+                                verbose=True):
+    """Reference ``position_dependent_power_spectrum.py:45-88`` (and ``_W_L`` ``:90-103``), restated line for line:
+    every sub-box masks the FULL cube and goes through power_spectrum_1d."""
+    assert cube1.shape == cube2.shape
+    assert cube1.shape[0] % Ncuts == 0 and cube1.shape[1] % Ncuts == 0 and cube1.shape[2] % Ncuts == 0
+    Lx, Ly, Lz = cube1.shape[0] / Ncuts, cube1.shape[1] / Ncuts, cube1.shape[2] / Ncuts
+    rLs = [[Lx / 2. + i * Lx, Ly / 2. + j * Ly, Lz / 2. + k * Lz] for i in range(Ncuts) for j in range(Ncuts) for k in range(Ncuts)]
+    B_k = np.zeros(kbins, dtype=np.float64)
+    P_k = np.zeros(kbins, dtype=np.float64)
+    sig2 = 0
+    n_box = Ncuts ** 3
+    V_L = (Lx * Ly * Lz)
+    for i in range(n_box):
+        w = np.zeros(cube1.shape)
+        r = rLs[i]
+        w[int(r[0] - Lx / 2):int(r[0] + Lx / 2), int(r[1] - Ly / 2):int(r[1] + Ly / 2), int(r[2] - Lz / 2):int(r[2] + Lz / 2)] = 1
+        c1 = cube1 * w
+        c2 = cube2 * w
+        pk, ks = power_spectrum_1d(c1, kbins=kbins, box_dims=box_dims, binning=binning)
+        d_mean = c2.sum(dtype=np.float64) / V_L
+        B_k += pk * d_mean
+        P_k += pk
+        sig2 += (d_mean) ** 2
+    B_k = B_k / n_box
+    P_k = P_k / n_box
+    sig2 = sig2 / n_box
+    if normalize:
+        with np.errstate(all="ignore"):
+            return B_k / P_k / sig2, ks
+    return B_k, ks
+
+
+def integrated_bispectrum(cube, Ncuts=4, kbins=15, box_dims=244 / .7, binning='log', normalize=False, verbose=True):
+    """Reference ``position_dependent_power_spectrum.py:25-43``."""
+    return integrated_bispectrum_cross(cube, cube, Ncuts=Ncuts, kbins=kbins, box_dims=box_dims, binning=binning,
+                                       normalize=normalize, verbose=verbose)
+
+
+def power_spectrum_response(cube, cube2=None, Ncuts=4, kbins=15, box_dims=244 / .7, binning='log', verbose=True):
+    """Reference ``position_dependent_power_spectrum.py:5-22``."""
+    return integrated_bispectrum_cross(cube, cube if cube2 is None else cube2, Ncuts=Ncuts, kbins=kbins,
+                                       box_dims=box_dims, binning=binning, normalize=True, verbose=verbose)

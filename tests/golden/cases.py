@@ -101,6 +101,12 @@ CASES = [
        los_axis=1, exclude_zero_modes=True),
     _c("mpoles_33_odd", "power_spectrum_multipoles", (33,) * 3, seed=74, dtype="float64", kbins=5, box_dims=50.0, los_axis=0,
        exclude_zero_modes=True),
+    # ---- integrated bispectrum / power-spectrum response ----------------------------
+    _c("ibis_32_c2", "integrated_bispectrum", (32,) * 3, field="toy", seed=81, Ncuts=2, kbins=6, box_dims=100.0, verbose=False),
+    _c("ibisx_32_c4_norm", "integrated_bispectrum_cross", (32,) * 3, field="c2ray", seed=2004, Ncuts=4, kbins=5,
+       box_dims=244 / H, binning="linear", normalize=True, verbose=False),
+    _c("psresp_64_c2", "power_spectrum_response", (64,) * 3, field="toy", seed=82, dtype="float64", Ncuts=2, kbins=8,
+       box_dims=200.0, verbose=False),
     # ---- stand-alone binning of caller-supplied fftshifted arrays ----------
     _c("ravg_3d", "radial_average", (32,) * 3, field="positive", seed=51, box_dims=[200.0] * 3, kbins=8),
     _c("ravg_3d_lin", "radial_average", (33, 32, 16), field="positive", seed=52, box_dims=[100.0, 90.0, 40.0],

@@ -34,6 +34,9 @@ def load_reference():
     import tools21cm.power_legendre as leg  # noqa
     leg._get_mu = lambda k_comp, k, los_axis: ref._get_mu(k_comp, k, los_axis, True)
     ref.power_spectrum_multipoles = leg.power_spectrum_multipoles
+    import tools21cm.position_dependent_power_spectrum as pdp  # noqa
+    for name in ("integrated_bispectrum", "integrated_bispectrum_cross", "power_spectrum_response"):
+        setattr(ref, name, getattr(pdp, name))
     return ref
 
 

@@ -26,6 +26,11 @@ REFERENCE_SIGNATURES = {
     "dimensionless_ps": "(data, kbins=100, box_dims=None, binning='log', factor=10)",
     "power_spectrum_2d": "(input_array, kbins=10, binning='log', box_dims=348.5714285714286, return_modes=False, "
                          "nu_axis=2, window=None, **kwargs)",
+    # position_dependent_power_spectrum.py:5,25,45
+    "power_spectrum_response": "(cube, cube2=None, Ncuts=4, kbins=15, box_dims=348.5714285714286, binning='log', verbose=True)",
+    "integrated_bispectrum": "(cube, Ncuts=4, kbins=15, box_dims=348.5714285714286, binning='log', normalize=False, verbose=True)",
+    "integrated_bispectrum_cross": "(cube1, cube2, Ncuts=4, kbins=15, box_dims=348.5714285714286, binning='log', "
+                                   "normalize=False, verbose=True)",
     # power_legendre.py:4-5
     "power_spectrum_multipoles": "(input_array, kbins=10, box_dims=None, los_axis=0, output=['P0', 'P2', 'P4', 'nmodes'], "
                                  "exclude_zero_modes=False)",

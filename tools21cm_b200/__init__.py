@@ -15,5 +15,8 @@ from .power_spectrum import (  # noqa: F401
 )
 
 from .power_legendre import power_spectrum_multipoles  # noqa: F401  (src/tools21cm/__init__.py:38)
+from .position_dependent_power_spectrum import (  # noqa: F401  (src/tools21cm/__init__.py: from .position_dependent_power_spectrum import *)
+    power_spectrum_response, integrated_bispectrum, integrated_bispectrum_cross,
+)
 
 __version__ = "0.2.0"

@@ -225,6 +225,17 @@ T21_API int t21_bin_multipoles_half(const void* p_half, int dtype, int row_pitch
                                     size_t workspace_bytes, void* stream);
 T21_API size_t t21_bin_multipoles_workspace_bytes(int nk);
 
+/* ---- input side ----
+ * t21_h2d_staged: pageable HOST memory -> device through a pinned ring filled by `threads` host threads (0: choose) while
+ * the previous chunk's DMA runs; returns when the last chunk is queued on `stream`.
+ * t21_f2c: a Fortran-ordered blob (x fastest: xfrac_file.py:62, density_file.py:51) -> C order [nx][ny][nz].
+ * t21_c2ray_dt: calc_dt (temperature.py:51-80, :215-222) fused with that transpose: out[x][y][z] =
+ *   factor * (1 - x_i) * rho from the two blobs as stored (neutral != 0: the first blob holds 1 - x_i). */
+T21_API int t21_h2d_staged(void* dst_dev, const void* src_host, size_t bytes, int threads, void* stream);
+T21_API int t21_f2c(const void* in_f, int dtype, int nx, int ny, int nz, void* out_c, int out_dtype, void* stream);
+T21_API int t21_c2ray_dt(const void* xfrac_f, int xfrac_dtype, int neutral, const void* dens_f, int dens_dtype, double factor,
+                         int nx, int ny, int nz, void* out_c, int out_dtype, void* stream);
+
 T21_API const char* t21_last_error(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 T21_API unsigned long long t21_launch_count(void);

@@ -412,3 +412,69 @@ def power_spectrum_response(cube, cube2=None, Ncuts=4, kbins=15, box_dims=244 / 
     """Reference ``position_dependent_power_spectrum.py:5-22``."""
     return integrated_bispectrum_cross(cube, cube if cube2 is None else cube2, Ncuts=Ncuts, kbins=kbins,
                                        box_dims=box_dims, binning=binning, normalize=True, verbose=verbose)
+
+
+# --------------------------------------------------------------------------
+# input side (SURVEY.md 8f rank 4): C2Ray-format readers, calc_dt, subtract_mean_signal
+# --------------------------------------------------------------------------
+def read_xfrac(filename, old_format=False, neutral=False, binary_format=False):
+    """Reference ``xfrac_file.py:34-73``: header of 3 (binary) or 6 (Fortran unformatted: record markers around the
+    three mesh sizes, then one more marker) int32, float64 (float32 for old files) payload in Fortran order."""
+    with open(filename, 'rb') as f:
+        if binary_format:
+            mesh = np.fromfile(f, count=3, dtype='int32')
+        else:
+            mesh = np.fromfile(f, count=6, dtype='int32')[1:4]
+        xi = np.fromfile(f, dtype='float32' if old_format else 'float64')
+    xi = xi.reshape(tuple(int(m) for m in mesh), order='F')
+    return 1.0 - xi if neutral else xi
+
+
+def read_density(filename):
+    """Reference ``density_file.py:41-57``: three int32 mesh sizes, float32 payload in Fortran order; returns
+    (raw_density, cgs_density) with cgs = raw * rho_crit_0 * (mesh / nbox_fine)**3 * OmegaB (float32 array times a
+    Python float: float32)."""
+    with open(filename, 'rb') as f:
+        mesh = np.fromfile(f, count=3, dtype='int32')
+        raw = np.fromfile(f, dtype='float32')
+    raw = raw.reshape(tuple(int(m) for m in mesh), order='F')
+    return raw, raw * (_RHO_CRIT_0 * (float(mesh[0]) / 8000.0) ** 3 * _OMEGA_B)
+
+
+# const.py:37-111 defaults
+_H = 0.7
+_OMEGA0 = 0.27
+_OMEGA_B = 0.044
+_LAM = 1.0 - _OMEGA0
+_H0CGS = 100.0 * _H * 1e5 / (1e6 * 3.086e18)
+_RHO_CRIT_0 = 3.0 * _H0CGS * _H0CGS / (8.0 * np.pi * 6.6732e-8)
+_LAMBDA0 = 3.0e5 * 1.0e5 / (1.42e3 * 1.0e6)
+_NUM_H_0 = (1 - 0.2486) * _OMEGA_B * _RHO_CRIT_0 / 1.672661e-24
+_MEANDT = 3.0 * _LAMBDA0 ** 3 / (32. * np.pi) * 2.85e-15 * 0.068 * _NUM_H_0 / (_H0CGS / _H) * 1000.
+
+
+def mean_dt(z):
+    """Reference ``temperature.py:200-212``."""
+    Ez = np.sqrt(_OMEGA0 * (1.0 + z) ** 3 + _LAM + (1.0 - _OMEGA0 - _LAM) * (1.0 + z) ** 2)
+    return _MEANDT / _H * (1.0 + z) ** 2 / Ez
+
+
+def calc_dt(xi, rho, z):
+    """Reference ``temperature.py:51-80`` and ``_dt`` ``:215-222`` on arrays."""
+    xi = xi.astype('float64')
+    rho = rho.astype('float64')
+    rho_mean = _RHO_CRIT_0 * _OMEGA_B if rho.min() >= 0 else 1
+    return mean_dt(z) * (1.0 - xi) * rho / rho_mean
+
+
+def subtract_mean_signal(signal, los_axis=2):
+    """Reference ``statistics.py:62-85``."""
+    out = signal.copy()
+    for i in range(signal.shape[los_axis]):
+        if los_axis in [0, -3]:
+            out[i, :, :] -= signal[i, :, :].mean()
+        if los_axis in [1, -2]:
+            out[:, i, :] -= signal[:, i, :].mean()
+        if los_axis in [2, -1]:
+            out[:, :, i] -= signal[:, :, i].mean()
+    return out

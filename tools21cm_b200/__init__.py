@@ -19,4 +19,6 @@ from .position_dependent_power_spectrum import (  # noqa: F401  (src/tools21cm/_
     power_spectrum_response, integrated_bispectrum, integrated_bispectrum_cross,
 )
 
+from .inputs import XfracFile, DensityFile, calc_dt, mean_dt, subtract_mean_signal  # noqa: F401
+
 __version__ = "0.2.0"

@@ -189,6 +189,12 @@ def load():
     lib.t21_bin_multipoles_half.restype = i32
     lib.t21_bin_multipoles_workspace_bytes.argtypes = [i32]
     lib.t21_bin_multipoles_workspace_bytes.restype = sz
+    lib.t21_h2d_staged.argtypes = [vp, vp, sz, i32, vp]
+    lib.t21_h2d_staged.restype = i32
+    lib.t21_f2c.argtypes = [vp, i32, i32, i32, i32, vp, i32, vp]
+    lib.t21_f2c.restype = i32
+    lib.t21_c2ray_dt.argtypes = [vp, i32, i32, vp, i32, dbl, i32, i32, i32, vp, i32, vp]
+    lib.t21_c2ray_dt.restype = i32
     lib.t21_profile.argtypes = [i32]
     lib.t21_profile.restype = i32
     lib.t21_profile_last.argtypes = [C.POINTER(C.c_float), i32]

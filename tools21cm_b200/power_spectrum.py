@@ -156,7 +156,7 @@ def _stage(arr):
         else:
             want = np.dtype(np.float32) if a.dtype == np.float32 else np.dtype(np.float64)
         a = np.ascontiguousarray(a, dtype=want)
-        t = torch.from_numpy(a).to("cuda", non_blocking=False)
+        t = _h2d(a)
     else:
         t = arr
         if _PRECISION is not None:
@@ -171,6 +171,26 @@ def _stage(arr):
     if t.data_ptr() % 16:
         t = t.clone()
     return t, was_numpy
+
+
+def _copy_threads():
+    """Host threads that fill the pinned ring: all cores for one process, a fair share when torchrun put several ranks on
+    the host (LOCAL_WORLD_SIZE)."""
+    import os
+    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    return max(2, min(32, (os.cpu_count() or 8) // ranks))
+
+
+def _h2d(a):
+    """A contiguous numpy array -> a CUDA tensor.  numpy memory is pageable: large arrays go through the library's pinned
+    ring filled by several host threads (t21_h2d_staged) instead of one blocking cudaMemcpy from pageable memory."""
+    torch = _torch()
+    if a.nbytes < (8 << 20) or not a.flags.c_contiguous:
+        return torch.from_numpy(np.ascontiguousarray(a)).to("cuda", non_blocking=False)
+    t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype if a.ndim else torch.from_numpy(a.reshape(1)).dtype, device="cuda")
+    rc = _lib.load().t21_h2d_staged(t.data_ptr(), a.ctypes.data, a.nbytes, _copy_threads(), _stream_ptr(torch, t.device.index))
+    _lib.check(rc, "t21_h2d_staged")
+    return t
 
 
 def _dtype_code(t):

@@ -91,10 +91,12 @@ def test_api_matches_reference_golden(t2c, case, golden):
         assert np.abs(res[0] - want[0]).max() <= tol * np.abs(want[0]).max()
 
 
-@pytest.mark.parametrize("shape", [(12, 20, 30), (1, 64, 64), (5, 7, 9), (250, 8, 16), (8, 250, 16), (16, 8, 250)])
+@pytest.mark.parametrize("shape", [(12, 20, 30), (1, 64, 64), (5, 7, 9), (250, 8, 16), (8, 250, 16), (16, 8, 250),
+                                   (22, 26, 39), (127, 9, 10), (300, 6, 49), (7, 600, 10), (45, 11, 1000)])
 def test_mixed_and_odd_shapes_against_oracle(t2c, shape):
-    """Axes that are not powers of two (C2Ray-like 250, odd light-cone chunks, degenerate axes)
-    go through the generic DFT kernels; any mix with Stockham axes must agree with the oracle."""
+    """Axes that are not powers of two (C2Ray-like 250 / 300 / 600, odd light-cone chunks, degenerate axes) go through the
+    generic kernels -- mixed-radix (2, 3, 4, 5, 7, 11, 13) in shared memory, direct sums for other primes (127); any mix with
+    Stockham axes must agree with the oracle."""
     from oracle import ps_oracle
     x = np.random.default_rng(sum(shape)).standard_normal(shape)
     box = [100.0, 80.0, 120.0]

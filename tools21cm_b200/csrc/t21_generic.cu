@@ -7,12 +7,118 @@
 // own implementation.  They are still CUDA -- there is no CPU path -- but they make no attempt
 // at speed-of-light: each output is a dot product with the n-th roots of unity (index k*j mod n,
 // so the twiddles are exact table entries).
+//
+// Round 2: lengths whose prime factors are all <= 13 (250 = 2 5^3, 300 = 2^2 3 5^2, 600, 1000, odd light-cone chunks
+// like 243 or 315 ...) no longer pay O(n^2): the tile a CTA already holds in shared memory is transformed there by a
+// mixed-radix Stockham FFT (radix 4 / 2 butterflies hard-wired, odd prime radices as small DFTs whose twiddles are
+// exact entries of the same root table), ping-ponging between two buffers.  O(n log n) per pencil, same layout, same
+// epilogues; only lengths with a larger prime factor (127, 509 ...) keep the direct sums.
 #include <string.h>
 #include "t21_launch.cuh"
 
 namespace t21 {
 
 constexpr int kGenThreads = 256;
+
+// ---- mixed-radix FFT of the pencils of a shared-memory tile -----------------------------------------------------------
+struct Factors {
+    int nf;             // 0: not smooth, use the direct sums
+    int radix[24];
+};
+
+static Factors factorize(int n) {
+    Factors f;
+    memset(&f, 0, sizeof(f));
+    if (n < 2) return f;
+    int m = n, k = 0;
+    while (m % 4 == 0) { f.radix[k++] = 4; m /= 4; }
+    for (int p : {2, 3, 5, 7, 11, 13})
+        while (m % p == 0) { f.radix[k++] = p; m /= p; }
+    f.nf = m == 1 ? k : 0;
+    return f;
+}
+
+// one butterfly of radix R on v[0..R-1] (already twiddled), natural order in and out.  Odd R: the R x R DFT with its
+// twiddles w_R^(jk) read from the n-th root table at stride n / R (exact entries), R^2 complex multiply-adds.
+template <int R, typename T>
+__device__ __forceinline__ void small_dft(cx<T>* v, const cx<T>* __restrict__ roots, int n) {
+    if constexpr (R == 2) {
+        const cx<T> a = v[0], b = v[1];
+        v[0] = cadd(a, b); v[1] = csub(a, b);
+    } else if constexpr (R == 4) {
+        const cx<T> a = cadd(v[0], v[2]), b = csub(v[0], v[2]), c = cadd(v[1], v[3]), d = csub(v[1], v[3]);
+        const cx<T> dmi = cmake<T>(d.y, -d.x);                 // -i d
+        v[0] = cadd(a, c); v[2] = csub(a, c); v[1] = cadd(b, dmi); v[3] = csub(b, dmi);
+    } else {
+        cx<T> in[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) in[j] = v[j];
+        const int step = n / R;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            cx<T> acc = in[0];
+            int idx = 0;
+#pragma unroll
+            for (int j = 1; j < R; ++j) {
+                idx += k * step;
+                if (idx >= n) idx -= n;             // k step < n
+                acc = cadd(acc, cmul(in[j], ldg(roots + idx)));
+            }
+            v[k] = acc;
+        }
+    }
+}
+
+template <int R, typename T>
+__device__ __forceinline__ void mixed_stage(const cx<T>* __restrict__ a, cx<T>* __restrict__ b, int n, int ncol, int ns,
+                                            const cx<T>* __restrict__ roots, int tid, int nthreads) {
+    const int nb = n / R;                       // butterflies per pencil
+    const int tstep = n / (ns * R);             // root index of w_(ns R)^1
+    for (int w = tid; w < nb * ncol; w += nthreads) {
+        const int jj = w / ncol, col = w - jj * ncol;
+        const int m = jj % ns;
+        cx<T> v[R];
+        int idx = 0;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            cx<T> x = a[(jj + k * nb) * ncol + col];
+            if (k > 0 && m > 0) {
+                idx += m * tstep;               // k m n / (ns R) < n: a single conditional subtraction keeps it in range
+                if (idx >= n) idx -= n;
+                x = cmul(x, ldg(roots + idx));
+            }
+            v[k] = x;
+        }
+        small_dft<R, T>(v, roots, n);
+        const int base = (jj - m) * R + m;
+#pragma unroll
+        for (int k = 0; k < R; ++k) b[(base + k * ns) * ncol + col] = v[k];
+    }
+}
+
+// transforms the ncol pencils of tile a[n][ncol] (forward, exp(-i ...)); b is scratch of the same size.  All threads of
+// the CTA take part (CTA barriers inside).  Returns the buffer that holds the result (a or b), natural order.
+template <typename T>
+__device__ __forceinline__ cx<T>* mixed_fft(cx<T>* a, cx<T>* b, int n, int ncol, const Factors& f, const cx<T>* __restrict__ roots) {
+    int ns = 1;
+    for (int s = 0; s < f.nf; ++s) {
+        const int R = f.radix[s];
+        const int tid = threadIdx.x, nt = blockDim.x;
+        switch (R) {
+            case 2: mixed_stage<2, T>(a, b, n, ncol, ns, roots, tid, nt); break;
+            case 3: mixed_stage<3, T>(a, b, n, ncol, ns, roots, tid, nt); break;
+            case 4: mixed_stage<4, T>(a, b, n, ncol, ns, roots, tid, nt); break;
+            case 5: mixed_stage<5, T>(a, b, n, ncol, ns, roots, tid, nt); break;
+            case 7: mixed_stage<7, T>(a, b, n, ncol, ns, roots, tid, nt); break;
+            case 11: mixed_stage<11, T>(a, b, n, ncol, ns, roots, tid, nt); break;
+            default: mixed_stage<13, T>(a, b, n, ncol, ns, roots, tid, nt); break;
+        }
+        __syncthreads();
+        cx<T>* t = a; a = b; b = t;
+        ns *= R;
+    }
+    return a;
+}
 
 template <typename T> struct GenWZ { static constexpr int value = sizeof(T) == 4 ? 8 : 4; };
 
@@ -47,14 +153,49 @@ gen_zpass_kernel(const T* __restrict__ in, cx<T>* __restrict__ out, long long nr
     }
 }
 
+// smooth nz: RZ rows at a time as the columns of a [nz][RZ] complex tile (imaginary parts zero), mixed-radix FFT, the
+// first nz/2+1 outputs of every row stored.  (The half-length packing trick of ZPass would halve the work; the real
+// rows of a 250^3 cube are 1 % of a millisecond either way.)
+constexpr int kGenRZ = 8;
+template <typename T>
+__global__ void __launch_bounds__(kGenThreads)
+gen_zpass_fft_kernel(const T* __restrict__ in, cx<T>* __restrict__ out, long long nrows, int nz, int nzh, int ny, long long nxa,
+                     const T* __restrict__ offset, const cx<T>* __restrict__ roots, const __grid_constant__ Factors f) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* ta = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* tb = ta + (size_t)nz * kGenRZ;
+    const T off = offset ? ldg(offset) : (T)0;
+    constexpr int LW = WLay<T>::LW;
+    const long long cstride = nxa * ny * LW;
+    const long long ngroups = (nrows + kGenRZ - 1) / kGenRZ;
+    for (long long g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const long long r0 = g * kGenRZ;
+        __syncthreads();
+        for (int e = threadIdx.x; e < nz * kGenRZ; e += kGenThreads) {
+            const int rr = e / nz, z = e - rr * nz;                   // consecutive threads read consecutive z of one row
+            const long long r = r0 + rr;
+            ta[z * kGenRZ + rr] = cmake<T>(r < nrows ? in[r * nz + z] - off : (T)0, (T)0);
+        }
+        __syncthreads();
+        const cx<T>* res = mixed_fft<T>(ta, tb, nz, kGenRZ, f, roots);
+        for (int e = threadIdx.x; e < nzh * kGenRZ; e += kGenThreads) {
+            const int k = e / kGenRZ, rr = e - k * kGenRZ;
+            const long long r = r0 + rr;
+            if (r >= nrows) continue;
+            const long long x = r / ny, y = r - x * ny;
+            out[(long long)(k / LW) * cstride + (x * ny + y) * LW + (k % LW)] = res[k * kGenRZ + rr];
+        }
+    }
+}
+
 // ---- Y: in-place strided pencils --------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kGenThreads)
 gen_ypass_kernel(cx<T>* __restrict__ w, long long nouter, int ny, int nzh, int pitch,
-                 const cx<T>* __restrict__ roots) {
+                 const cx<T>* __restrict__ roots, const __grid_constant__ Factors f) {
     constexpr int WZ = GenWZ<T>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cx<T>* tile = reinterpret_cast<cx<T>*>(smem_raw);      // [ny][WZ]
+    cx<T>* tile = reinterpret_cast<cx<T>*>(smem_raw);      // [ny][WZ] (+ a second one when the length is smooth)
     const int nchunks = (nzh + WZ - 1) / WZ;
     const long long ntiles = nouter * nchunks;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -70,6 +211,14 @@ gen_ypass_kernel(cx<T>* __restrict__ w, long long nouter, int ny, int nzh, int p
             tile[e] = (chunk * WZ + zl < nzh) ? base[y * stride + zl] : cmake<T>(0, 0);
         }
         __syncthreads();
+        if (f.nf > 0) {
+            const cx<T>* res = mixed_fft<T>(tile, tile + (size_t)ny * WZ, ny, WZ, f, roots);
+            for (int e = threadIdx.x; e < ny * WZ; e += kGenThreads) {
+                const int zl = e % WZ;
+                if (chunk * WZ + zl < nzh) base[(e / WZ) * stride + zl] = res[e];
+            }
+            continue;
+        }
         for (int e = threadIdx.x; e < ny * WZ; e += kGenThreads) {
             const int k = e / WZ, zl = e % WZ;
             if (chunk * WZ + zl >= nzh) continue;
@@ -95,12 +244,13 @@ gen_xpass_kernel(const cx<T>* __restrict__ w0, const cx<T>* __restrict__ w1, int
                  int pitch, const cx<T>* __restrict__ roots, const T* off0, const T* off1, double ntot,
                  const __grid_constant__ t21_binspec B, int nbins, double* __restrict__ part_sum,
                  unsigned* __restrict__ part_cnt, double* gsum, unsigned long long* gcnt, void* nd_out, int nd_f64,
-                 int nd_half, double scale) {
+                 int nd_half, double scale, const __grid_constant__ Factors f) {
     constexpr int WZ = GenWZ<T>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<T>* tile0 = reinterpret_cast<cx<T>*>(smem_raw);                 // [nx][WZ]
     cx<T>* tile1 = tile0 + (NF == 2 ? (size_t)nx * WZ : 0);
-    double* hs = reinterpret_cast<double*>(tile0 + (size_t)NF * nx * WZ);
+    cx<T>* scratch = tile0 + (size_t)NF * nx * WZ;                     // (smooth lengths only) ping-pong partner
+    double* hs = reinterpret_cast<double*>(tile0 + (size_t)(NF + (f.nf > 0 ? 1 : 0)) * nx * WZ);
     unsigned* hc = reinterpret_cast<unsigned*>(hs + (HK == 0 ? nbins : 0));
     if (HK == 0) {
         for (int b = threadIdx.x; b < nbins; b += kGenThreads) { hs[b] = 0.0; hc[b] = 0u; }
@@ -124,12 +274,24 @@ gen_xpass_kernel(const cx<T>* __restrict__ w0, const cx<T>* __restrict__ w1, int
             if (NF == 2) tile1[e] = ok ? w1[o] : cmake<T>(0, 0);
         }
         __syncthreads();
+        const cx<T>* res0 = tile0;
+        const cx<T>* res1 = tile1;
+        if (f.nf > 0) {
+            // the transformed field ends in its own tile or in the scratch buffer; whichever is free serves the next field
+            cx<T>* r0 = mixed_fft<T>(tile0, scratch, nx, WZ, f, roots);
+            res0 = r0;
+            if (NF == 2) res1 = mixed_fft<T>(tile1, r0 == tile0 ? scratch : tile0, nx, WZ, f, roots);
+        }
         for (int e = threadIdx.x; e < nx * WZ; e += kGenThreads) {
             const int ix = e / WZ, zl = e % WZ, iz = chunk * WZ + zl;
             if (iz >= nzh) continue;
             T ar = 0, ai = 0, br = 0, bi = 0;
             int idx = 0;
-            for (int x = 0; x < nx; ++x) {
+            if (f.nf > 0) {
+                ar = res0[e].x; ai = res0[e].y;
+                if (NF == 2) { br = res1[e].x; bi = res1[e].y; }
+            }
+            for (int x = 0; x < (f.nf > 0 ? 0 : nx); ++x) {
                 const cx<T> r = ldg(roots + idx);
                 const cx<T> v = tile0[x * WZ + zl];
                 ar += v.x * r.x - v.y * r.y;
@@ -198,6 +360,21 @@ gen_xpass_kernel(const cx<T>* __restrict__ w0, const cx<T>* __restrict__ w1, int
 template <typename T>
 static int gen_z(const ZArgs& a, cudaStream_t st) {
     const int nzh = a.nz / 2 + 1;
+    const Factors f = factorize(a.nz);
+    const size_t smem_fft = 2 * (size_t)a.nz * kGenRZ * sizeof(cx<T>);
+    if (f.nf > 0 && smem_fft <= 200 * 1024 && !a.window) {
+        auto kern = gen_zpass_fft_kernel<T>;
+        if (int rc = ensure_smem(kern, smem_fft)) return rc;
+        const long long ngroups = (a.nrows + kGenRZ - 1) / kGenRZ;
+        long long g = ngroups < (long long)device_sm_count() * 8 ? ngroups : (long long)device_sm_count() * 8;
+        if (g < 1) return 0;
+        kern<<<(unsigned)g, kGenThreads, smem_fft, st>>>((const T*)a.in, (cx<T>*)a.out, a.nrows, a.nz, nzh, a.ny, a.nxa,
+                                                         (const T*)a.offset, (const cx<T>*)a.twr, f);
+        count_launch();
+        T21_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+    if (a.window) { set_error("windowed passes need power-of-two axes"); return T21_EINVAL; }
     const size_t smem = (size_t)a.nz * sizeof(T);
     auto kern = gen_zpass_kernel<T>;
     if (int rc = ensure_smem(kern, smem)) return rc;
@@ -216,14 +393,16 @@ int launch_zpass_generic(int dtype, const ZArgs& a, cudaStream_t st) {
 template <typename T>
 static int gen_y(const YArgs& a, cudaStream_t st) {
     constexpr int WZ = GenWZ<T>::value;
-    const size_t smem = (size_t)a.ny * WZ * sizeof(cx<T>);
+    size_t smem = (size_t)a.ny * WZ * sizeof(cx<T>);
+    Factors f = factorize(a.ny);
+    if (f.nf > 0 && 2 * smem <= 200 * 1024) smem *= 2; else f.nf = 0;      // smooth length: room for the ping-pong partner
     if (smem > 200 * 1024) { set_error("axis of length %d is too long for the generic pass", a.ny); return T21_EINVAL; }
     auto kern = gen_ypass_kernel<T>;
     if (int rc = ensure_smem(kern, smem)) return rc;
     const long long ntiles = a.nouter * ((a.nzh + WZ - 1) / WZ);
     long long g = ntiles < (long long)device_sm_count() * 8 ? ntiles : (long long)device_sm_count() * 8;
     if (g < 1) return 0;
-    kern<<<(unsigned)g, kGenThreads, smem, st>>>((cx<T>*)a.w, a.nouter, a.ny, a.nzh, a.pitch, (const cx<T>*)a.tw);
+    kern<<<(unsigned)g, kGenThreads, smem, st>>>((cx<T>*)a.w, a.nouter, a.ny, a.nzh, a.pitch, (const cx<T>*)a.tw, f);
     count_launch();
     T21_CUDA_OK(cudaGetLastError());
     return 0;
@@ -238,7 +417,11 @@ static int gen_x(XArgs& a, cudaStream_t st) {
     const bool is_bin = a.bins != nullptr;
     const int hk = !is_bin ? 2 : (a.hist_global ? 1 : 0);
     size_t smem = (size_t)NF * a.nx * WZ * sizeof(cx<T>);
-    if (hk == 0) smem += (size_t)a.nbins * (sizeof(double) + sizeof(unsigned));
+    const size_t hist = hk == 0 ? (size_t)a.nbins * (sizeof(double) + sizeof(unsigned)) : 0;
+    Factors f = factorize(a.nx);
+    if (f.nf > 0 && smem + (size_t)a.nx * WZ * sizeof(cx<T>) + hist <= 200 * 1024) smem += (size_t)a.nx * WZ * sizeof(cx<T>);
+    else f.nf = 0;
+    smem += hist;
     if (smem > 200 * 1024) { set_error("axis of length %d is too long for the generic pass", a.nx); return T21_EINVAL; }
     const long long ntiles = (long long)a.ny * ((a.nzh + WZ - 1) / WZ);
     long long g = ntiles < (long long)device_sm_count() * 4 ? ntiles : (long long)device_sm_count() * 4;
@@ -253,7 +436,7 @@ static int gen_x(XArgs& a, cudaStream_t st) {
         if (int rc = ensure_smem(kern, smem)) return rc;                                                        \
         kern<<<(unsigned)g, kGenThreads, smem, st>>>((const cx<T>*)a.w[0], (const cx<T>*)a.w[1], a.nx, a.ny, a.nz,  \
             a.nzh, a.pitch, (const cx<T>*)a.tw, (const T*)a.offset[0], (const T*)a.offset[1], a.ntot, B,        \
-            a.nbins, a.part_sum, a.part_cnt, a.gsum, a.gcnt, a.nd_out, a.nd_f64, a.nd_half, a.scale);                      \
+            a.nbins, a.part_sum, a.part_cnt, a.gsum, a.gcnt, a.nd_out, a.nd_f64, a.nd_half, a.scale, f);                      \
     }
     if (hk == 0) T21_GEN_X(0) else if (hk == 1) T21_GEN_X(1) else T21_GEN_X(2)
 #undef T21_GEN_X

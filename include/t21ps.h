@@ -164,9 +164,11 @@ T21_API int t21_peer_wait(const void* my_buf, int nranks, unsigned long long epo
 /* Assembles the fftshifted n-D power of a slab-sharded cube from every rank's half spectrum (t21_slab_stage2_nd):
  * half[nx][ny/P][row_pitch] -> outs_dev[r] = rank r's output [nx][ny/P][nz] (peer-mapped; a DEVICE array of nranks
  * addresses).  A rank writes the kz >= 0 part of its own rows and stores the mirrored kz < 0 part straight into the
- * output of the rank that owns row -ky.  Follow it with a barrier (t21_peer_signal / t21_peer_wait) before reading. */
+ * output of the rank that owns row -ky.  Follow it with a barrier (t21_peer_signal / t21_peer_wait) before reading.
+ * Rows keep their FFT order along y (the caller knows which ky each local row is); with ONE rank, shift_y != 0 shifts
+ * that axis too, which makes `outs_dev[0]` the complete fftshifted array of power_spectrum_nd (power_spectrum.py:45). */
 T21_API int t21_nd_assemble(const void* half, int dtype, int nx, int nyl, int nz, int row_pitch, int iy0, int ny_global,
-                            void* const* outs_dev, int nranks, int rank, void* stream);
+                            void* const* outs_dev, int nranks, int rank, int shift_y, void* stream);
 /* c ~ mean(x) of n elements from a strided sample, written to a device scalar of x's type (the offset of the passes) */
 T21_API int t21_mean_estimate(const void* x, long long n, int dtype, void* out_dev, void* stream);
 T21_API int t21_slab_stage1_p2p(const t21_plan* plan_slab, const void* x_slab, const void* offset_or_null,

@@ -65,4 +65,12 @@ if args.quick:
     sys.exit(0)
 out["power_spectrum_nd"] = timed(lambda: t2c.power_spectrum_nd(a, box_dims=L))
 out["power_spectrum_2d"] = timed(lambda: t2c.power_spectrum_2d(a, kbins=10, box_dims=L))
+out["power_spectrum_multipoles_los0"] = timed(lambda: t2c.power_spectrum_multipoles(a, kbins=15, box_dims=L, los_axis=0))
+out["power_spectrum_multipoles_los2"] = timed(lambda: t2c.power_spectrum_multipoles(a, kbins=15, box_dims=L, los_axis=2))
+if n >= 256:
+    import time
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    t2c.integrated_bispectrum(a, Ncuts=4, kbins=15, box_dims=L, verbose=False)
+    torch.cuda.synchronize()
+    out["integrated_bispectrum_Ncuts4_64_subboxes"] = (time.perf_counter() - t0) * 1e3
 print(json.dumps(out))

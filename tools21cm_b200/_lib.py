@@ -161,7 +161,7 @@ def load():
     lib.t21_peer_signal.restype = i32
     lib.t21_peer_wait.argtypes = [vp, i32, C.c_ulonglong, vp, dbl, vp]
     lib.t21_peer_wait.restype = i32
-    lib.t21_nd_assemble.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, i32, vp]
+    lib.t21_nd_assemble.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, i32, i32, vp]
     lib.t21_nd_assemble.restype = i32
     lib.t21_mean_estimate.argtypes = [vp, C.c_longlong, i32, vp, vp]
     lib.t21_mean_estimate.restype = i32

@@ -61,7 +61,7 @@ peer_wait_kernel(const void* mine, int nranks, unsigned long long epoch, int* __
 template <typename T>
 __global__ void __launch_bounds__(256)
 nd_assemble_kernel(const T* __restrict__ half, int nx, int nyl, int nz, int pitch, int iy0, int ny, void* const* __restrict__ outs,
-                   int rank) {
+                   int rank, int shift_y) {
     const int lane = threadIdx.x & 31;
     const long long nrows = (long long)nx * nyl;
     const long long w0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = (long long)gridDim.x * (blockDim.x >> 5);
@@ -72,8 +72,10 @@ nd_assemble_kernel(const T* __restrict__ half, int nx, int nyl, int nz, int pitc
         const int sx = (ix + nx / 2) % nx, sxm = ((nx - ix) % nx + nx / 2) % nx;
         const int iym = (ny - (iy0 + j)) % ny, rm = iym / nyl, jm = iym - rm * nyl;
         const T* src = half + r * pitch;
-        T* lo = out_mine + ((long long)sx * nyl + j) * nz;
-        T* mi = static_cast<T*>(outs[rm]) + ((long long)sxm * nyl + jm) * nz;
+        // one rank holding every row (shift_y): the rows are fftshifted along y as well
+        const int jo = shift_y ? (j + ny / 2) % ny : j, jmo = shift_y ? (jm + ny / 2) % ny : jm;
+        T* lo = out_mine + ((long long)sx * nyl + jo) * nz;
+        T* mi = static_cast<T*>(outs[rm]) + ((long long)sxm * nyl + jmo) * nz;
         for (int kz = lane; kz <= nneg; kz += 32) lo[cz + kz] = src[kz];
         if (nz % 2 == 0 && lane == 0) lo[0] = src[nz / 2];                     // the Nyquist plane sits at index 0
         for (int kz = 1 + lane; kz <= nneg; kz += 32) mi[cz - kz] = src[kz];
@@ -115,18 +117,18 @@ int t21_peer_wait(const void* my_buf, int nranks, unsigned long long epoch, int*
 }
 
 int t21_nd_assemble(const void* half, int dtype, int nx, int nyl, int nz, int row_pitch, int iy0, int ny_global,
-                    void* const* outs_dev, int nranks, int rank, void* stream) {
+                    void* const* outs_dev, int nranks, int rank, int shift_y, void* stream) {
     if (!half || !outs_dev || nx < 1 || nyl < 1 || nz < 1 || row_pitch < nz / 2 + 1 || nranks < 1 || rank < 0 || rank >= nranks ||
-        ny_global != nyl * nranks || iy0 != rank * nyl || (dtype != T21_F32 && dtype != T21_F64)) {
+        ny_global != nyl * nranks || iy0 != rank * nyl || (dtype != T21_F32 && dtype != T21_F64) || (shift_y && nranks != 1)) {
         set_error("bad argument to t21_nd_assemble"); return T21_EINVAL;
     }
     long long g = ((long long)nx * nyl + 7) / 8;
     const long long cap = (long long)device_sm_count() * 8;
     if (g > cap) g = cap;
     if (dtype == T21_F32)
-        nd_assemble_kernel<float><<<(int)g, 256, 0, (cudaStream_t)stream>>>((const float*)half, nx, nyl, nz, row_pitch, iy0, ny_global, outs_dev, rank);
+        nd_assemble_kernel<float><<<(int)g, 256, 0, (cudaStream_t)stream>>>((const float*)half, nx, nyl, nz, row_pitch, iy0, ny_global, outs_dev, rank, shift_y);
     else
-        nd_assemble_kernel<double><<<(int)g, 256, 0, (cudaStream_t)stream>>>((const double*)half, nx, nyl, nz, row_pitch, iy0, ny_global, outs_dev, rank);
+        nd_assemble_kernel<double><<<(int)g, 256, 0, (cudaStream_t)stream>>>((const double*)half, nx, nyl, nz, row_pitch, iy0, ny_global, outs_dev, rank, shift_y);
     count_launch();
     T21_CUDA_OK(cudaGetLastError());
     return T21_OK;

@@ -579,7 +579,7 @@ def _sharded_nd(slabs, box_dims, out_dtype, group, backend, copy=True):
         out, tab = peer.nd_out((nx, nyl, nz), out_dtype)
         base = half._base if half._base is not None else half
         rc = _lib.load().t21_nd_assemble(base.data_ptr(), _lib.T21_F32 if out_dtype == torch.float32 else _lib.T21_F64,
-                                         nx, nyl, nz, int(base.shape[2]), rank * nyl, ny, tab.data_ptr(), world, rank,
+                                         nx, nyl, nz, int(base.shape[2]), rank * nyl, ny, tab.data_ptr(), world, rank, 0,
                                          C.c_void_p(torch.cuda.current_stream(out.device).cuda_stream))
         _lib.check(rc, "t21_nd_assemble")
         peer.gather(None)                                          # every rank's mirrored rows have landed

@@ -16,6 +16,7 @@ struct YArgs {
     void* w; long long nouter; int ny; int nzh; int pitch; const void* tw;
     void* send; int nyl_log2;          // slab mode: packed all-to-all send buffer (or null)
     void* const* peers; int npeers; long long xg0; long long nx_global;   // fused exchange: peer y-slab buffers (or null)
+    long long nxa;                     // x planes in the allocation `w` points into (0: nouter) -- plane-group launches
 };
 struct XArgs {
     const void* w[2]; int nf; int nx, ny, nz, nzh, pitch; int xs_log2; int iy0;   // xs_log2: log2(x planes per slab), <0 = one slab

@@ -36,7 +36,7 @@ static int launch_ypass_t(const YArgs& a, cudaStream_t st) {
         typename K::Params p;                                                            \
         memset(&p, 0, sizeof(p));                                                        \
         p.w = (cx<T>*)a.w; p.nzh = a.nzh; p.pitch = a.pitch; p.nchunks = nchunks;        \
-        p.cstride = a.nouter * a.ny * WLay<T>::LW; p.tw = (const cx<T>*)a.tw;            \
+        p.cstride = (a.nxa ? a.nxa : a.nouter) * a.ny * WLay<T>::LW; p.tw = (const cx<T>*)a.tw; \
         p.nouter = a.nouter;                                                             \
         return launch_tiles<K, T>(p, a.nouter * nchunks, st);                            \
     }

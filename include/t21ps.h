@@ -83,7 +83,22 @@ typedef struct t21_binspec {
     const float* k_hi_f;
     const float* mu_lo_f;
     const float* mu_hi_f;
+    /* Optional pencil segment table of the warp-per-pencil X pass (t21_build_pencil_segments), or NULL.
+     * seg_tab[(iy * (n[2]/2+1) + iz) * seg_stride + j] = (p_j << 16) | (bin_j + 1): along the x pencil (iy, iz) the
+     * modes with p_j <= |kx index| < p_{j+1} fall in flat bin bin_j (-1: none); p_0 = 0; unused entries 0xFFFF0000. */
+    const uint32_t* seg_tab;
+    int32_t seg_stride;   /* entries per pencil: 8, 16 or 32 */
 } t21_binspec;
+
+/* Bins are index ranges along an x pencil: for fixed (ky, kz), k only grows with |kx| and so does |mu| when the line of
+ * sight is x (it only falls otherwise), and a mode and its mirror -kx share a bin unless mu is signed.  This builds, once
+ * per (shape, bin spec), the table of those ranges for every pencil of the computed half spectrum -- with the very
+ * classification every other kernel uses per mode (float64 sequence of power_spectrum.py:477,498 where the fp32
+ * look-up cannot decide) -- so that the X pass adds whole ranges instead of classifying 10^9 modes per cube.
+ * `spec` must be in FFT index order with shells or |mu| bins (absolute_mus != 0).  out: ny * (nz/2+1) * stride uint32
+ * (device).  max_segments_dev (device int): largest number of ranges any pencil needs; a value above `stride` means
+ * the table is unusable (rebuild with a larger stride, 32 at most; above 32 the X pass classifies per mode). */
+T21_API int t21_build_pencil_segments(const t21_binspec* spec, uint32_t* out, int stride, int* max_segments_dev, void* stream);
 
 /* Plan for real cubes of shape (nx, ny, nz), C order.  dtype T21_F32 / T21_F64 is the
  * arithmetic type of the transform.  Replaces the implicit scipy.fftpack plan behind

@@ -45,6 +45,8 @@ class BinSpecC(C.Structure):
         ("k_hi_f", C.c_void_p),
         ("mu_lo_f", C.c_void_p),
         ("mu_hi_f", C.c_void_p),
+        ("seg_tab", C.c_void_p),
+        ("seg_stride", C.c_int32),
     ]
 
 
@@ -195,6 +197,8 @@ def load():
     lib.t21_f2c.restype = i32
     lib.t21_c2ray_dt.argtypes = [vp, i32, i32, vp, i32, dbl, i32, i32, i32, vp, i32, vp]
     lib.t21_c2ray_dt.restype = i32
+    lib.t21_build_pencil_segments.argtypes = [C.POINTER(BinSpecC), vp, i32, vp, vp]
+    lib.t21_build_pencil_segments.restype = i32
     lib.t21_profile.argtypes = [i32]
     lib.t21_profile.restype = i32
     lib.t21_profile_last.argtypes = [C.POINTER(C.c_float), i32]

@@ -385,6 +385,15 @@ static int ps_nd_impl(const t21_plan* p, const void* x1, const void* x2, int sub
     return rc;
 }
 
+int t21_build_pencil_segments(const t21_binspec* spec, uint32_t* out, int stride, int* max_segments_dev, void* stream) {
+    if (!spec || !out || !max_segments_dev) { set_error("null argument to t21_build_pencil_segments"); return T21_EINVAL; }
+    if (stride != 8 && stride != 16 && stride != 32) { set_error("segment stride must be 8, 16 or 32"); return T21_EINVAL; }
+    if (spec->nmu > 0 && !spec->absolute_mus) { set_error("signed mu bins are not even in kx: no segment table"); return T21_EINVAL; }
+    if (spec->zero_idx[0] != 0 || spec->n[0] < 2 || spec->n[0] >= 65535) { set_error("segment tables need a spec in FFT index order"); return T21_EINVAL; }
+    if (spec->nk * (spec->nmu > 0 ? spec->nmu : 1) >= 65535) { set_error("too many bins for a segment table"); return T21_EINVAL; }
+    return launch_pencil_segments(*spec, out, stride, max_segments_dev, (cudaStream_t)stream);
+}
+
 int t21_profile(int enable) {
     g_prof.on = enable != 0;
     return T21_OK;

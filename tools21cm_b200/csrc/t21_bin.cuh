@@ -132,6 +132,32 @@ T21_HD ModeBins classify(const t21_binspec& B, int ix, int iy, int iz, bool has_
     return r;
 }
 
+// ---- pencil segment table (warp-per-pencil X pass) ------------------------------------------------------------------
+// Along the x pencil (iy, iz) the bin of a mode changes only a few times: k grows with |kx| and mu is monotonic in it.
+// The table lists the ranges: entry j = (p_j << 16) | (bin_j + 1), modes p_j <= |kx index| < p_{j+1} fall in bin_j.
+// It is built by running classify() -- the per-mode classification every other kernel uses -- over |kx| = 0 .. nx/2 of
+// the pencil and cutting wherever its answer changes: no monotonicity is assumed, only counted on for the table to be
+// short.  The mirror mode nx - f must agree (shells and |mu| bins are even in kx; signed mu is refused by the caller):
+// a pencil where it does not, or with more than `stride` ranges, reports stride + 1 and the table is not used.
+constexpr unsigned kSegSentinel = 0xFFFF0000u;
+T21_HD int build_pencil_segments(const t21_binspec& B, int iy, int iz, unsigned* __restrict__ out, int stride) {
+    const int nx = B.n[0], nz = B.n[2];
+    const bool has_twin = (iz != 0) && (iz != nz - iz);
+    int s = 0, prev = -2;
+    bool bad = false;
+    for (int f = 0; f <= nx / 2; ++f) {
+        const int b = classify(B, f, iy, iz, has_twin).own;
+        if (f > 0 && f < nx - f && classify(B, nx - f, iy, iz, has_twin).own != b) bad = true;
+        if (b != prev) {
+            if (s < stride) out[s] = ((unsigned)f << 16) | (unsigned)(b + 1);
+            ++s;
+            prev = b;
+        }
+    }
+    for (int j = s; j < stride; ++j) out[j] = kSegSentinel;
+    return (bad || s > stride) ? stride + 1 : s;
+}
+
 // ---- accumulators ---------------------------------------------------------------------
 // RunAcc: per-thread run-length accumulator.  Used where one thread walks modes whose bin
 // changes slowly (t21_bin_only: consecutive z samples) and by the CPU replay of the X pass.

@@ -46,6 +46,8 @@ struct Params {
     const float* offset;   // mean offset (device scalar) or null
     double ntot;
     t21_binspec bins;
+    const unsigned* seg;   // pencil segment table (t21_build_pencil_segments) or null
+    int seg_stride;
 };
 
 #if T21_DEVICE_CODE
@@ -213,7 +215,95 @@ __device__ __forceinline__ void epilogue_shells(const Params& p, const cx<float>
     __syncwarp();
 }
 
+// ---- bins as index ranges from the pencil segment table (shells and |mu| bins) -----------------------------------------
+// Lane j holds entry j of the pencil's table: range j starts at |kx| = pos_j and falls in bin binp1_j - 1.  A step of
+// 64 modes (|kx| in [32k, 32k + 32]) no range boundary falls into is added whole, as two packed FMAs per lane; a step
+// that holds a boundary parks the running sum and its two powers in a lane-private strip of shared memory, and a
+// rolled loop then closes the ranges in order: every lane adds its modes below the boundary, one shuffle tree sums the
+// range over the warp, lane 0 adds it -- and the closed-form mode count of the range -- to the warp's histogram.
+constexpr int kSlots = 8;                            // boundary steps per half pencil (there are 8 steps in a half)
 template <class Hist>
+__device__ __forceinline__ void epilogue_segments(const Params& p, cx<float>* v, int lane, int iy, int iz, unsigned ent,
+                                                  float* __restrict__ strip, Hist& hist) {
+    const bool has_twin = (iz != 0) && (iz != p.nz - iz);
+    const unsigned wt = has_twin ? 2u : 1u;
+    const float wf = (float)wt;
+    const unsigned pos = ent >> 16, binp1 = ent & 0xFFFFu;
+    const unsigned S = (unsigned)__popc(__ballot_sync(0xffffffffu, pos != 0xFFFFu));
+    const unsigned mixed = __reduce_or_sync(0xffffffffu, ((unsigned)lane >= 1u && (unsigned)lane < S) ? 1u << ((pos - 1u) >> 5) : 0u);
+
+    if (iy == 0 && iz == 0) {
+        // DC of (x - c) plus c*N: the only sample the mean offset changes.  It stays in the flow with power 0 (so
+        // that it is counted like any other mode); its true power goes to the histogram here, with count 0.
+        const int b0 = (int)__shfl_sync(0xffffffffu, binp1, 0) - 1;
+        if (lane == 0) {
+            const double c0 = p.offset ? (double)ldg(p.offset) : 0.0;
+            const double ra = (double)v[0].x + c0 * p.ntot;
+            const double dc = ra * ra + (double)v[0].y * (double)v[0].y;
+            v[0] = cmake<float>(0.f, 0.f);
+            if (b0 >= 0) hist.add(b0, dc, 0u);
+        }
+    }
+
+    float cur = 0.f;
+    unsigned j = 0u;
+    unsigned nextpos = S > 1u ? __shfl_sync(0xffffffffu, pos, 1) : 0xFFFFu;
+    // close range j at boundary b (exclusive end): sum over the warp, lane 0 books it
+    auto close = [&](unsigned b) {
+        float t = cur;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        const unsigned a = __shfl_sync(0xffffffffu, pos, j);
+        const int bin = (int)__shfl_sync(0xffffffffu, binp1, j) - 1;
+        if (lane == 0 && bin >= 0) {
+            const unsigned cnt = 2u * (b - a) - (a == 0u ? 1u : 0u) - (b == (unsigned)(NX / 2 + 1) ? 1u : 0u);
+            hist.add(bin, (double)(t * wf), cnt * wt);
+        }
+    };
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        cx<float> run2 = cmake<float>(0.f, 0.f);
+        unsigned slot = 0u, ks = 0u;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const int k = half * 8 + kk;
+            if ((mixed >> k) & 1u) {
+                float* d = strip + slot * 96u + lane;
+                d[0] = run2.x + run2.y;
+                d[32] = v[k].x * v[k].x + v[k].y * v[k].y;
+                d[64] = v[31 - k].x * v[31 - k].x + v[31 - k].y * v[31 - k].y;
+                run2 = cmake<float>(0.f, 0.f);
+                ks |= (unsigned)k << (4u * slot);
+                ++slot;
+            } else {
+                run2 = fma2(v[k], v[k], run2);
+                run2 = fma2(v[31 - k], v[31 - k], run2);
+            }
+        }
+        // (every lane reads back only what it wrote itself: no warp synchronisation needed)
+#pragma unroll 1
+        for (unsigned i = 0; i < slot; ++i) {
+            const float* d = strip + i * 96u + lane;
+            cur += d[0];
+            float plo = d[32], phi = d[64];
+            const unsigned k32 = ((ks >> (4u * i)) & 15u) << 5;
+            const unsigned flo = k32 + (unsigned)lane, fhi = k32 + 32u - (unsigned)lane;
+            while (nextpos <= k32 + 32u) {                  // warp-uniform: a boundary inside this step
+                if (flo < nextpos) { cur += plo; plo = 0.f; }
+                if (fhi < nextpos) { cur += phi; phi = 0.f; }
+                close(nextpos);
+                cur = 0.f;
+                ++j;
+                nextpos = j + 1u < S ? __shfl_sync(0xffffffffu, pos, (j + 1u) & 31u) : 0xFFFFu;
+            }
+            cur += plo + phi;
+        }
+        cur += run2.x + run2.y;
+    }
+    close((unsigned)(NX / 2 + 1));
+}
+
+template <bool SEG, class Hist>
 __device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& p, unsigned char* smem_raw, Hist& hist, int nbins) {
     cx<float>* buf = reinterpret_cast<cx<float>*>(smem_raw);
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + BAR_OFF);
@@ -245,6 +335,10 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& 
         const unsigned chunk = (unsigned)tile / (unsigned)p.ny;
         const int iy = (int)((unsigned)tile - chunk * (unsigned)p.ny) + p.iy0;
         cx<float> v[32];
+        const int iz = (int)chunk * WZ + warp;
+        // this pencil's ranges: asked for now, needed after the two butterfly stages
+        unsigned ent = kSegSentinel;
+        if (SEG && lane < p.seg_stride && iz < p.nzh) ent = ldg(p.seg + ((size_t)iy * p.nzh + iz) * p.seg_stride + lane);
         mbar_wait(bar, parity);
         parity ^= 1u;
         // stage 0: rows j0 + 32 k of column zl0 from the landed [x][8] tile
@@ -276,10 +370,13 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& 
 #pragma unroll
         for (int k = 1; k < 32; ++k) v[k] = cmul(v[k], ldg(p.tw + (k - 1) * 32 + lane));
         DFT<32, float>::run(v);                            // v[k] = X[lane + 32 k]
-        const int iz = (int)chunk * WZ + warp;
-        if (iz < p.nzh) epilogue_shells(p, v, lane, iy, iz, reinterpret_cast<float*>(smem_raw + STAGE_OFF) + warp * 1024, wbc, hist);
+        if (iz < p.nzh) {
+            float* stage = reinterpret_cast<float*>(smem_raw + STAGE_OFF) + warp * 1024;
+            if constexpr (SEG) epilogue_segments(p, v, lane, iy, iz, ent, stage, hist);
+            else epilogue_shells(p, v, lane, iy, iz, stage, wbc, hist);
+        }
     }
-    wbc_flush(wbc, hist);
+    if constexpr (!SEG) wbc_flush(wbc, hist);
 }
 
 #endif  // T21_DEVICE_CODE
@@ -287,6 +384,7 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& 
 // The histogram (at most 31 bins) lives in shared memory, one copy per warp: only lane 0 of the owning warp writes
 // it, in program order; warps are summed in order here and CTAs in order by reduce_partials_kernel, so the result
 // is bit-reproducible run to run.
+template <bool SEG>
 __global__ void __launch_bounds__(THREADS, 2)
 xpass32_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ Params p, int nbins,
                double* __restrict__ part_sum, unsigned* __restrict__ part_cnt) {
@@ -303,7 +401,7 @@ xpass32_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ 
     for (int b = tid; b < NW * nbins; b += THREADS) { hs[b] = 0.0; hc[b] = 0u; }
     __syncthreads();
     WarpPrivHist hist{hs + (size_t)(tid >> 5) * nbins, hc + (size_t)(tid >> 5) * nbins};
-    run_tiles(&map, p, smem_raw, hist, nbins);
+    run_tiles<SEG>(&map, p, smem_raw, hist, nbins);
     __syncthreads();
     for (int b = tid; b < nbins; b += THREADS) {
         double s = 0.0;
@@ -313,6 +411,12 @@ xpass32_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ 
         part_cnt[(size_t)blockIdx.x * nbins + b] = c;
     }
 #endif
+}
+
+// T21_X32_SEGMENTS=0 keeps the in-kernel boundary search even when the spec carries a table (A/B runs); read once
+static bool use_segments() {
+    static const bool on = [] { const char* e = getenv("T21_X32_SEGMENTS"); return !(e && e[0] == '0'); }();
+    return on;
 }
 
 static int launch(XArgs& a, cudaStream_t st) {
@@ -328,11 +432,14 @@ static int launch(XArgs& a, cudaStream_t st) {
     p.offset = (const float*)a.offset[0];
     p.ntot = a.ntot;
     p.bins = *a.bins;
+    p.seg = a.bins->seg_tab;
+    p.seg_stride = a.bins->seg_stride;
+    const bool seg = p.seg != nullptr && use_segments();
     CUtensorMap map;
     if (int rc = make_wmap_f32(&map, a.w[0], nxs, a.ny, a.pitch / WZ, NX / nxs, p.box_rows)) return rc;
 
     const size_t smem = HIST_OFF + (size_t)(THREADS / 32) * a.nbins * 12;
-    auto kern = xpass32_kernel;
+    auto kern = seg ? xpass32_kernel<true> : xpass32_kernel<false>;
     if (int rc = ensure_smem(kern, smem)) return rc;
     int occ = 0;
     T21_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
@@ -354,8 +461,12 @@ bool xpass32_applicable(int dtype, const XArgs& a) {
     // bins were tried here with the guard-interval cache of XPass: a warp that walks a whole pencil crosses ~7
     // (k, mu) bins per pencil and a two-entry cache thrashes -- 9.1 ms against 6.0 ms at 1024^3; it needs the
     // boundary form with host-built mu thresholds, which is not written.)
-    return dtype == T21_F32 && a.nx == x32::NX && a.nf == 1 && a.bins != nullptr && a.tw32 != nullptr && a.pitch % x32::WZ == 0 &&
-           a.bins->nmu == 0 && a.bins->nk <= 31 && !a.hist_global;
+    if (!(dtype == T21_F32 && a.nx == x32::NX && a.nf == 1 && a.bins != nullptr && a.tw32 != nullptr && a.pitch % x32::WZ == 0 &&
+          !a.hist_global))
+        return false;
+    if (a.bins->seg_tab != nullptr && x32::use_segments())       // bins as table-driven index ranges: shells and |mu| bins
+        return a.nbins <= 128 && (a.bins->nmu == 0 || a.bins->absolute_mus != 0);
+    return a.bins->nmu == 0 && a.bins->nk <= 31;
 }
 
 int launch_xpass32_bin(XArgs& a, cudaStream_t st) {

@@ -16,6 +16,7 @@ uses float64; ``set_precision`` overrides the choice).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -91,10 +92,12 @@ class _Device:
             t = self._scratch[key] = torch.empty(n, dtype=dtype, device="cuda:%d" % self.index)
         return t[:n].view(shape)
 
-    def spec(self, key, builder):
+    def spec(self, key, builder, segments=False):
         hit = self.specs.get(key)
         if hit is not None:
             self.specs.move_to_end(key)
+            if segments:
+                self._attach_segments(hit)
             return hit
         torch = _torch()
         spec = builder()
@@ -104,11 +107,48 @@ class _Device:
             return t.data_ptr(), t
 
         cspec, owner = _lib.pack_binspec(spec, upload)
-        hit = (spec, cspec, owner)
+        hit = (spec, cspec, [owner])
         self.specs[key] = hit
         while len(self.specs) > 64:
             self.specs.popitem(last=False)
+        if segments:
+            self._attach_segments(hit)
         return hit
+
+    def _attach_segments(self, hit):
+        """The pencil segment table of the warp-per-pencil X pass (``t21_build_pencil_segments``): along an x pencil the
+        bins are index ranges, found once per (shape, bin spec) on the device with the per-mode classification of the
+        other kernels and kept with the cached spec -- plan data like the twiddle tables, 8-32 entries per pencil.
+        Only shapes that kernel takes (nx = 1024) and bins that are even in kx (shells, |mu|) get one."""
+        spec, cspec, owners = hit
+        if getattr(spec, "_segments_tried", False):
+            return
+        spec._segments_tried = True
+        if os.environ.get("T21_X32_SEGMENTS", "1") == "0":
+            return
+        if spec.shape[0] != 1024 or spec.nbins > 128 or (spec.nmu and not spec.absolute_mus) or int(spec.zero_idx[0]) != 0:
+            return
+        torch = _torch()
+        lib = _lib.load()
+        dev = "cuda:%d" % self.index
+        npencils = int(spec.shape[1]) * (int(spec.shape[2]) // 2 + 1)
+        maxseg = torch.zeros(1, dtype=torch.int32, device=dev)
+        stream = _stream_ptr(torch, self.index)
+        stride, table = 32, None
+        for _ in range(2):
+            table = torch.empty(npencils * stride, dtype=torch.int32, device=dev)
+            _lib.check(lib.t21_build_pencil_segments(C.byref(cspec), table.data_ptr(), stride, maxseg.data_ptr(), stream),
+                       "t21_build_pencil_segments")
+            m = int(maxseg.item())
+            if m > stride:
+                return                      # some pencil needs more ranges than the table holds: classify per mode
+            want = 8 if m <= 8 else (16 if m <= 16 else 32)
+            if want == stride:
+                break
+            stride = want
+        owners.append(table)
+        cspec.seg_tab = table.data_ptr()
+        cspec.seg_stride = stride
 
 
     def cyl(self, key, builder):
@@ -220,7 +260,8 @@ def _fused_binned(fields, spec_key, spec_builder):
         lib = _lib.load()
         code = _dtype_code(x)
         plan = dev.plan(tuple(x.shape), code)
-        spec, cspec, _owner = dev.spec((tuple(x.shape), spec_key), spec_builder)
+        spec, cspec, _owner = dev.spec((tuple(x.shape), spec_key), spec_builder,
+                                       segments=(code == T21_F32 and len(fields) == 1))
         nb = spec.nbins
         need = lib.t21_workspace_bytes(plan, len(fields), nb)
         ws = dev.workspace(need)

@@ -88,6 +88,7 @@ typedef struct t21_binspec {
      * modes with p_j <= |kx index| < p_{j+1} fall in flat bin bin_j (-1: none); p_0 = 0; unused entries 0xFFFF0000. */
     const uint32_t* seg_tab;
     int32_t seg_stride;   /* entries per pencil: 8, 16 or 32 */
+    int32_t seg_ntab;     /* 1 (shells, |mu|) or 4 (signed mu: own bin for kx >= 0, own for kx < 0, twin's bin for each) */
 } t21_binspec;
 
 /* Bins are index ranges along an x pencil: for fixed (ky, kz), k only grows with |kx| and so does |mu| when the line of
@@ -95,8 +96,9 @@ typedef struct t21_binspec {
  * per (shape, bin spec), the table of those ranges for every pencil of the computed half spectrum -- with the very
  * classification every other kernel uses per mode (float64 sequence of power_spectrum.py:477,498 where the fp32
  * look-up cannot decide) -- so that the X pass adds whole ranges instead of classifying 10^9 modes per cube.
- * `spec` must be in FFT index order with shells or |mu| bins (absolute_mus != 0).  out: ny * (nz/2+1) * stride uint32
- * (device).  max_segments_dev (device int): largest number of ranges any pencil needs; a value above `stride` means
+ * `spec` must be in FFT index order.  out: T * ny * (nz/2+1) * stride uint32 (device), T = 1 table for shells and |mu|
+ * bins (even in kx), T = 4 consecutive tables for signed mu (the stored mode's own bin for kx = +f and for kx = -f, then
+ * the bin of its Hermitian twin for each; seg_ntab).  max_segments_dev (device int): largest number of ranges any pencil needs; a value above `stride` means
  * the table is unusable (rebuild with a larger stride, 32 at most; above 32 the X pass classifies per mode). */
 T21_API int t21_build_pencil_segments(const t21_binspec* spec, uint32_t* out, int stride, int* max_segments_dev, void* stream);
 

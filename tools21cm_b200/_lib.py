@@ -47,6 +47,7 @@ class BinSpecC(C.Structure):
         ("mu_hi_f", C.c_void_p),
         ("seg_tab", C.c_void_p),
         ("seg_stride", C.c_int32),
+        ("seg_ntab", C.c_int32),
     ]
 
 

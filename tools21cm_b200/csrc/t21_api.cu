@@ -388,10 +388,16 @@ static int ps_nd_impl(const t21_plan* p, const void* x1, const void* x2, int sub
 int t21_build_pencil_segments(const t21_binspec* spec, uint32_t* out, int stride, int* max_segments_dev, void* stream) {
     if (!spec || !out || !max_segments_dev) { set_error("null argument to t21_build_pencil_segments"); return T21_EINVAL; }
     if (stride != 8 && stride != 16 && stride != 32) { set_error("segment stride must be 8, 16 or 32"); return T21_EINVAL; }
-    if (spec->nmu > 0 && !spec->absolute_mus) { set_error("signed mu bins are not even in kx: no segment table"); return T21_EINVAL; }
     if (spec->zero_idx[0] != 0 || spec->n[0] < 2 || spec->n[0] >= 65535) { set_error("segment tables need a spec in FFT index order"); return T21_EINVAL; }
     if (spec->nk * (spec->nmu > 0 ? spec->nmu : 1) >= 65535) { set_error("too many bins for a segment table"); return T21_EINVAL; }
-    return launch_pencil_segments(*spec, out, stride, max_segments_dev, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    T21_CUDA_OK(cudaMemsetAsync(max_segments_dev, 0, sizeof(int), st));
+    const bool is_signed = spec->nmu > 0 && !spec->absolute_mus;
+    if (!is_signed) return launch_pencil_segments(*spec, 0, out, stride, max_segments_dev, st);
+    const size_t per_table = (size_t)spec->n[1] * (spec->n[2] / 2 + 1) * stride;
+    for (int w = 1; w <= 4; ++w)
+        if (int rc = launch_pencil_segments(*spec, w, out + (size_t)(w - 1) * per_table, stride, max_segments_dev, st)) return rc;
+    return T21_OK;
 }
 
 int t21_profile(int enable) {

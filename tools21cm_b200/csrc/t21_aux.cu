@@ -586,20 +586,19 @@ int launch_reduce_moments(const double* part_sum, const unsigned* part_cnt, int 
 // ---- pencil segment table (t21_build_pencil_segments) ------------------------------------------------------------------
 // one thread per pencil of the computed half spectrum; see build_pencil_segments() in t21_bin.cuh
 __global__ void __launch_bounds__(128)
-pencil_segments_kernel(const __grid_constant__ t21_binspec B, unsigned* __restrict__ out, int stride, int* __restrict__ max_seg) {
+pencil_segments_kernel(const __grid_constant__ t21_binspec B, int which, unsigned* __restrict__ out, int stride, int* __restrict__ max_seg) {
     const int nzh = B.n[2] / 2 + 1;
     const long long np = (long long)B.n[1] * nzh;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int s = 0;
-    if (i < np) s = build_pencil_segments(B, (int)(i / nzh), (int)(i % nzh), out + i * stride, stride);
+    if (i < np) s = build_pencil_segments(B, (int)(i / nzh), (int)(i % nzh), which, out + i * stride, stride);
     for (int o = 16; o > 0; o >>= 1) { const int t = __shfl_xor_sync(0xffffffffu, s, o); s = t > s ? t : s; }
     if ((threadIdx.x & 31) == 0 && s > 0) atomicMax(max_seg, s);
 }
 
-int launch_pencil_segments(const t21_binspec& spec, unsigned* out, int stride, int* max_seg_dev, cudaStream_t st) {
+int launch_pencil_segments(const t21_binspec& spec, int which, unsigned* out, int stride, int* max_seg_dev, cudaStream_t st) {
     const long long np = (long long)spec.n[1] * (spec.n[2] / 2 + 1);
-    T21_CUDA_OK(cudaMemsetAsync(max_seg_dev, 0, sizeof(int), st));
-    pencil_segments_kernel<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(spec, out, stride, max_seg_dev);
+    pencil_segments_kernel<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(spec, which, out, stride, max_seg_dev);
     count_launch();
     T21_CUDA_OK(cudaGetLastError());
     return 0;

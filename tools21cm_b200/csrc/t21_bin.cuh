@@ -140,14 +140,19 @@ T21_HD ModeBins classify(const t21_binspec& B, int ix, int iy, int iz, bool has_
 // short.  The mirror mode nx - f must agree (shells and |mu| bins are even in kx; signed mu is refused by the caller):
 // a pencil where it does not, or with more than `stride` ranges, reports stride + 1 and the table is not used.
 constexpr unsigned kSegSentinel = 0xFFFF0000u;
-T21_HD int build_pencil_segments(const t21_binspec& B, int iy, int iz, unsigned* __restrict__ out, int stride) {
+// which: 0  bins even in kx (shells, |mu|): the stored mode's bin, checked against its mirror nx - f;
+//        1 / 2  signed mu, the stored mode's own bin for kx = +f / kx = -f;
+//        3 / 4  signed mu, the bin of its Hermitian twin (-1 where the twin is itself stored) for kx = +f / -f.
+T21_HD int build_pencil_segments(const t21_binspec& B, int iy, int iz, int which, unsigned* __restrict__ out, int stride) {
     const int nx = B.n[0], nz = B.n[2];
     const bool has_twin = (iz != 0) && (iz != nz - iz);
     int s = 0, prev = -2;
     bool bad = false;
     for (int f = 0; f <= nx / 2; ++f) {
-        const int b = classify(B, f, iy, iz, has_twin).own;
-        if (f > 0 && f < nx - f && classify(B, nx - f, iy, iz, has_twin).own != b) bad = true;
+        const int ix = (which == 2 || which == 4) ? (nx - f) % nx : f;
+        const ModeBins mb = classify(B, ix, iy, iz, has_twin);
+        const int b = which >= 3 ? mb.twin : mb.own;
+        if (which == 0 && f > 0 && f < nx - f && classify(B, nx - f, iy, iz, has_twin).own != b) bad = true;
         if (b != prev) {
             if (s < stride) out[s] = ((unsigned)f << 16) | (unsigned)(b + 1);
             ++s;

@@ -78,7 +78,7 @@ int launch_bin_multipoles(const void* p, int dtype, const t21_binspec& spec, int
 int launch_reduce_moments(const double* part_sum, const unsigned* part_cnt, int nparts, int nk, double* sums_out,
                           long long* counts_out, cudaStream_t st);
 
-int launch_pencil_segments(const t21_binspec& spec, unsigned* out, int stride, int* max_seg_dev, cudaStream_t st);
+int launch_pencil_segments(const t21_binspec& spec, int which, unsigned* out, int stride, int* max_seg_dev, cudaStream_t st);
 
 // error plumbing (t21_api.cu)
 void set_error(const char* fmt, ...);

@@ -46,8 +46,9 @@ struct Params {
     const float* offset;   // mean offset (device scalar) or null
     double ntot;
     t21_binspec bins;
-    const unsigned* seg;   // pencil segment table (t21_build_pencil_segments) or null
+    const unsigned* seg;   // pencil segment table(s) (t21_build_pencil_segments) or null
     int seg_stride;
+    long long seg_pencils; // pencils per table: ny_global * nzh
 };
 
 #if T21_DEVICE_CODE
@@ -215,36 +216,22 @@ __device__ __forceinline__ void epilogue_shells(const Params& p, const cx<float>
     __syncwarp();
 }
 
-// ---- bins as index ranges from the pencil segment table (shells and |mu| bins) -----------------------------------------
+// ---- bins as index ranges from the pencil segment table (shells, |mu| and signed mu bins) ------------------------------
 // Lane j holds entry j of the pencil's table: range j starts at |kx| = pos_j and falls in bin binp1_j - 1.  A step of
 // 64 modes (|kx| in [32k, 32k + 32]) no range boundary falls into is added whole, as two packed FMAs per lane; a step
 // that holds a boundary parks the running sum and its two powers in a lane-private strip of shared memory, and a
 // rolled loop then closes the ranges in order: every lane adds its modes below the boundary, one shuffle tree sums the
 // range over the warp, lane 0 adds it -- and the closed-form mode count of the range -- to the warp's histogram.
-constexpr int kSlots = 8;                            // boundary steps per half pencil (there are 8 steps in a half)
-template <class Hist>
-__device__ __forceinline__ void epilogue_segments(const Params& p, cx<float>* v, int lane, int iy, int iz, unsigned ent,
-                                                  float* __restrict__ strip, Hist& hist) {
-    const bool has_twin = (iz != 0) && (iz != p.nz - iz);
-    const unsigned wt = has_twin ? 2u : 1u;
-    const float wf = (float)wt;
+// LO / HI: take the kx >= 0 half (v[0..15], |kx| = 32k + lane) / the kx < 0 half (v[31-k], |kx| = 32k + 32 - lane).
+// Signed mu walks the halves separately (mu changes sign with kx when the line of sight is x), once with the stored
+// modes' own bins and once with their twins'.
+template <bool LO, bool HI, class Hist>
+__device__ __forceinline__ void walk_segments(const cx<float>* v, int lane, unsigned ent, float wf, unsigned wt,
+                                              float* __restrict__ strip, Hist& hist) {
     const unsigned pos = ent >> 16, binp1 = ent & 0xFFFFu;
     const unsigned S = (unsigned)__popc(__ballot_sync(0xffffffffu, pos != 0xFFFFu));
+    if (S == 1u && __shfl_sync(0xffffffffu, binp1, 0) == 0u) return;          // the whole pencil is in no bin
     const unsigned mixed = __reduce_or_sync(0xffffffffu, ((unsigned)lane >= 1u && (unsigned)lane < S) ? 1u << ((pos - 1u) >> 5) : 0u);
-
-    if (iy == 0 && iz == 0) {
-        // DC of (x - c) plus c*N: the only sample the mean offset changes.  It stays in the flow with power 0 (so
-        // that it is counted like any other mode); its true power goes to the histogram here, with count 0.
-        const int b0 = (int)__shfl_sync(0xffffffffu, binp1, 0) - 1;
-        if (lane == 0) {
-            const double c0 = p.offset ? (double)ldg(p.offset) : 0.0;
-            const double ra = (double)v[0].x + c0 * p.ntot;
-            const double dc = ra * ra + (double)v[0].y * (double)v[0].y;
-            v[0] = cmake<float>(0.f, 0.f);
-            if (b0 >= 0) hist.add(b0, dc, 0u);
-        }
-    }
-
     float cur = 0.f;
     unsigned j = 0u;
     unsigned nextpos = S > 1u ? __shfl_sync(0xffffffffu, pos, 1) : 0xFFFFu;
@@ -256,7 +243,11 @@ __device__ __forceinline__ void epilogue_segments(const Params& p, cx<float>* v,
         const unsigned a = __shfl_sync(0xffffffffu, pos, j);
         const int bin = (int)__shfl_sync(0xffffffffu, binp1, j) - 1;
         if (lane == 0 && bin >= 0) {
-            const unsigned cnt = 2u * (b - a) - (a == 0u ? 1u : 0u) - (b == (unsigned)(NX / 2 + 1) ? 1u : 0u);
+            constexpr unsigned H = NX / 2;
+            unsigned cnt;
+            if (LO && HI) cnt = 2u * (b - a) - (a == 0u ? 1u : 0u) - (b == H + 1u ? 1u : 0u);   // kx = 0 and the Nyquist sample are single
+            else if (LO) cnt = (b < H ? b : H) - (a < H ? a : H);                            // |kx| in [a, b) and [0, H - 1]
+            else cnt = b - (a > 1u ? a : 1u);                                                 // |kx| in [a, b) and [1, H]
             hist.add(bin, (double)(t * wf), cnt * wt);
         }
     };
@@ -270,14 +261,14 @@ __device__ __forceinline__ void epilogue_segments(const Params& p, cx<float>* v,
             if ((mixed >> k) & 1u) {
                 float* d = strip + slot * 96u + lane;
                 d[0] = run2.x + run2.y;
-                d[32] = v[k].x * v[k].x + v[k].y * v[k].y;
-                d[64] = v[31 - k].x * v[31 - k].x + v[31 - k].y * v[31 - k].y;
+                d[32] = LO ? v[k].x * v[k].x + v[k].y * v[k].y : 0.f;
+                d[64] = HI ? v[31 - k].x * v[31 - k].x + v[31 - k].y * v[31 - k].y : 0.f;
                 run2 = cmake<float>(0.f, 0.f);
                 ks |= (unsigned)k << (4u * slot);
                 ++slot;
             } else {
-                run2 = fma2(v[k], v[k], run2);
-                run2 = fma2(v[31 - k], v[31 - k], run2);
+                if (LO) run2 = fma2(v[k], v[k], run2);
+                if (HI) run2 = fma2(v[31 - k], v[31 - k], run2);
             }
         }
         // (every lane reads back only what it wrote itself: no warp synchronisation needed)
@@ -303,7 +294,35 @@ __device__ __forceinline__ void epilogue_segments(const Params& p, cx<float>* v,
     close((unsigned)(NX / 2 + 1));
 }
 
-template <bool SEG, class Hist>
+// NT = 1: bins even in kx, one table; NT = 4: signed mu, tables {own kx>=0, own kx<0, twin kx>=0, twin kx<0}
+template <int NT, class Hist>
+__device__ __forceinline__ void epilogue_segments(const Params& p, cx<float>* v, int lane, int iy, int iz, const unsigned* ent,
+                                                  float* __restrict__ strip, Hist& hist) {
+    if (iy == 0 && iz == 0) {
+        // DC of (x - c) plus c*N: the only sample the mean offset changes.  It stays in the flow with power 0 (so
+        // that it is counted like any other mode); its true power goes to the histogram here, with count 0.
+        const int b0 = (int)(__shfl_sync(0xffffffffu, ent[0], 0) & 0xFFFFu) - 1;
+        if (lane == 0) {
+            const double c0 = p.offset ? (double)ldg(p.offset) : 0.0;
+            const double ra = (double)v[0].x + c0 * p.ntot;
+            const double dc = ra * ra + (double)v[0].y * (double)v[0].y;
+            v[0] = cmake<float>(0.f, 0.f);
+            if (b0 >= 0) hist.add(b0, dc, 0u);
+        }
+    }
+    if constexpr (NT == 1) {
+        const bool has_twin = (iz != 0) && (iz != p.nz - iz);
+        const unsigned wt = has_twin ? 2u : 1u;
+        walk_segments<true, true>(v, lane, ent[0], (float)wt, wt, strip, hist);
+    } else {
+        walk_segments<true, false>(v, lane, ent[0], 1.f, 1u, strip, hist);
+        walk_segments<false, true>(v, lane, ent[1], 1.f, 1u, strip, hist);
+        walk_segments<true, false>(v, lane, ent[2], 1.f, 1u, strip, hist);
+        walk_segments<false, true>(v, lane, ent[3], 1.f, 1u, strip, hist);
+    }
+}
+
+template <int NT, class Hist>
 __device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& p, unsigned char* smem_raw, Hist& hist, int nbins) {
     cx<float>* buf = reinterpret_cast<cx<float>*>(smem_raw);
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + BAR_OFF);
@@ -337,8 +356,13 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& 
         cx<float> v[32];
         const int iz = (int)chunk * WZ + warp;
         // this pencil's ranges: asked for now, needed after the two butterfly stages
-        unsigned ent = kSegSentinel;
-        if (SEG && lane < p.seg_stride && iz < p.nzh) ent = ldg(p.seg + ((size_t)iy * p.nzh + iz) * p.seg_stride + lane);
+        unsigned ent[NT > 0 ? NT : 1];
+#pragma unroll
+        for (int t = 0; t < (NT > 0 ? NT : 1); ++t) {
+            ent[t] = kSegSentinel;
+            if (NT > 0 && lane < p.seg_stride && iz < p.nzh)
+                ent[t] = ldg(p.seg + ((size_t)t * p.seg_pencils + (size_t)iy * p.nzh + iz) * p.seg_stride + lane);
+        }
         mbar_wait(bar, parity);
         parity ^= 1u;
         // stage 0: rows j0 + 32 k of column zl0 from the landed [x][8] tile
@@ -372,11 +396,11 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& 
         DFT<32, float>::run(v);                            // v[k] = X[lane + 32 k]
         if (iz < p.nzh) {
             float* stage = reinterpret_cast<float*>(smem_raw + STAGE_OFF) + warp * 1024;
-            if constexpr (SEG) epilogue_segments(p, v, lane, iy, iz, ent, stage, hist);
+            if constexpr (NT > 0) epilogue_segments<NT>(p, v, lane, iy, iz, ent, stage, hist);
             else epilogue_shells(p, v, lane, iy, iz, stage, wbc, hist);
         }
     }
-    if constexpr (!SEG) wbc_flush(wbc, hist);
+    if constexpr (NT == 0) wbc_flush(wbc, hist);
 }
 
 #endif  // T21_DEVICE_CODE
@@ -384,7 +408,7 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& 
 // The histogram (at most 31 bins) lives in shared memory, one copy per warp: only lane 0 of the owning warp writes
 // it, in program order; warps are summed in order here and CTAs in order by reduce_partials_kernel, so the result
 // is bit-reproducible run to run.
-template <bool SEG>
+template <int NT>
 __global__ void __launch_bounds__(THREADS, 2)
 xpass32_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ Params p, int nbins,
                double* __restrict__ part_sum, unsigned* __restrict__ part_cnt) {
@@ -401,7 +425,7 @@ xpass32_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ 
     for (int b = tid; b < NW * nbins; b += THREADS) { hs[b] = 0.0; hc[b] = 0u; }
     __syncthreads();
     WarpPrivHist hist{hs + (size_t)(tid >> 5) * nbins, hc + (size_t)(tid >> 5) * nbins};
-    run_tiles<SEG>(&map, p, smem_raw, hist, nbins);
+    run_tiles<NT>(&map, p, smem_raw, hist, nbins);
     __syncthreads();
     for (int b = tid; b < nbins; b += THREADS) {
         double s = 0.0;
@@ -434,12 +458,14 @@ static int launch(XArgs& a, cudaStream_t st) {
     p.bins = *a.bins;
     p.seg = a.bins->seg_tab;
     p.seg_stride = a.bins->seg_stride;
-    const bool seg = p.seg != nullptr && use_segments();
+    p.seg_pencils = (long long)a.bins->n[1] * a.nzh;
+    const int nt = (p.seg != nullptr && use_segments()) ? a.bins->seg_ntab : 0;
+    if (nt != 0 && nt != 1 && nt != 4) { set_error("bad segment table count %d", nt); return T21_EINVAL; }
     CUtensorMap map;
     if (int rc = make_wmap_f32(&map, a.w[0], nxs, a.ny, a.pitch / WZ, NX / nxs, p.box_rows)) return rc;
 
     const size_t smem = HIST_OFF + (size_t)(THREADS / 32) * a.nbins * 12;
-    auto kern = seg ? xpass32_kernel<true> : xpass32_kernel<false>;
+    auto kern = nt == 0 ? xpass32_kernel<0> : (nt == 1 ? xpass32_kernel<1> : xpass32_kernel<4>);
     if (int rc = ensure_smem(kern, smem)) return rc;
     int occ = 0;
     T21_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
@@ -464,8 +490,10 @@ bool xpass32_applicable(int dtype, const XArgs& a) {
     if (!(dtype == T21_F32 && a.nx == x32::NX && a.nf == 1 && a.bins != nullptr && a.tw32 != nullptr && a.pitch % x32::WZ == 0 &&
           !a.hist_global))
         return false;
-    if (a.bins->seg_tab != nullptr && x32::use_segments())       // bins as table-driven index ranges: shells and |mu| bins
-        return a.nbins <= 128 && (a.bins->nmu == 0 || a.bins->absolute_mus != 0);
+    if (a.bins->seg_tab != nullptr && x32::use_segments()) {     // bins as table-driven index ranges
+        const bool is_signed = a.bins->nmu > 0 && !a.bins->absolute_mus;
+        return a.nbins <= 128 && a.bins->seg_ntab == (is_signed ? 4 : 1);
+    }
     return a.bins->nmu == 0 && a.bins->nk <= 31;
 }
 

@@ -119,15 +119,16 @@ class _Device:
         """The pencil segment table of the warp-per-pencil X pass (``t21_build_pencil_segments``): along an x pencil the
         bins are index ranges, found once per (shape, bin spec) on the device with the per-mode classification of the
         other kernels and kept with the cached spec -- plan data like the twiddle tables, 8-32 entries per pencil.
-        Only shapes that kernel takes (nx = 1024) and bins that are even in kx (shells, |mu|) get one."""
+        Only shapes that kernel takes (nx = 1024) get one (four for signed mu bins, which are not even in kx)."""
         spec, cspec, owners = hit
         if getattr(spec, "_segments_tried", False):
             return
         spec._segments_tried = True
         if os.environ.get("T21_X32_SEGMENTS", "1") == "0":
             return
-        if spec.shape[0] != 1024 or spec.nbins > 128 or (spec.nmu and not spec.absolute_mus) or int(spec.zero_idx[0]) != 0:
+        if spec.shape[0] != 1024 or spec.nbins > 128 or int(spec.zero_idx[0]) != 0:
             return
+        ntab = 4 if (spec.nmu and not spec.absolute_mus) else 1      # signed mu: own / twin bins for kx >= 0 and kx < 0
         torch = _torch()
         lib = _lib.load()
         dev = "cuda:%d" % self.index
@@ -136,7 +137,7 @@ class _Device:
         stream = _stream_ptr(torch, self.index)
         stride, table = 32, None
         for _ in range(2):
-            table = torch.empty(npencils * stride, dtype=torch.int32, device=dev)
+            table = torch.empty(ntab * npencils * stride, dtype=torch.int32, device=dev)
             _lib.check(lib.t21_build_pencil_segments(C.byref(cspec), table.data_ptr(), stride, maxseg.data_ptr(), stream),
                        "t21_build_pencil_segments")
             m = int(maxseg.item())
@@ -149,6 +150,7 @@ class _Device:
         owners.append(table)
         cspec.seg_tab = table.data_ptr()
         cspec.seg_stride = stride
+        cspec.seg_ntab = ntab
 
 
     def cyl(self, key, builder):

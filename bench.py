@@ -423,6 +423,30 @@ def config5_leg(args, D, lib, synthetic, dist, dev, rank, world, barrier):
                          "parseval_rel_err_vs_auto_level": abs(float(s.item()) - expect) / ref,
                          "rows_shape": list(rows.shape)}
             del rows
+            if mode == "p2p":
+                # per-stage CUDA events of the library (max over ranks): stage 1 of the LAST field (Z pass, then the Y
+                # pass whose stores are the exchange) and the X pass of stage 2 over both fields
+                buf = (C.c_float * 5)()
+                lib.t21_profile(1)
+                acc = np.zeros(5)
+                for _ in range(2):
+                    D.sharded_cross_power_spectrum_nd(a, b, 714.0, copy=False)
+                    lib.t21_profile_last(buf, 5)
+                    acc += np.array(list(buf))
+                lib.t21_profile(0)
+                tt = torch.tensor(acc / 2.0, device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                acc = tt.cpu().numpy()
+                if acc[2] > 0:
+                    gbs = a_bytes / 2 / 1e9 / (acc[2] / 1e3)
+                    out[mode]["stages_ms"] = {"z_per_field": float(acc[1]), "y_fused_exchange_per_field": float(acc[2]),
+                                              "barrier_plus_x_both_fields": float(acc[3]),
+                                              "rest_assembly_and_barriers": float(ms - 2 * (acc[1] + acc[2]) - acc[3])}
+                    out[mode]["all_to_all_phase"] = {
+                        "ms_both_fields": float(2 * acc[2]), "achieved_gbs": gbs, "frac_of_770_measured_peer": gbs / 770.0,
+                        "frac_of_900_nominal": gbs / 900.0,
+                        "what": "the Y pass with SEND=2 IS the all-to-all (its stores go to the owners' y slabs over NVLink); "
+                                "bytes = A(N,P) per field (SURVEY.md 8d)"}
         except Exception as exc:                       # keep the bench line alive; say what failed
             out[mode] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
         torch.cuda.empty_cache()

@@ -3,7 +3,8 @@
 //
 //  * t21_h2d_staged: pageable host memory -> device through a pinned ring, filled by several host threads while the
 //    previous chunk's DMA runs.  A numpy array handed to the estimators is pageable: one blocking cudaMemcpy of it
-//    stages through the driver's own small bounce buffers on one thread (~10 GB/s); this keeps PCIe busy instead.
+//    stages through the driver's own small bounce buffers on one thread (~10 GB/s); this keeps PCIe busy instead
+//    (52-54 GB/s against 55.6 GB/s from pinned memory).
 //  * t21_f2c: C2Ray / CubeP3M blobs are Fortran ordered (x fastest; xfrac_file.py:62, density_file.py:51
 //    `reshape(..., order='F')`); the passes read C order (z fastest).  Tiled transpose through shared memory.
 //  * t21_c2ray_dt: calc_dt (temperature.py:51-80, _dt :215-222) FUSED with that transpose: reads the ionised fraction and
@@ -11,6 +12,7 @@
 //    Z pass -- the float64 copies, the cgs density and the two transposed arrays of the reference are never formed.
 #include <immintrin.h>
 #include <omp.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <mutex>
@@ -20,7 +22,12 @@ namespace t21 {
 
 // ---- staged host -> device copy ---------------------------------------------------------------------------------
 constexpr int kRing = 4;
-constexpr size_t kChunk = 32u << 20;
+// Chunk and store kind were measured on the B200 host (16 cores, 60 MB L3, tools/r2_h2d.py; pinned copy 55.6 GB/s):
+//   32 MB chunks, streaming stores (round 2 as first built): 30-37 GB/s -- source read + ring write + the DMA's read
+//   of the ring are three passes over host DRAM, and the VM's memory bandwidth is what runs out;
+//   8 MB chunks, plain stores: 52-54 GB/s -- the 32 MB ring stays in the last-level cache, the DMA engine's reads are
+//   served from it, and only the source is read from DRAM.  1-2 MB chunks pay the per-chunk launch (33 GB/s).
+static size_t kChunk = 8u << 20;       // T21_H2D_CHUNK_MB overrides it (read once, at the first copy)
 
 struct StageRing {
     unsigned char* buf[kRing] = {nullptr, nullptr, nullptr, nullptr};
@@ -31,12 +38,13 @@ struct StageRing {
 };
 static StageRing g_ring;
 
-// copy into the pinned ring with streaming stores: the ring is only ever read by the DMA engine, so the lines need not
-// be pulled into the cache first (a plain memcpy of a few MB per thread reads every destination line for ownership)
+// copy into the pinned ring.  With streaming stores the lines are not pulled into the cache first; with plain stores
+// (default) the ring is small enough to live in the last-level cache, where the DMA engine finds it
+static bool g_nt_stores = false;       // T21_H2D_NT=1: streaming stores (for rings larger than the last-level cache)
 static void stream_copy(unsigned char* dst, const unsigned char* src, size_t n) {
 #if defined(__AVX2__)
     size_t i = 0;
-    if (((uintptr_t)dst & 31) == 0) {
+    if (g_nt_stores && ((uintptr_t)dst & 31) == 0) {
         for (; i + 128 <= n; i += 128) {
             const __m256i a = _mm256_loadu_si256((const __m256i*)(src + i)), b = _mm256_loadu_si256((const __m256i*)(src + i + 32));
             const __m256i c = _mm256_loadu_si256((const __m256i*)(src + i + 64)), d = _mm256_loadu_si256((const __m256i*)(src + i + 96));
@@ -55,6 +63,8 @@ static void stream_copy(unsigned char* dst, const unsigned char* src, size_t n) 
 
 static int ring_init() {
     if (g_ring.ok) return 0;
+    if (const char* e = getenv("T21_H2D_NT")) g_nt_stores = e[0] != '0';
+    if (const char* e = getenv("T21_H2D_CHUNK_MB")) { const long mb = atol(e); if (mb >= 1 && mb <= 1024) kChunk = (size_t)mb << 20; }
     for (int i = 0; i < kRing; ++i) {
         T21_CUDA_OK(cudaHostAlloc((void**)&g_ring.buf[i], kChunk, cudaHostAllocDefault));
         T21_CUDA_OK(cudaEventCreateWithFlags(&g_ring.ev[i], cudaEventDisableTiming));

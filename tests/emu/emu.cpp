@@ -205,4 +205,43 @@ int emu_bin_only(const double* p, const t21_binspec* spec, double* sums, long lo
     for (int b = 0; b < nb; ++b) { sums[b] = hs[b]; counts[b] = hc[b]; }
     return 0;
 }
+
+// The epilogue of the warp-per-pencil X pass as plain loops: bins are index ranges along x pencils, taken from the
+// segment tables build_pencil_segments() makes (one table for shells / |mu| bins, four for signed mu).  phalf is the
+// power of the computed half spectrum, [nx][ny][nz/2+1], nx even.  Returns 1 if a pencil needs more than 32 ranges,
+// 2 if the closed-form mode count of a range (segment_modes, what the kernel books) disagrees with counting them.
+int emu_bin_segments(const double* phalf, const t21_binspec* spec, double* sums, long long* counts) {
+    const t21_binspec& B = *spec;
+    const int nx = B.n[0], ny = B.n[1], nz = B.n[2], nzh = nz / 2 + 1, H = nx / 2;
+    const int nb = B.nk * (B.nmu > 0 ? B.nmu : 1);
+    const bool is_signed = B.nmu > 0 && !B.absolute_mus;
+    const int ntab = is_signed ? 4 : 1;
+    for (int b = 0; b < nb; ++b) { sums[b] = 0.0; counts[b] = 0; }
+    unsigned ent[32];
+    for (int iy = 0; iy < ny; ++iy)
+        for (int iz = 0; iz < nzh; ++iz) {
+            const bool has_twin = (iz != 0) && (iz != nz - iz);
+            for (int t = 0; t < ntab; ++t) {
+                const int S = build_pencil_segments(B, iy, iz, is_signed ? t + 1 : 0, ent, 32);
+                if (S > 32) return 1;
+                const bool lo = ntab == 1 || t == 0 || t == 2, hi = ntab == 1 || t == 1 || t == 3;
+                const unsigned wt = (ntab == 1 && has_twin) ? 2u : 1u;
+                for (int j = 0; j < S; ++j) {
+                    const unsigned a = ent[j] >> 16, b = j + 1 < S ? ent[j + 1] >> 16 : (unsigned)H + 1u;
+                    const int bin = (int)(ent[j] & 0xFFFFu) - 1;
+                    if (bin < 0) continue;
+                    double sum = 0.0;
+                    unsigned cnt = 0;
+                    for (unsigned f = a; f < b; ++f) {
+                        if (lo && f < (unsigned)H) { sum += phalf[((size_t)f * ny + iy) * nzh + iz]; ++cnt; }
+                        if (hi && f >= 1) { sum += phalf[((size_t)(nx - f) * ny + iy) * nzh + iz]; ++cnt; }
+                    }
+                    if (cnt != segment_modes(lo, hi, a, b, (unsigned)H)) return 2;
+                    sums[bin] += sum * wt;
+                    counts[bin] += (long long)cnt * wt;
+                }
+            }
+        }
+    return 0;
+}
 }

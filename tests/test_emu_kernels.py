@@ -36,6 +36,8 @@ def emu():
     lib.emu_run.restype = C.c_int
     lib.emu_bin_only.argtypes = [C.c_void_p, C.POINTER(_lib.BinSpecC), C.c_void_p, C.c_void_p]
     lib.emu_pitch.argtypes = [C.c_int]
+    lib.emu_bin_segments.argtypes = [C.c_void_p, C.POINTER(_lib.BinSpecC), C.c_void_p, C.c_void_p]
+    lib.emu_bin_segments.restype = C.c_int
     return lib
 
 
@@ -145,3 +147,30 @@ def test_emulated_bin_only_vs_golden(emu, case, golden):
         ps = (sums / counts).reshape(want[0].shape)
     assert np.array_equal(counts.reshape(want[-1].shape).astype(float), want[-1])
     np.testing.assert_allclose(ps, want[0], rtol=1e-12, equal_nan=True)
+
+
+SEG = [c for c in FUSED if c["shape"][0] % 2 == 0]
+
+
+@pytest.mark.parametrize("case", SEG, ids=[c["id"] for c in SEG])
+def test_pencil_segment_tables_vs_golden(emu, case, golden):
+    """The table-driven epilogue of the warp-per-pencil X pass (t21_xpass32.cu) as plain loops: build_pencil_segments()
+    turns every x pencil into index ranges (one table for shells and |mu| bins, four for signed mu), the power of the
+    numpy half spectrum is added range by range, the mode count of a range is the kernel's closed form -- and the
+    result must be the reference's P and n_modes for every golden case of the fused estimators."""
+    cubes = [np.asarray(c, dtype=np.float64) for c in build_inputs(case)]
+    spec, box = spec_for(case, cubes[0].shape)
+    want = golden_outputs(golden, case["id"])
+    f0 = np.fft.rfftn(cubes[0])
+    f1 = np.fft.rfftn(cubes[1]) if len(cubes) == 2 else f0
+    phalf = np.ascontiguousarray((f0 * np.conj(f1)).real)
+    cspec, keep = _lib.pack_binspec(spec, _lib.host_buffer)
+    sums = np.zeros(spec.nbins)
+    counts = np.zeros(spec.nbins, dtype=np.int64)
+    rc = emu.emu_bin_segments(phalf.ctypes.data, C.byref(cspec), sums.ctypes.data, counts.ctypes.data)
+    assert rc == 0, "more than 32 ranges on a pencil" if rc == 1 else "closed-form range count is wrong"
+    with np.errstate(all="ignore"):
+        ps = (sums * bs.volume_scale(cubes[0].shape, box) / counts).reshape(want[0].shape)
+    assert np.array_equal(counts.reshape(want[-1].shape).astype(float), want[-1]), "n_modes differ"
+    atol = 1e-9 * np.nanmax(np.abs(want[0])) if len(cubes) == 2 else 0.0
+    np.testing.assert_allclose(ps, want[0], rtol=2e-7, atol=atol, equal_nan=True)

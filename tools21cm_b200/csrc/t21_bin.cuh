@@ -140,6 +140,13 @@ T21_HD ModeBins classify(const t21_binspec& B, int ix, int iy, int iz, bool has_
 // short.  The mirror mode nx - f must agree (shells and |mu| bins are even in kx; signed mu is refused by the caller):
 // a pencil where it does not, or with more than `stride` ranges, reports stride + 1 and the table is not used.
 constexpr unsigned kSegSentinel = 0xFFFF0000u;
+// modes of an x pencil (even nx, H = nx / 2) with a <= |kx index| < b, 0 <= a < b <= H + 1, in the kx >= 0 half
+// (indices 0 .. H-1: LO), the kx < 0 half (|kx| = 1 .. H, the Nyquist sample counted there: HI), or both
+T21_HD unsigned segment_modes(bool lo, bool hi, unsigned a, unsigned b, unsigned H) {
+    if (lo && hi) return 2u * (b - a) - (a == 0u ? 1u : 0u) - (b == H + 1u ? 1u : 0u);
+    if (lo) return (b < H ? b : H) - (a < H ? a : H);
+    return b - (a > 1u ? a : 1u);
+}
 // which: 0  bins even in kx (shells, |mu|): the stored mode's bin, checked against its mirror nx - f;
 //        1 / 2  signed mu, the stored mode's own bin for kx = +f / kx = -f;
 //        3 / 4  signed mu, the bin of its Hermitian twin (-1 where the twin is itself stored) for kx = +f / -f.

@@ -243,11 +243,7 @@ __device__ __forceinline__ void walk_segments(const cx<float>* v, int lane, unsi
         const unsigned a = __shfl_sync(0xffffffffu, pos, j);
         const int bin = (int)__shfl_sync(0xffffffffu, binp1, j) - 1;
         if (lane == 0 && bin >= 0) {
-            constexpr unsigned H = NX / 2;
-            unsigned cnt;
-            if (LO && HI) cnt = 2u * (b - a) - (a == 0u ? 1u : 0u) - (b == H + 1u ? 1u : 0u);   // kx = 0 and the Nyquist sample are single
-            else if (LO) cnt = (b < H ? b : H) - (a < H ? a : H);                            // |kx| in [a, b) and [0, H - 1]
-            else cnt = b - (a > 1u ? a : 1u);                                                 // |kx| in [a, b) and [1, H]
+            const unsigned cnt = segment_modes(LO, HI, a, b, (unsigned)(NX / 2));   // kx = 0 and the Nyquist sample are single
             hist.add(bin, (double)(t * wf), cnt * wt);
         }
     };

@@ -243,6 +243,13 @@ T21_API int t21_bin_multipoles_half(const void* p_half, int dtype, int row_pitch
                                     int exclude_zero, double* sums_out, long long* counts_out, void* workspace,
                                     size_t workspace_bytes, void* stream);
 T21_API size_t t21_bin_multipoles_workspace_bytes(int nk);
+/* power_spectrum_multipoles (power_legendre.py:4-90) as ONE pipeline: Z / Y passes, then the warp-per-pencil X pass whose
+ * epilogue adds the five sums above per k bin -- no power array is written.  fp32, nx = 1024, and `spec` (shells, FFT
+ * order, half-open last bin, los_axis / exclude_zero set) must carry the segment table t21_build_pencil_segments made
+ * for it; T21_EINVAL otherwise (take t21_ps_half + t21_bin_multipoles_half).  sums_out[nk][5], counts_out[nk];
+ * workspace t21_workspace_bytes(plan, 1, 5 * nk). */
+T21_API int t21_ps_multipoles(const t21_plan* plan, const void* x1, int subtract_mean, const t21_binspec* spec, int los_axis,
+                              double* sums_out, long long* counts_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- input side ----
  * t21_h2d_staged: pageable HOST memory -> device through a pinned ring filled by `threads` host threads (0: choose) while

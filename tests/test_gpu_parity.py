@@ -184,6 +184,27 @@ def test_multipoles_against_oracle(t2c, shape, los):
         np.testing.assert_allclose(got["P4"], want["P4"], rtol=1e-6, atol=atol, equal_nan=True)
 
 
+@pytest.mark.parametrize("shape", [(1024, 16, 32), (1024, 32, 16)])
+@pytest.mark.parametrize("los", [0, 1, 2])
+def test_fused_multipoles_on_the_warp_per_pencil_pass(t2c, shape, los):
+    """fp32 cubes with nx = 1024 take the fused route (t21_ps_multipoles: the five sums per k bin are added by the X pass
+    from its registers, bins from the pencil segment table, the excluded k_perp = 0 line dropped by the table): against
+    the oracle, with and without the line, and with explicit edges whose first bin holds DC (mu = NaN there)."""
+    from oracle import ps_oracle
+    x = (np.random.default_rng(11 + los).standard_normal(shape) + 1.5).astype(np.float32)
+    box = [300.0, 40.0, 60.0]
+    for kb, excl in ((7, True), (7, False), (np.array([0.0, 0.2, 0.5, 1.0, 2.5]), False)):
+        got, kc = t2c.power_spectrum_multipoles(x, kbins=kb, box_dims=box, los_axis=los, exclude_zero_modes=excl)
+        with np.errstate(all="ignore"):
+            want, kc_o = ps_oracle.power_spectrum_multipoles(x, kbins=kb, box_dims=box, los_axis=los, exclude_zero_modes=excl)
+        assert np.array_equal(kc, kc_o)
+        assert np.array_equal(got["n_modes"], want["n_modes"]) and np.array_equal(got["nmodes"], want["nmodes"])
+        np.testing.assert_allclose(got["P0"], want["P0"], rtol=1e-5, equal_nan=True)
+        atol = 1e-5 * float(np.nanmax(np.abs(want["P0"])))
+        np.testing.assert_allclose(got["P2"], want["P2"], rtol=1e-4, atol=atol, equal_nan=True)
+        np.testing.assert_allclose(got["P4"], want["P4"], rtol=1e-4, atol=atol, equal_nan=True)
+
+
 @pytest.mark.parametrize("n,ncuts,dtype", [(64, 4, "float32"), (128, 2, "float32"), (64, 2, "float64"), (48, 3, "float64")])
 def test_integrated_bispectrum_against_oracle(t2c, n, ncuts, dtype):
     """The batched windowed estimator (mask fused into the Z-pass load) against the reference's loop over masked full

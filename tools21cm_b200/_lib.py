@@ -192,6 +192,8 @@ def load():
     lib.t21_bin_multipoles_half.restype = i32
     lib.t21_bin_multipoles_workspace_bytes.argtypes = [i32]
     lib.t21_bin_multipoles_workspace_bytes.restype = sz
+    lib.t21_ps_multipoles.argtypes = [vp, vp, i32, C.POINTER(BinSpecC), i32, vp, vp, vp, sz, vp]
+    lib.t21_ps_multipoles.restype = i32
     lib.t21_h2d_staged.argtypes = [vp, vp, sz, i32, vp]
     lib.t21_h2d_staged.restype = i32
     lib.t21_f2c.argtypes = [vp, i32, i32, i32, i32, vp, i32, vp]

@@ -284,6 +284,50 @@ int t21_ps_binned(const t21_plan* p, const void* x1, const void* x2, int subtrac
     return rc;
 }
 
+// power_spectrum_multipoles (power_legendre.py:4-90) in ONE pipeline: the Z / Y passes, then the warp-per-pencil X pass
+// whose epilogue adds, per k bin, sum P, sum P L2, sum P L4, sum L2^2, sum L4^2 and the mode count -- no power array is
+// written.  Needs what that kernel needs (fp32, nx = 1024) and a shell spec carrying its pencil segment table, built
+// with spec->los_axis / spec->exclude_zero set (t21_build_pencil_segments drops the k_perp = 0 line then); returns
+// T21_EINVAL otherwise and the caller takes t21_ps_half + t21_bin_multipoles_half.  sums_out[nk][5], counts_out[nk];
+// workspace: t21_workspace_bytes(plan, 1, 5 * nk).
+int t21_ps_multipoles(const t21_plan* p, const void* x1, int subtract_mean, const t21_binspec* spec, int los_axis,
+                      double* sums_out, long long* counts_out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!spec || !sums_out || !counts_out) { set_error("null spec or outputs"); return T21_EINVAL; }
+    if (los_axis < 0 || los_axis > 2 || spec->nmu != 0 || spec->nk < 1) { set_error("bad multipole spec"); return T21_EINVAL; }
+    if (p && (spec->n[0] != p->n[0] || spec->n[1] != p->n[1] || spec->n[2] != p->n[2])) {
+        set_error("bin spec shape does not match the plan"); return T21_EINVAL;
+    }
+    const int nk = spec->nk;
+    const WsLayout L = p ? ws_layout(p, 1, nk * 5) : WsLayout();
+    if (int rc = check_common(p, x1, workspace, L.total, workspace_bytes)) return rc;
+    if (!(p->fast[0] && p->fast[1] && p->fast[2]) || L.nbins_cap == 0) { set_error("fused multipoles need power-of-two axes"); return T21_EINVAL; }
+    XArgs a;
+    memset(&a, 0, sizeof(a));
+    unsigned char* ws = (unsigned char*)workspace;
+    a.w[0] = ws + L.w[0];
+    a.nf = 1;
+    a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch; a.xs_log2 = -1;
+    a.tw = p->tw[0]; a.tw32 = p->tw32[0];
+    a.ntot = (double)p->n[0] * p->n[1] * p->n[2];
+    a.bins = spec;
+    a.nbins = nk * 5;
+    a.part_sum = (double*)(ws + L.part_sum);
+    a.part_cnt = (unsigned*)(ws + L.part_cnt);
+    a.max_grid = p->max_grid;
+    if (!xpass32_moments_applicable(p->dtype, a)) { set_error("fused multipoles: fp32, nx = 1024 and a spec with a segment table only"); return T21_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const void* x[2] = {x1, nullptr};
+    const void* offs[2] = {nullptr, nullptr};
+    prof_begin(st);
+    if (int rc = forward_zy(p, x, 1, subtract_mean, ws, L, offs, st)) return rc;
+    a.offset[0] = offs[0];
+    if (int rc = launch_xpass32_moments(a, los_axis, st)) return rc;
+    prof_mark(st, SLOT_X);
+    const int rc = launch_reduce_moments(a.part_sum, a.part_cnt, a.grid_used, nk, sums_out, counts_out, st);
+    prof_mark(st, SLOT_REDUCE);
+    return rc;
+}
+
 static int binned_windowed(const t21_plan* p, const void* x1, const int* window, const t21_binspec* spec, double* sums_out,
                            long long* counts_out, unsigned char* ws, const WsLayout& L, cudaStream_t st);
 
@@ -393,7 +437,7 @@ int t21_build_pencil_segments(const t21_binspec* spec, uint32_t* out, int stride
     cudaStream_t st = (cudaStream_t)stream;
     T21_CUDA_OK(cudaMemsetAsync(max_segments_dev, 0, sizeof(int), st));
     const bool is_signed = spec->nmu > 0 && !spec->absolute_mus;
-    if (!is_signed) return launch_pencil_segments(*spec, 0, out, stride, max_segments_dev, st);
+    if (!is_signed) return launch_pencil_segments(*spec, (spec->nmu == 0 && spec->exclude_zero) ? 5 : 0, out, stride, max_segments_dev, st);
     const size_t per_table = (size_t)spec->n[1] * (spec->n[2] / 2 + 1) * stride;
     for (int w = 1; w <= 4; ++w)
         if (int rc = launch_pencil_segments(*spec, w, out + (size_t)(w - 1) * per_table, stride, max_segments_dev, st)) return rc;

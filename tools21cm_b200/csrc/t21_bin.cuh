@@ -149,7 +149,9 @@ T21_HD unsigned segment_modes(bool lo, bool hi, unsigned a, unsigned b, unsigned
 }
 // which: 0  bins even in kx (shells, |mu|): the stored mode's bin, checked against its mirror nx - f;
 //        1 / 2  signed mu, the stored mode's own bin for kx = +f / kx = -f;
-//        3 / 4  signed mu, the bin of its Hermitian twin (-1 where the twin is itself stored) for kx = +f / -f.
+//        3 / 4  signed mu, the bin of its Hermitian twin (-1 where the twin is itself stored) for kx = +f / -f;
+//        5  shells for the multipole moments: as 0, minus the k_perp = 0 line of B.los_axis when B.exclude_zero is set
+//           (power_legendre.py:51, power_spectrum.py:563-575).
 T21_HD int build_pencil_segments(const t21_binspec& B, int iy, int iz, int which, unsigned* __restrict__ out, int stride) {
     const int nx = B.n[0], nz = B.n[2];
     const bool has_twin = (iz != 0) && (iz != nz - iz);
@@ -158,8 +160,14 @@ T21_HD int build_pencil_segments(const t21_binspec& B, int iy, int iz, int which
     for (int f = 0; f <= nx / 2; ++f) {
         const int ix = (which == 2 || which == 4) ? (nx - f) % nx : f;
         const ModeBins mb = classify(B, ix, iy, iz, has_twin);
-        const int b = which >= 3 ? mb.twin : mb.own;
-        if (which == 0 && f > 0 && f < nx - f && classify(B, nx - f, iy, iz, has_twin).own != b) bad = true;
+        int b = (which == 3 || which == 4) ? mb.twin : mb.own;
+        if (which == 5 && B.exclude_zero) {
+            const int los = B.los_axis;
+            const int pa = los == 0 ? iy : ix, pb = los == 2 ? iy : iz;
+            const int za = los == 0 ? B.zero_idx[1] : B.zero_idx[0], zb = los == 2 ? B.zero_idx[1] : B.zero_idx[2];
+            if (pa == za && pb == zb) b = -1;
+        }
+        if ((which == 0 || which == 5) && f > 0 && f < nx - f && classify(B, nx - f, iy, iz, has_twin).own != b) bad = true;
         if (b != prev) {
             if (s < stride) out[s] = ((unsigned)f << 16) | (unsigned)(b + 1);
             ++s;

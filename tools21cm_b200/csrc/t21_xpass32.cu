@@ -33,6 +33,7 @@ constexpr int BUF_BYTES = WZ * PITCH * 8;           // 67 712 >= the landed tile
 constexpr int BAR_OFF = (BUF_BYTES + 127) / 128 * 128;
 constexpr int STAGE_OFF = BAR_OFF + 128;           // per-warp strips of 32 x 32 powers (shells epilogue)
 constexpr int HIST_OFF = STAGE_OFF + (THREADS / 32) * 32 * 32 * 4;
+constexpr int kMoments = 5;                         // multipole sums per k bin: P, P L2, P L4, L2^2, L4^2
 using P = Plan<NX, 32>;
 static_assert(P::NS == 2 && P::T == 32 && P::E == 32, "one warp per pencil");
 
@@ -49,6 +50,7 @@ struct Params {
     const unsigned* seg;   // pencil segment table(s) (t21_build_pencil_segments) or null
     int seg_stride;
     long long seg_pencils; // pencils per table: ny_global * nzh
+    int mp_los;            // multipoles: line-of-sight axis
 };
 
 #if T21_DEVICE_CODE
@@ -318,6 +320,126 @@ __device__ __forceinline__ void epilogue_segments(const Params& p, cx<float>* v,
     }
 }
 
+// ---- multipole moments per k bin (power_legendre.py:55-87) on the same ranges ----------------------------------------
+// Five sums per range: P, P L2, P L4, L2^2, L4^2 with L2 = (3 mu^2 - 1)/2, L4 = 4.375 (mu^2 - 0.115587)(mu^2 - 0.741556)
+// as the reference writes them (:57-60), mu^2 = k_los^2 / k^2 from fp32 (a weight, not a decision: the bin comes from
+// the table).  k^2 = f^2 d + (ky^2 + kz^2) with f = |kx index| (exact up to 2^24) and d the squared kx spacing.  Modes
+// with k < 0.001 have mu = NaN in the reference (:501) and here.  The steps of a quarter pencil that hold a range
+// boundary park the running sums and their two powers; a rolled loop closes the ranges in order (five shuffle trees).
+struct MomentHist {
+    double* sum;      // [nk][5], this warp's copy
+    unsigned* cnt;    // [nk]
+};
+
+__device__ __forceinline__ void epilogue_multipoles(const Params& p, cx<float>* v, int lane, int iy, int iz, unsigned ent,
+                                                    float* __restrict__ strip, MomentHist& hist) {
+    const t21_binspec& B = p.bins;
+    const bool has_twin = (iz != 0) && (iz != p.nz - iz);
+    const unsigned wt = has_twin ? 2u : 1u;
+    const float wf = (float)wt;
+    const unsigned pos = ent >> 16, binp1 = ent & 0xFFFFu;
+    const unsigned S = (unsigned)__popc(__ballot_sync(0xffffffffu, pos != 0xFFFFu));
+    if (S == 1u && __shfl_sync(0xffffffffu, binp1, 0) == 0u) return;          // the whole pencil is in no bin
+    const unsigned mixed = __reduce_or_sync(0xffffffffu, ((unsigned)lane >= 1u && (unsigned)lane < S) ? 1u << ((pos - 1u) >> 5) : 0u);
+
+    const float d2 = ldg(B.tab_sf[0] + 1);                                   // squared kx spacing
+    const float sy = ldg(B.tab_sf[1] + iy), sz = ldg(B.tab_sf[2] + iz);
+    const float cyz = sy + sz;
+    const float klc = p.mp_los == 1 ? sy : sz;                               // k_los^2 when the line of sight is not x
+    const bool los_x = p.mp_los == 0;
+    const float snan = (float)B.s_nan;
+
+    if (iy == 0 && iz == 0) {
+        // DC of (x - c) plus c*N (see epilogue_segments): power 0 in the flow (its mu is NaN there, like the
+        // reference's), true power straight to the P sum of its bin
+        const int b0 = (int)__shfl_sync(0xffffffffu, binp1, 0) - 1;
+        if (lane == 0) {
+            const double c0 = p.offset ? (double)ldg(p.offset) : 0.0;
+            const double ra = (double)v[0].x + c0 * p.ntot;
+            const double dc = ra * ra + (double)v[0].y * (double)v[0].y;
+            v[0] = cmake<float>(0.f, 0.f);
+            if (b0 >= 0) hist.sum[b0 * kMoments] += dc;
+        }
+    }
+
+    // contribution of the mode |kx index| = f with power pw to five running sums
+    auto add_mode = [&](unsigned f, float pw, float* a) {
+        const float sx = (float)(f * f) * d2;
+        const float s = sx + cyz;
+        float mu2 = __fdividef(los_x ? sx : klc, s);
+        mu2 = s >= snan ? mu2 : __int_as_float(0x7fc00000);
+        const float l2 = fmaf(1.5f, mu2, -0.5f);
+        const float l4 = 4.375f * (mu2 - 0.115587f) * (mu2 - 0.741556f);
+        a[0] += pw; a[1] = fmaf(pw, l2, a[1]); a[2] = fmaf(pw, l4, a[2]); a[3] = fmaf(l2, l2, a[3]); a[4] = fmaf(l4, l4, a[4]);
+    };
+
+    float cur[kMoments] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    unsigned j = 0u;
+    unsigned nextpos = S > 1u ? __shfl_sync(0xffffffffu, pos, 1) : 0xFFFFu;
+    auto close = [&](unsigned b) {
+        float t[kMoments];
+#pragma unroll
+        for (int q = 0; q < kMoments; ++q) {
+            t[q] = cur[q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t[q] += __shfl_xor_sync(0xffffffffu, t[q], o);
+            cur[q] = 0.f;
+        }
+        const unsigned a = __shfl_sync(0xffffffffu, pos, j);
+        const int bin = (int)__shfl_sync(0xffffffffu, binp1, j) - 1;
+        if (lane == 0 && bin >= 0) {
+#pragma unroll
+            for (int q = 0; q < kMoments; ++q) hist.sum[bin * kMoments + q] += (double)(t[q] * wf);
+            hist.cnt[bin] += segment_modes(true, true, a, b, (unsigned)(NX / 2)) * wt;
+        }
+    };
+#pragma unroll
+    for (int quarter = 0; quarter < 4; ++quarter) {
+        float run[kMoments] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        unsigned slot = 0u, ks = 0u;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const int k = quarter * 4 + kk;
+            const float plo = v[k].x * v[k].x + v[k].y * v[k].y;
+            const float phi = v[31 - k].x * v[31 - k].x + v[31 - k].y * v[31 - k].y;
+            if ((mixed >> k) & 1u) {
+                float* d = strip + slot * 224u + lane;                       // 7 values per slot and lane
+#pragma unroll
+                for (int q = 0; q < kMoments; ++q) { d[32 * q] = run[q]; run[q] = 0.f; }
+                d[160] = plo;
+                d[192] = phi;
+                ks |= (unsigned)k << (4u * slot);
+                ++slot;
+            } else {
+                add_mode(32u * k + (unsigned)lane, plo, run);
+                add_mode(32u * k + 32u - (unsigned)lane, phi, run);
+            }
+        }
+#pragma unroll 1
+        for (unsigned i = 0; i < slot; ++i) {
+            const float* d = strip + i * 224u + lane;
+#pragma unroll
+            for (int q = 0; q < kMoments; ++q) cur[q] += d[32 * q];
+            const float plo = d[160], phi = d[192];
+            const unsigned k32 = ((ks >> (4u * i)) & 15u) << 5;
+            const unsigned flo = k32 + (unsigned)lane, fhi = k32 + 32u - (unsigned)lane;
+            bool lo_open = true, hi_open = true;
+            while (nextpos <= k32 + 32u) {                  // warp-uniform: a boundary inside this step
+                if (lo_open && flo < nextpos) { add_mode(flo, plo, cur); lo_open = false; }
+                if (hi_open && fhi < nextpos) { add_mode(fhi, phi, cur); hi_open = false; }
+                close(nextpos);
+                ++j;
+                nextpos = j + 1u < S ? __shfl_sync(0xffffffffu, pos, (j + 1u) & 31u) : 0xFFFFu;
+            }
+            if (lo_open) add_mode(flo, plo, cur);
+            if (hi_open) add_mode(fhi, phi, cur);
+        }
+#pragma unroll
+        for (int q = 0; q < kMoments; ++q) cur[q] += run[q];
+    }
+    close((unsigned)(NX / 2 + 1));
+}
+
 template <int NT, class Hist>
 __device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& p, unsigned char* smem_raw, Hist& hist, int nbins) {
     cx<float>* buf = reinterpret_cast<cx<float>*>(smem_raw);
@@ -326,7 +448,7 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& 
     const int zl0 = tid & (WZ - 1), j0 = tid >> 3;          // stage 0: lanes across the columns
 
     WarpBinCache wbc;
-    wbc_init(wbc);
+    if constexpr (NT == 0) wbc_init(wbc);
 
     auto issue = [&](long long tile) {
         const unsigned chunk = (unsigned)tile / (unsigned)p.ny;
@@ -352,9 +474,10 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& 
         cx<float> v[32];
         const int iz = (int)chunk * WZ + warp;
         // this pencil's ranges: asked for now, needed after the two butterfly stages
-        unsigned ent[NT > 0 ? NT : 1];
+        constexpr int NTAB = NT == 4 ? 4 : 1;             // NT: 0 in-kernel shells, 1 one table, 4 signed mu, 5 multipoles
+        unsigned ent[NTAB];
 #pragma unroll
-        for (int t = 0; t < (NT > 0 ? NT : 1); ++t) {
+        for (int t = 0; t < NTAB; ++t) {
             ent[t] = kSegSentinel;
             if (NT > 0 && lane < p.seg_stride && iz < p.nzh)
                 ent[t] = ldg(p.seg + ((size_t)t * p.seg_pencils + (size_t)iy * p.nzh + iz) * p.seg_stride + lane);
@@ -392,7 +515,8 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& 
         DFT<32, float>::run(v);                            // v[k] = X[lane + 32 k]
         if (iz < p.nzh) {
             float* stage = reinterpret_cast<float*>(smem_raw + STAGE_OFF) + warp * 1024;
-            if constexpr (NT > 0) epilogue_segments<NT>(p, v, lane, iy, iz, ent, stage, hist);
+            if constexpr (NT == 5) epilogue_multipoles(p, v, lane, iy, iz, ent[0], stage, hist);
+            else if constexpr (NT > 0) epilogue_segments<NT>(p, v, lane, iy, iz, ent, stage, hist);
             else epilogue_shells(p, v, lane, iy, iz, stage, wbc, hist);
         }
     }
@@ -433,13 +557,47 @@ xpass32_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ 
 #endif
 }
 
+// multipole moments: per-warp private [nk][5] sums + [nk] counts, same fixed summation order
+__global__ void __launch_bounds__(THREADS, 2)
+xpass32_moments_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ Params p, int nk,
+                       double* __restrict__ part_sum, unsigned* __restrict__ part_cnt) {
+#if T21_DEVICE_CODE
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(smem_raw + BAR_OFF, 1);
+        mbar_init_fence();
+    }
+    constexpr int NW = THREADS / 32;
+    const int ns = nk * kMoments;
+    double* hs = reinterpret_cast<double*>(smem_raw + HIST_OFF);
+    unsigned* hc = reinterpret_cast<unsigned*>(hs + (size_t)NW * ns);
+    for (int b = tid; b < NW * ns; b += THREADS) hs[b] = 0.0;
+    for (int b = tid; b < NW * nk; b += THREADS) hc[b] = 0u;
+    __syncthreads();
+    MomentHist hist{hs + (size_t)(tid >> 5) * ns, hc + (size_t)(tid >> 5) * nk};
+    run_tiles<5>(&map, p, smem_raw, hist, ns);
+    __syncthreads();
+    for (int b = tid; b < ns; b += THREADS) {
+        double s = 0.0;
+        for (int w = 0; w < NW; ++w) s += hs[(size_t)w * ns + b];
+        part_sum[(size_t)blockIdx.x * ns + b] = s;
+    }
+    for (int b = tid; b < nk; b += THREADS) {
+        unsigned c = 0;
+        for (int w = 0; w < NW; ++w) c += hc[(size_t)w * nk + b];
+        part_cnt[(size_t)blockIdx.x * nk + b] = c;
+    }
+#endif
+}
+
 // T21_X32_SEGMENTS=0 keeps the in-kernel boundary search even when the spec carries a table (A/B runs); read once
 static bool use_segments() {
     static const bool on = [] { const char* e = getenv("T21_X32_SEGMENTS"); return !(e && e[0] == '0'); }();
     return on;
 }
 
-static int launch(XArgs& a, cudaStream_t st) {
+static int launch(XArgs& a, cudaStream_t st, int moments_los = -1) {
     Params p;
     memset(&p, 0, sizeof(p));
     p.ny = a.ny; p.nz = a.nz; p.nzh = a.nzh; p.iy0 = a.iy0;
@@ -457,6 +615,27 @@ static int launch(XArgs& a, cudaStream_t st) {
     p.seg_pencils = (long long)a.bins->n[1] * a.nzh;
     const int nt = (p.seg != nullptr && use_segments()) ? a.bins->seg_ntab : 0;
     if (nt != 0 && nt != 1 && nt != 4) { set_error("bad segment table count %d", nt); return T21_EINVAL; }
+    p.mp_los = moments_los;
+    if (moments_los >= 0) {
+        if (nt != 1 || a.bins->nmu != 0) { set_error("the fused multipole pass needs a shell spec with one segment table"); return T21_EINVAL; }
+        const int nk = a.bins->nk;
+        const size_t smem_m = HIST_OFF + (size_t)(THREADS / 32) * nk * (kMoments * 8 + 4);
+        auto kern_m = xpass32_moments_kernel;
+        if (int rc = ensure_smem(kern_m, smem_m)) return rc;
+        int occ_m = 0;
+        T21_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_m, kern_m, THREADS, smem_m));
+        if (occ_m < 1) { set_error("x pass (multipoles) does not fit on an SM (smem %zu)", smem_m); return T21_EINVAL; }
+        CUtensorMap map_m;
+        if (int rc = make_wmap_f32(&map_m, a.w[0], nxs, a.ny, a.pitch / WZ, NX / nxs, p.box_rows)) return rc;
+        long long gm = (long long)occ_m * device_sm_count();
+        if (gm > p.ntiles) gm = p.ntiles;
+        if (gm > a.max_grid) gm = a.max_grid;
+        kern_m<<<(int)gm, THREADS, smem_m, st>>>(map_m, p, nk, a.part_sum, a.part_cnt);
+        count_launch();
+        T21_CUDA_OK(cudaGetLastError());
+        a.grid_used = (int)gm;
+        return 0;
+    }
     CUtensorMap map;
     if (int rc = make_wmap_f32(&map, a.w[0], nxs, a.ny, a.pitch / WZ, NX / nxs, p.box_rows)) return rc;
 
@@ -495,6 +674,15 @@ bool xpass32_applicable(int dtype, const XArgs& a) {
 
 int launch_xpass32_bin(XArgs& a, cudaStream_t st) {
     return x32::launch(a, st);
+}
+
+// multipole moments fused into the X pass: fp32, nx = 1024, one field, a shell spec that carries its segment table
+bool xpass32_moments_applicable(int dtype, const XArgs& a) {
+    return dtype == T21_F32 && a.nx == x32::NX && a.nf == 1 && a.bins != nullptr && a.tw32 != nullptr && a.pitch % x32::WZ == 0 &&
+           a.bins->seg_tab != nullptr && a.bins->seg_ntab == 1 && a.bins->nmu == 0 && a.bins->nk <= 64 && x32::use_segments();
+}
+int launch_xpass32_moments(XArgs& a, int los_axis, cudaStream_t st) {
+    return x32::launch(a, st, los_axis);
 }
 
 }  // namespace t21

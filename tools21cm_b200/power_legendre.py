@@ -40,26 +40,46 @@ def power_spectrum_multipoles(input_array, kbins=10, box_dims=None, los_axis=0, 
     shape = tuple(x.shape)
     if len(shape) != 3 or los_axis > 2:
         raise ValueError("power_spectrum_multipoles needs a 3-D array and a line of sight along one of its axes")
-    power = _ps._fused_half([x], _bs.volume_scale(shape, box_dims), x.dtype)
     dev = _ps._device(x.device.index)
-    key = ("multipoles", _ps._freeze(list(box_dims)), _ps._freeze(kbins), int(los_axis))
-    spec, cspec, _owner = dev.spec((shape, key), lambda: _bs.build_binspec(
-        shape, box_dims, kbins, binning="log", los_axis=los_axis, last_bin_closed=False, shells_with_los=True))
+    # the excluded line only exists when both perpendicular axes are even (power_spectrum.py:567-573 compares an
+    # integer index with N/2 as a float)
+    perp = [a for a in (0, 1, 2) if a != los_axis]
+    excl = bool(exclude_zero_modes) and all(shape[a] % 2 == 0 for a in perp)
+    key = ("multipoles", _ps._freeze(list(box_dims)), _ps._freeze(kbins), int(los_axis), excl)
+
+    def make_spec():
+        sp = _bs.build_binspec(shape, box_dims, kbins, binning="log", los_axis=los_axis, last_bin_closed=False,
+                               shells_with_los=True)
+        sp.exclude_zero = excl        # shells otherwise ignore both; the segment table of the fused pass drops the
+        sp.los_axis = int(los_axis)   # k_perp = 0 line of this axis
+        return sp
+
+    code = _ps._dtype_code(x)
+    fused = code == _lib.T21_F32 and shape[0] == 1024
+    spec, cspec, _owner = dev.spec((shape, key), make_spec, segments=fused)
     nk = spec.nk
+    scale = _bs.volume_scale(shape, box_dims)
     with torch.cuda.device(x.device):
         lib = _lib.load()
-        ws = dev.workspace(lib.t21_bin_multipoles_workspace_bytes(nk))
         sums = torch.empty(nk * 5, dtype=torch.float64, device=x.device)
         counts = torch.empty(nk, dtype=torch.int64, device=x.device)
-        # the excluded line only exists when both perpendicular axes are even (power_spectrum.py:567-573 compares an
-        # integer index with N/2 as a float)
-        perp = [a for a in (0, 1, 2) if a != los_axis]
-        excl = bool(exclude_zero_modes) and all(shape[a] % 2 == 0 for a in perp)
-        rc = lib.t21_bin_multipoles_half(power.data_ptr(), _ps._dtype_code(power), int(power.shape[2]), C.byref(cspec), int(los_axis), int(excl),
-                                         sums.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(),
-                                         _ps._stream_ptr(torch, x.device.index))
-        _lib.check(rc, "t21_bin_multipoles_half")
-        s = sums.cpu().numpy().reshape(nk, 5)
+        if fused and cspec.seg_tab and nk <= 64:
+            # one pipeline: Z / Y passes, then the warp-per-pencil X pass adds the five sums per bin from its registers
+            plan = dev.plan(shape, code)
+            ws = dev.workspace(lib.t21_workspace_bytes(plan, 1, 5 * nk))
+            rc = lib.t21_ps_multipoles(plan, x.data_ptr(), 1, C.byref(cspec), int(los_axis), sums.data_ptr(), counts.data_ptr(),
+                                       ws.data_ptr(), ws.numel(), _ps._stream_ptr(torch, x.device.index))
+            _lib.check(rc, "t21_ps_multipoles")
+            s = sums.cpu().numpy().reshape(nk, 5)
+            s[:, :3] *= scale                      # the three sums that carry the power
+        else:
+            power = _ps._fused_half([x], scale, x.dtype)
+            ws = dev.workspace(lib.t21_bin_multipoles_workspace_bytes(nk))
+            rc = lib.t21_bin_multipoles_half(power.data_ptr(), _ps._dtype_code(power), int(power.shape[2]), C.byref(cspec), int(los_axis), int(excl),
+                                             sums.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(),
+                                             _ps._stream_ptr(torch, x.device.index))
+            _lib.check(rc, "t21_bin_multipoles_half")
+            s = sums.cpu().numpy().reshape(nk, 5)
         n = counts.cpu().numpy().astype("float")
     multipoles = {}
     with np.errstate(all="ignore"):

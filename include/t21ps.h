@@ -102,6 +102,13 @@ typedef struct t21_binspec {
  * the table is unusable (rebuild with a larger stride, 32 at most; above 32 the X pass classifies per mode). */
 T21_API int t21_build_pencil_segments(const t21_binspec* spec, uint32_t* out, int stride, int* max_segments_dev, void* stream);
 
+/* The same table for the (k_perp, k_par) bins of power_spectrum_2d (power_spectrum.py:177-254), from the separable tables of
+ * t21_bin_cyl_half (FFT index order; flat bin = perp * npar + par).  A t21_binspec that carries only n, nk = nperp * npar,
+ * nmu = 0 and this table (every other pointer NULL) makes t21_ps_binned the fused form of that estimator; such a
+ * table-only spec is refused (T21_EINVAL) wherever the warp-per-pencil X pass does not apply. */
+T21_API int t21_build_pencil_segments_cyl(int n0, int n1, int n2, int nu_axis, const int* perp_tab, const int* par_tab, int nperp,
+                                          int npar, uint32_t* out, int stride, int* max_segments_dev, void* stream);
+
 /* Plan for real cubes of shape (nx, ny, nz), C order.  dtype T21_F32 / T21_F64 is the
  * arithmetic type of the transform.  Replaces the implicit scipy.fftpack plan behind
  * power_spectrum.py:45,85-86. */

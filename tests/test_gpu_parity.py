@@ -205,6 +205,24 @@ def test_fused_multipoles_on_the_warp_per_pencil_pass(t2c, shape, los):
         np.testing.assert_allclose(got["P4"], want["P4"], rtol=1e-4, atol=atol, equal_nan=True)
 
 
+@pytest.mark.parametrize("shape", [(1024, 16, 32), (1024, 32, 16)])
+@pytest.mark.parametrize("nu_axis", [0, 1, 2])
+def test_fused_power_spectrum_2d_on_the_warp_per_pencil_pass(t2c, shape, nu_axis):
+    """fp32 cubes with nx = 1024: the (k_perp, k_par) bins are index ranges along x pencils too, so power_spectrum_2d runs
+    as t21_ps_binned with a table-only spec (t21_build_pencil_segments_cyl).  Against the oracle for every nu_axis; the
+    mode counts come from the kernel's closed-form range counts and must equal the reference's."""
+    from oracle import ps_oracle
+    x = (np.random.default_rng(23 + nu_axis).standard_normal(shape) + 0.5).astype(np.float32)
+    box = [300.0, 40.0, 60.0]
+    for binning in ("log", "linear"):
+        got = t2c.power_spectrum_2d(x, kbins=8, binning=binning, box_dims=box, return_modes=True, nu_axis=nu_axis)
+        with np.errstate(all="ignore"):
+            want = ps_oracle.power_spectrum_2d(x, kbins=8, binning=binning, box_dims=box, return_modes=True, nu_axis=nu_axis)
+        assert np.array_equal(got[3], want[3]), "n_modes differ"
+        assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+        np.testing.assert_allclose(got[0], want[0], rtol=1e-5, equal_nan=True)
+
+
 @pytest.mark.parametrize("n,ncuts,dtype", [(64, 4, "float32"), (128, 2, "float32"), (64, 2, "float64"), (48, 3, "float64")])
 def test_integrated_bispectrum_against_oracle(t2c, n, ncuts, dtype):
     """The batched windowed estimator (mask fused into the Z-pass load) against the reference's loop over masked full

@@ -202,6 +202,8 @@ def load():
     lib.t21_c2ray_dt.restype = i32
     lib.t21_build_pencil_segments.argtypes = [C.POINTER(BinSpecC), vp, i32, vp, vp]
     lib.t21_build_pencil_segments.restype = i32
+    lib.t21_build_pencil_segments_cyl.argtypes = [i32, i32, i32, i32, vp, vp, i32, i32, vp, i32, vp, vp]
+    lib.t21_build_pencil_segments_cyl.restype = i32
     lib.t21_profile.argtypes = [i32]
     lib.t21_profile.restype = i32
     lib.t21_profile_last.argtypes = [C.POINTER(C.c_float), i32]

@@ -271,6 +271,9 @@ int t21_ps_binned(const t21_plan* p, const void* x1, const void* x2, int subtrac
     a.gsum = sums_out;
     a.gcnt = (unsigned long long*)counts_out;
     a.max_grid = p->max_grid;
+    if (!spec->thr && !(p->fast[0] && xpass32_applicable(p->dtype, a))) {
+        set_error("a table-only bin spec (no thresholds) can only run on the warp-per-pencil X pass"); return T21_EINVAL;
+    }
     if (a.hist_global)
         if (int rc = launch_zero_hist(sums_out, counts_out, nbins, st)) return rc;
     int rc = !p->fast[0] ? launch_xpass_generic(p->dtype, a, st)
@@ -442,6 +445,18 @@ int t21_build_pencil_segments(const t21_binspec* spec, uint32_t* out, int stride
     for (int w = 1; w <= 4; ++w)
         if (int rc = launch_pencil_segments(*spec, w, out + (size_t)(w - 1) * per_table, stride, max_segments_dev, st)) return rc;
     return T21_OK;
+}
+
+int t21_build_pencil_segments_cyl(int n0, int n1, int n2, int nu_axis, const int* perp_tab, const int* par_tab, int nperp, int npar,
+                                  uint32_t* out, int stride, int* max_segments_dev, void* stream) {
+    if (!perp_tab || !par_tab || !out || !max_segments_dev) { set_error("null argument to t21_build_pencil_segments_cyl"); return T21_EINVAL; }
+    if (stride != 8 && stride != 16 && stride != 32) { set_error("segment stride must be 8, 16 or 32"); return T21_EINVAL; }
+    if (n0 < 2 || n0 >= 65535 || n1 < 1 || n2 < 1 || nu_axis < 0 || nu_axis > 2 || nperp < 1 || npar < 1 || (long long)nperp * npar >= 65535) {
+        set_error("bad argument to t21_build_pencil_segments_cyl"); return T21_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    T21_CUDA_OK(cudaMemsetAsync(max_segments_dev, 0, sizeof(int), st));
+    return launch_pencil_segments_cyl(n0, n1, n2, nu_axis, perp_tab, par_tab, npar, out, stride, max_segments_dev, st);
 }
 
 int t21_profile(int enable) {

@@ -596,6 +596,27 @@ pencil_segments_kernel(const __grid_constant__ t21_binspec B, int which, unsigne
     if ((threadIdx.x & 31) == 0 && s > 0) atomicMax(max_seg, s);
 }
 
+__global__ void __launch_bounds__(128)
+pencil_segments_cyl_kernel(int n0, int n1, int n2, int nu_axis, const int* __restrict__ perp_tab, const int* __restrict__ par_tab,
+                           int npar, unsigned* __restrict__ out, int stride, int* __restrict__ max_seg) {
+    const int nzh = n2 / 2 + 1;
+    const long long np = (long long)n1 * nzh;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int s = 0;
+    if (i < np) s = build_pencil_segments_cyl(n0, n1, n2, nu_axis, perp_tab, par_tab, npar, (int)(i / nzh), (int)(i % nzh), out + i * stride, stride);
+    for (int o = 16; o > 0; o >>= 1) { const int t = __shfl_xor_sync(0xffffffffu, s, o); s = t > s ? t : s; }
+    if ((threadIdx.x & 31) == 0 && s > 0) atomicMax(max_seg, s);
+}
+
+int launch_pencil_segments_cyl(int n0, int n1, int n2, int nu_axis, const int* perp_tab, const int* par_tab, int npar,
+                               unsigned* out, int stride, int* max_seg_dev, cudaStream_t st) {
+    const long long np = (long long)n1 * (n2 / 2 + 1);
+    pencil_segments_cyl_kernel<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(n0, n1, n2, nu_axis, perp_tab, par_tab, npar, out, stride, max_seg_dev);
+    count_launch();
+    T21_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int launch_pencil_segments(const t21_binspec& spec, int which, unsigned* out, int stride, int* max_seg_dev, cudaStream_t st) {
     const long long np = (long long)spec.n[1] * (spec.n[2] / 2 + 1);
     pencil_segments_kernel<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(spec, which, out, stride, max_seg_dev);

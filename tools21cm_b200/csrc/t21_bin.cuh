@@ -152,22 +152,14 @@ T21_HD unsigned segment_modes(bool lo, bool hi, unsigned a, unsigned b, unsigned
 //        3 / 4  signed mu, the bin of its Hermitian twin (-1 where the twin is itself stored) for kx = +f / -f;
 //        5  shells for the multipole moments: as 0, minus the k_perp = 0 line of B.los_axis when B.exclude_zero is set
 //           (power_legendre.py:51, power_spectrum.py:563-575).
-T21_HD int build_pencil_segments(const t21_binspec& B, int iy, int iz, int which, unsigned* __restrict__ out, int stride) {
-    const int nx = B.n[0], nz = B.n[2];
-    const bool has_twin = (iz != 0) && (iz != nz - iz);
+// bin_of(ix) -> flat bin or -1, for ix = f (and ix = nx - f when `mirror_of` is asked to agree)
+template <class BinOf>
+T21_HD int emit_pencil_segments(int nx, bool check_mirror, bool negative_half, BinOf&& bin_of, unsigned* __restrict__ out, int stride) {
     int s = 0, prev = -2;
     bool bad = false;
     for (int f = 0; f <= nx / 2; ++f) {
-        const int ix = (which == 2 || which == 4) ? (nx - f) % nx : f;
-        const ModeBins mb = classify(B, ix, iy, iz, has_twin);
-        int b = (which == 3 || which == 4) ? mb.twin : mb.own;
-        if (which == 5 && B.exclude_zero) {
-            const int los = B.los_axis;
-            const int pa = los == 0 ? iy : ix, pb = los == 2 ? iy : iz;
-            const int za = los == 0 ? B.zero_idx[1] : B.zero_idx[0], zb = los == 2 ? B.zero_idx[1] : B.zero_idx[2];
-            if (pa == za && pb == zb) b = -1;
-        }
-        if ((which == 0 || which == 5) && f > 0 && f < nx - f && classify(B, nx - f, iy, iz, has_twin).own != b) bad = true;
+        const int b = bin_of(negative_half ? (nx - f) % nx : f);
+        if (check_mirror && f > 0 && f < nx - f && bin_of(nx - f) != b) bad = true;
         if (b != prev) {
             if (s < stride) out[s] = ((unsigned)f << 16) | (unsigned)(b + 1);
             ++s;
@@ -176,6 +168,34 @@ T21_HD int build_pencil_segments(const t21_binspec& B, int iy, int iz, int which
     }
     for (int j = s; j < stride; ++j) out[j] = kSegSentinel;
     return (bad || s > stride) ? stride + 1 : s;
+}
+
+T21_HD int build_pencil_segments(const t21_binspec& B, int iy, int iz, int which, unsigned* __restrict__ out, int stride) {
+    const int nz = B.n[2];
+    const bool has_twin = (iz != 0) && (iz != nz - iz);
+    return emit_pencil_segments(B.n[0], which == 0 || which == 5, which == 2 || which == 4, [&](int ix) {
+        const ModeBins mb = classify(B, ix, iy, iz, has_twin);
+        int b = (which == 3 || which == 4) ? mb.twin : mb.own;
+        if (which == 5 && B.exclude_zero) {
+            const int los = B.los_axis;
+            const int pa = los == 0 ? iy : ix, pb = los == 2 ? iy : iz;
+            const int za = los == 0 ? B.zero_idx[1] : B.zero_idx[0], zb = los == 2 ? B.zero_idx[1] : B.zero_idx[2];
+            if (pa == za && pb == zb) b = -1;
+        }
+        return b;
+    }, out, stride);
+}
+
+// (k_perp, k_par) bins of power_spectrum_2d (power_spectrum.py:177-254) from the separable host-built tables in FFT
+// index order (binspec.build_cyl_tables): flat bin = perp * npar + par, -1 if either part is outside its bins
+T21_HD int build_pencil_segments_cyl(int n0, int n1, int n2, int nu_axis, const int* __restrict__ perp_tab,
+                                     const int* __restrict__ par_tab, int npar, int iy, int iz, unsigned* __restrict__ out, int stride) {
+    return emit_pencil_segments(n0, true, false, [&](int ix) {
+        const int pe = nu_axis == 2 ? ldg(perp_tab + (long long)ix * n1 + iy)
+                                    : ldg(perp_tab + (long long)(nu_axis == 1 ? ix : iy) * n2 + iz);
+        const int pa = ldg(par_tab + (nu_axis == 2 ? iz : (nu_axis == 1 ? iy : ix)));
+        return (pe < 0 || pa < 0) ? -1 : pe * npar + pa;
+    }, out, stride);
 }
 
 // ---- accumulators ---------------------------------------------------------------------

@@ -82,6 +82,9 @@ int launch_reduce_moments(const double* part_sum, const unsigned* part_cnt, int 
 
 int launch_pencil_segments(const t21_binspec& spec, int which, unsigned* out, int stride, int* max_seg_dev, cudaStream_t st);
 
+int launch_pencil_segments_cyl(int n0, int n1, int n2, int nu_axis, const int* perp_tab, const int* par_tab, int npar,
+                               unsigned* out, int stride, int* max_seg_dev, cudaStream_t st);
+
 // error plumbing (t21_api.cu)
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);

@@ -55,6 +55,7 @@ class _Device:
         self.plans = {}
         self.specs = OrderedDict()
         self.cyls = OrderedDict()
+        self.cylsegs = OrderedDict()
         self.ws = {}
         self._scratch = {}
 
@@ -115,6 +116,26 @@ class _Device:
             self._attach_segments(hit)
         return hit
 
+    def _segment_table(self, entries_per_stride, build):
+        """Run a segment-table builder with 32 entries per pencil, then again with 8 or 16 if that is all any pencil
+        needs.  Returns (int32 tensor, stride) or (None, 0) when some pencil needs more than 32 ranges."""
+        torch = _torch()
+        dev = "cuda:%d" % self.index
+        maxseg = torch.zeros(1, dtype=torch.int32, device=dev)
+        stream = _stream_ptr(torch, self.index)
+        stride = 32
+        for _ in range(2):
+            table = torch.empty(entries_per_stride * stride, dtype=torch.int32, device=dev)
+            build(table.data_ptr(), stride, maxseg.data_ptr(), stream)
+            m = int(maxseg.item())
+            if m > stride:
+                return None, 0
+            want = 8 if m <= 8 else (16 if m <= 16 else 32)
+            if want == stride:
+                break
+            stride = want
+        return table, stride
+
     def _attach_segments(self, hit):
         """The pencil segment table of the warp-per-pencil X pass (``t21_build_pencil_segments``): along an x pencil the
         bins are index ranges, found once per (shape, bin spec) on the device with the per-mode classification of the
@@ -129,29 +150,46 @@ class _Device:
         if spec.shape[0] != 1024 or spec.nbins > 128 or int(spec.zero_idx[0]) != 0:
             return
         ntab = 4 if (spec.nmu and not spec.absolute_mus) else 1      # signed mu: own / twin bins for kx >= 0 and kx < 0
-        torch = _torch()
         lib = _lib.load()
-        dev = "cuda:%d" % self.index
         npencils = int(spec.shape[1]) * (int(spec.shape[2]) // 2 + 1)
-        maxseg = torch.zeros(1, dtype=torch.int32, device=dev)
-        stream = _stream_ptr(torch, self.index)
-        stride, table = 32, None
-        for _ in range(2):
-            table = torch.empty(ntab * npencils * stride, dtype=torch.int32, device=dev)
-            _lib.check(lib.t21_build_pencil_segments(C.byref(cspec), table.data_ptr(), stride, maxseg.data_ptr(), stream),
-                       "t21_build_pencil_segments")
-            m = int(maxseg.item())
-            if m > stride:
-                return                      # some pencil needs more ranges than the table holds: classify per mode
-            want = 8 if m <= 8 else (16 if m <= 16 else 32)
-            if want == stride:
-                break
-            stride = want
+        table, stride = self._segment_table(ntab * npencils, lambda ptr, st, mx, stream: _lib.check(
+            lib.t21_build_pencil_segments(C.byref(cspec), ptr, st, mx, stream), "t21_build_pencil_segments"))
+        if table is None:
+            return                          # some pencil needs more ranges than a table holds: classify per mode
         owners.append(table)
         cspec.seg_tab = table.data_ptr()
         cspec.seg_stride = stride
         cspec.seg_ntab = ntab
 
+
+    def cyl_segments(self, key, cyl, perp, par, nu_axis):
+        """(table-only BinSpecC, table) for the fused power_spectrum_2d, or None: the pencil segment table of the
+        (k_perp, k_par) bins (``t21_build_pencil_segments_cyl``), cached beside the separable tables it is made from."""
+        hit = self.cylsegs.get(key)
+        if hit is None:
+            if os.environ.get("T21_X32_SEGMENTS", "1") == "0":
+                return None
+            lib = _lib.load()
+            n0, n1, n2 = (int(v) for v in key[0])
+            table, stride = self._segment_table(n1 * (n2 // 2 + 1), lambda ptr, st, mx, stream: _lib.check(
+                lib.t21_build_pencil_segments_cyl(n0, n1, n2, nu_axis, perp.data_ptr(), par.data_ptr(), cyl.nperp, cyl.npar,
+                                                  ptr, st, mx, stream), "t21_build_pencil_segments_cyl"))
+            if table is None:
+                hit = (None, None)
+            else:
+                c = _lib.BinSpecC()
+                for d in range(3):
+                    c.n[d] = key[0][d]
+                    c.nyq_idx[d] = -1
+                c.nk, c.nmu, c.los_axis = cyl.nperp * cyl.npar, 0, -1
+                c.seg_tab, c.seg_stride, c.seg_ntab = table.data_ptr(), stride, 1
+                hit = (c, table)
+            self.cylsegs[key] = hit
+            while len(self.cylsegs) > 8:
+                self.cylsegs.popitem(last=False)
+        else:
+            self.cylsegs.move_to_end(key)
+        return hit if hit[0] is not None else None
 
     def cyl(self, key, builder):
         """(CylSpec, perp table, par table) of power_spectrum_2d, tables resident on the device."""
@@ -659,24 +697,39 @@ def power_spectrum_2d(input_array, kbins=10, binning="log", box_dims=244 / .7, r
     shape = tuple(x.shape)
     if len(shape) != 3:
         raise ValueError("power_spectrum_2d needs a 3-D array")
-    # the power of the computed half spectrum in the transform's own precision (a quarter of the reference's
-    # fftshifted float64 cube, :229), then the separable (k_perp, k_par) tables applied to it
-    power = _fused_half([x], _bs.volume_scale(shape, box_dims), x.dtype)
     dev = _device(x.device.index)
-    cyl, perp, par = dev.cyl((shape, _freeze(list(box_dims)), _freeze(kbins), binning, int(nu_axis)),
-                             lambda: _bs.build_cyl_tables(shape, box_dims, kbins, binning=binning, nu_axis=nu_axis,
-                                                          order="fft"))
+    ckey = (shape, _freeze(list(box_dims)), _freeze(kbins), binning, int(nu_axis))
+    cyl, perp, par = dev.cyl(ckey, lambda: _bs.build_cyl_tables(shape, box_dims, kbins, binning=binning, nu_axis=nu_axis,
+                                                                order="fft"))
+    nb = cyl.nperp * cyl.npar
+    scale = _bs.volume_scale(shape, box_dims)
+    code = _dtype_code(x)
+    cseg = dev.cyl_segments(ckey, cyl, perp, par, int(nu_axis)) if (code == T21_F32 and shape[0] == 1024 and nb <= 128) else None
     with torch.cuda.device(x.device):
         lib = _lib.load()
-        nb = cyl.nperp * cyl.npar
-        ws = dev.workspace(lib.t21_bin_cyl_workspace_bytes(cyl.nperp, cyl.npar))
         sums = torch.empty(nb, dtype=torch.float64, device=x.device)
-        rc = lib.t21_bin_cyl_half(power.data_ptr(), _dtype_code(power), shape[0], shape[1], shape[2], int(power.shape[2]),
-                                  int(nu_axis), perp.data_ptr(), par.data_ptr(), cyl.nperp, cyl.npar, sums.data_ptr(),
-                                  ws.data_ptr(), ws.numel(), _stream_ptr(torch, x.device.index))
-        _lib.check(rc, "t21_bin_cyl_half")
-        s = sums.cpu().numpy().reshape(cyl.nperp, cyl.npar)
-        n = cyl.counts()          # separable bins: (index pairs in the perp bin) x (indices in the par bin), exact
+        if cseg is not None:
+            # fused: along an x pencil the (k_perp, k_par) bins are index ranges too, so the warp-per-pencil X pass adds
+            # them from its registers (t21_ps_binned with a table-only spec); no power array is written
+            plan = dev.plan(shape, code)
+            ws = dev.workspace(lib.t21_workspace_bytes(plan, 1, nb))
+            counts = torch.empty(nb, dtype=torch.int64, device=x.device)
+            rc = lib.t21_ps_binned(plan, x.data_ptr(), None, 1, C.byref(cseg[0]), sums.data_ptr(), counts.data_ptr(),
+                                   ws.data_ptr(), ws.numel(), _stream_ptr(torch, x.device.index))
+            _lib.check(rc, "t21_ps_binned")
+            s = sums.cpu().numpy().reshape(cyl.nperp, cyl.npar) * scale
+            n = counts.cpu().numpy().astype(float).reshape(cyl.nperp, cyl.npar)
+        else:
+            # the power of the computed half spectrum in the transform's own precision (a quarter of the reference's
+            # fftshifted float64 cube, :229), then the separable (k_perp, k_par) tables applied to it
+            power = _fused_half([x], scale, x.dtype)
+            ws = dev.workspace(lib.t21_bin_cyl_workspace_bytes(cyl.nperp, cyl.npar))
+            rc = lib.t21_bin_cyl_half(power.data_ptr(), _dtype_code(power), shape[0], shape[1], shape[2], int(power.shape[2]),
+                                      int(nu_axis), perp.data_ptr(), par.data_ptr(), cyl.nperp, cyl.npar, sums.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), _stream_ptr(torch, x.device.index))
+            _lib.check(rc, "t21_bin_cyl_half")
+            s = sums.cpu().numpy().reshape(cyl.nperp, cyl.npar)
+            n = cyl.counts()          # separable bins: (index pairs in the perp bin) x (indices in the par bin), exact
     ps = _finish(s, n, 1.0)
     if return_modes:
         return ps, cyl.kper_mid, cyl.kpar_mid, n

@@ -132,6 +132,12 @@ inline int launch_tiles(const typename K::Params& p, long long nctas, cudaStream
     return 0;
 }
 
+// T21_X_SEGMENTS=0: the CTA-per-tile X pass classifies per mode even when the spec carries a segment table (A/B runs)
+inline bool x_use_segments() {
+    static const bool on = [] { const char* e = getenv("T21_X_SEGMENTS"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 template <class K, typename T>
 inline int launch_x(XArgs& a, cudaStream_t st) {
     typename K::Params p;
@@ -149,6 +155,16 @@ inline int launch_x(XArgs& a, cudaStream_t st) {
     p.offset[1] = (const T*)a.offset[1];
     p.ntot = a.ntot;
     if (a.bins) p.bins = *a.bins;
+    if constexpr (K::kMode == MODE_BIN) {
+        // bins as index ranges from the spec's pencil segment table, when it carries one this kernel can use
+        const bool is_signed = a.bins && a.bins->nmu > 0 && !a.bins->absolute_mus;
+        if (K::kSegOk && a.bins && a.bins->seg_tab && a.bins->seg_ntab == (is_signed ? 4 : 1) && x_use_segments()) {
+            p.seg = a.bins->seg_tab;
+            p.seg_stride = a.bins->seg_stride;
+            p.seg_ntab = a.bins->seg_ntab;
+            p.seg_pencils = (long long)a.bins->n[1] * a.nzh;
+        }
+    }
     p.nd_out = a.nd_out; p.nd_f64 = a.nd_f64; p.nd_half = a.nd_half; p.scale = a.scale;
 
     const bool is_bin = a.bins != nullptr;

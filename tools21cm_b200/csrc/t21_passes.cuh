@@ -432,7 +432,15 @@ struct XPass {
         int nd_half;          // MODE_ND: > 0 = store only the computed half spectrum, unshifted, rows of nd_half elements
                               // (a multiple of 8 keeps every 32-byte run of a tile inside one DRAM sector)
         double scale;         // MODE_ND
+        // MODE_BIN with a pencil segment table (t21_build_pencil_segments): bins are index ranges along the pencil
+        const unsigned* seg;  // null: classify per mode (warp-uniform bin cache)
+        int seg_stride, seg_ntab;
+        long long seg_pencils;
     };
+    // pencil-major, padded power tile of the table-driven epilogue: pencil zl at zl * PP (PP = 4 mod 32: the stores
+    // of a warp -- 8 pencils x 4 consecutive kx -- fall on 32 different banks, a warp reading one pencil is contiguous)
+    static constexpr int PP = NX + 4;
+    static constexpr bool kSegOk = (S::NS > 1) && (THREADS % 32 == 0) && (NX % 2 == 0);
     struct Regs {
         cx<T> v[NF][E];
         Acc acc[NACC];        // [0] stored modes, [1] Hermitian twins when they bin separately (signed mu)
@@ -516,13 +524,16 @@ struct XPass {
                                 // the tile keeps 0 for this sample (so it is counted like any other mode);
                                 // its power goes to the histogram here, once, with count 0
                                 pw = (T)0;
-                                const ModeBins mb = classify(p.bins, 0, 0, 0, false);
-                                if (mb.own >= 0) hist.add(mb.own, dc, 0u);
+                                int b0;
+                                if (kSegOk && p.seg) b0 = (int)(ldg(p.seg) & 0xFFFFu) - 1;     // range 0 of pencil (0, 0)
+                                else b0 = classify(p.bins, 0, 0, 0, false).own;
+                                if (b0 >= 0) hist.add(b0, dc, 0u);
                             } else {
                                 *dc_slot(smem) = dc;
                             }
                         }
-                        ptile(smem)[i * WZ + zl] = pw;
+                        if (MODE == MODE_BIN && kSegOk && p.seg) ptile(smem)[zl * PP + i] = pw;
+                        else ptile(smem)[i * WZ + zl] = pw;
                     }
                 };
             S::template fft_phase<FPH>(r.v[F], j, zl, p.tw, smem, [&](int) { return cmake<T>((T)0, (T)0); }, fin, true);
@@ -557,9 +568,70 @@ struct XPass {
         }
     }
 
+#if T21_DEVICE_CODE
+    // Table-driven epilogue: warp teams walk the pencils of the (pencil-major) power tile range by range.  A team of
+    // TW warps shares a pencil (lanes and team warps interleave over |kx|), each warp books its partial sum of a range,
+    // the first one also the range's closed-form mode count.  LO / HI: the kx >= 0 / kx < 0 half (signed mu walks them
+    // separately, with the own and the twin tables).
+    template <bool LO, bool HI, class Hist>
+    static __device__ __forceinline__ void walk_tile_pencil(const T* __restrict__ pp, unsigned ent, int lane, int sub, int tw,
+                                                            unsigned wt, Hist& hist) {
+        const unsigned pos = ent >> 16, binp1 = ent & 0xFFFFu;
+        const unsigned S = (unsigned)__popc(__ballot_sync(0xffffffffu, pos != 0xFFFFu));
+        constexpr unsigned H = NX / 2;
+        for (unsigned j = 0; j < S; ++j) {                          // warp-uniform
+            const int bin = (int)__shfl_sync(0xffffffffu, binp1, j) - 1;
+            const unsigned a = __shfl_sync(0xffffffffu, pos, j);
+            const unsigned b = j + 1u < S ? __shfl_sync(0xffffffffu, pos, (j + 1u) & 31u) : H + 1u;
+            if (bin < 0) continue;
+            T sum = (T)0;
+            for (unsigned f = a + (unsigned)lane + 32u * (unsigned)sub; f < b; f += 32u * (unsigned)tw) {
+                if (LO && f < H) sum += pp[f];
+                if (HI && f >= 1u) sum += pp[NX - f];
+            }
+            double t = (double)sum;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0) hist.add(bin, t * (double)wt, sub == 0 ? segment_modes(LO, HI, a, b, H) * wt : 0u);
+        }
+    }
+
+    template <class Hist>
+    static __device__ __forceinline__ void epilogue_bin_segments(const Params& p, int tid, int iy, int iz0, cx<T>* smem, Hist& hist) {
+        constexpr int NWARP = THREADS / 32;
+        constexpr int TW = NWARP > WZ ? NWARP / WZ : 1;            // warps per pencil
+        const int lane = tid & 31, w = tid >> 5;
+        const int sub = w / WZ;                                     // (TW == 1: w < WZ or the loop below strides)
+        for (int pz = NWARP > WZ ? w % WZ : w; pz < WZ; pz += (NWARP > WZ ? WZ : NWARP)) {
+            const int iz = iz0 + pz;
+            if (iz >= p.nzh) continue;
+            const bool has_twin = (iz != 0) && (iz != p.nz - iz);
+            const T* pp = ptile(smem) + pz * PP;
+            const unsigned* e0 = p.seg + ((size_t)iy * p.nzh + iz) * p.seg_stride + lane;
+            const size_t tstep = (size_t)p.seg_pencils * p.seg_stride;
+            const bool on = lane < p.seg_stride;
+            if (MU != 2) {
+                walk_tile_pencil<true, true>(pp, on ? ldg(e0) : kSegSentinel, lane, NWARP > WZ ? sub : 0, TW, has_twin ? 2u : 1u, hist);
+            } else {
+                walk_tile_pencil<true, false>(pp, on ? ldg(e0) : kSegSentinel, lane, NWARP > WZ ? sub : 0, TW, 1u, hist);
+                walk_tile_pencil<false, true>(pp, on ? ldg(e0 + tstep) : kSegSentinel, lane, NWARP > WZ ? sub : 0, TW, 1u, hist);
+                if (has_twin) {
+                    walk_tile_pencil<true, false>(pp, on ? ldg(e0 + 2 * tstep) : kSegSentinel, lane, NWARP > WZ ? sub : 0, TW, 1u, hist);
+                    walk_tile_pencil<false, true>(pp, on ? ldg(e0 + 3 * tstep) : kSegSentinel, lane, NWARP > WZ ? sub : 0, TW, 1u, hist);
+                }
+            }
+        }
+    }
+#endif
+
     template <class Hist>
     static T21_HD void epilogue_bin(const Params& p, int tid, int iy, int iz, int zl, bool active, Regs& r,
                                     cx<T>* smem, Hist& hist) {
+#if T21_DEVICE_CODE
+        if constexpr (kSegOk) {
+            if (p.seg) { epilogue_bin_segments(p, tid, iy, iz - zl, smem, hist); return; }
+        }
+#endif
         const t21_binspec& B = p.bins;
         const int q = tid / WZ;                                   // row id of this thread, 0..TP-1
         const int ix0 = (q / RPI) * (E * RPI) + (q % RPI);

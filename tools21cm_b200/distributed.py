@@ -156,8 +156,7 @@ class CudaBackend:
         code = _lib.T21_F32 if w.dtype == torch.complex64 else _lib.T21_F64
         nx, nyl = cols[0].nx, cols[0].nyl
         plan = dev.plan((nx, nyl, nz), code)
-        spec, cspec, _own = dev.spec(((nx, ny_global, nz), spec_key), spec_builder,
-                                     segments=(code == _lib.T21_F32 and len(cols) == 1))
+        spec, cspec, _own = dev.spec(((nx, ny_global, nz), spec_key), spec_builder, segments=True)
         nb = spec.nbins
         need = lib.t21_workspace_bytes(plan, 0, nb)
         ws = dev.workspace(need)

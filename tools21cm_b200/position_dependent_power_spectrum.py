@@ -68,8 +68,7 @@ def _window_spectra(x, windows, kbins, box_dims, binning):
         code = _ps._dtype_code(x)
         plan = dev.plan(shape, code)
         key = ("1d", _ps._freeze(list(box)), _ps._freeze(kbins), binning, 0.1)
-        spec, cspec, _owner = dev.spec((shape, key), lambda: _bs.build_binspec(shape, box, kbins, binning=binning),
-                                       segments=(code == _lib.T21_F32))
+        spec, cspec, _owner = dev.spec((shape, key), lambda: _bs.build_binspec(shape, box, kbins, binning=binning), segments=True)
         nb, nw = spec.nbins, len(windows)
         ws = dev.workspace(lib.t21_workspace_bytes(plan, 1, nb))
         sums = torch.empty((nw, nb), dtype=torch.float64, device=x.device)

@@ -140,14 +140,16 @@ class _Device:
         """The pencil segment table of the warp-per-pencil X pass (``t21_build_pencil_segments``): along an x pencil the
         bins are index ranges, found once per (shape, bin spec) on the device with the per-mode classification of the
         other kernels and kept with the cached spec -- plan data like the twiddle tables, 8-32 entries per pencil.
-        Only shapes that kernel takes (nx = 1024) get one (four for signed mu bins, which are not even in kx)."""
+        Power-of-two nx from 64 to 4096 (the Stockham X passes) and at most 128 bins get one; four for signed mu bins,
+        which are not even in kx."""
         spec, cspec, owners = hit
         if getattr(spec, "_segments_tried", False):
             return
         spec._segments_tried = True
         if os.environ.get("T21_X32_SEGMENTS", "1") == "0":
             return
-        if spec.shape[0] != 1024 or spec.nbins > 128 or int(spec.zero_idx[0]) != 0:
+        nx = int(spec.shape[0])
+        if nx < 64 or nx > 4096 or (nx & (nx - 1)) or spec.nbins > 128 or int(spec.zero_idx[0]) != 0 or len(spec.shape) != 3:
             return
         ntab = 4 if (spec.nmu and not spec.absolute_mus) else 1      # signed mu: own / twin bins for kx >= 0 and kx < 0
         lib = _lib.load()
@@ -300,8 +302,7 @@ def _fused_binned(fields, spec_key, spec_builder):
         lib = _lib.load()
         code = _dtype_code(x)
         plan = dev.plan(tuple(x.shape), code)
-        spec, cspec, _owner = dev.spec((tuple(x.shape), spec_key), spec_builder,
-                                       segments=(code == T21_F32 and len(fields) == 1))
+        spec, cspec, _owner = dev.spec((tuple(x.shape), spec_key), spec_builder, segments=True)
         nb = spec.nbins
         need = lib.t21_workspace_bytes(plan, len(fields), nb)
         ws = dev.workspace(need)

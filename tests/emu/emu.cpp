@@ -208,7 +208,7 @@ int emu_bin_only(const double* p, const t21_binspec* spec, double* sums, long lo
 
 // The epilogue of the warp-per-pencil X pass as plain loops: bins are index ranges along x pencils, taken from the
 // segment tables build_pencil_segments() makes (one table for shells / |mu| bins, four for signed mu).  phalf is the
-// power of the computed half spectrum, [nx][ny][nz/2+1], nx even.  Returns 1 if a pencil needs more than 32 ranges,
+// power of the computed half spectrum, [nx][ny][nz/2+1].  Returns 1 if a pencil needs more than 32 ranges,
 // 2 if the closed-form mode count of a range (segment_modes, what the kernel books) disagrees with counting them.
 int emu_bin_segments(const double* phalf, const t21_binspec* spec, double* sums, long long* counts) {
     const t21_binspec& B = *spec;
@@ -233,10 +233,10 @@ int emu_bin_segments(const double* phalf, const t21_binspec* spec, double* sums,
                     double sum = 0.0;
                     unsigned cnt = 0;
                     for (unsigned f = a; f < b; ++f) {
-                        if (lo && f < (unsigned)H) { sum += phalf[((size_t)f * ny + iy) * nzh + iz]; ++cnt; }
+                        if (lo && f < (unsigned)(nx % 2 == 0 ? H : H + 1)) { sum += phalf[((size_t)f * ny + iy) * nzh + iz]; ++cnt; }
                         if (hi && f >= 1) { sum += phalf[((size_t)(nx - f) * ny + iy) * nzh + iz]; ++cnt; }
                     }
-                    if (cnt != segment_modes(lo, hi, a, b, (unsigned)H)) return 2;
+                    if (cnt != segment_modes(lo, hi, a, b, (unsigned)H, nx % 2 == 0)) return 2;
                     sums[bin] += sum * wt;
                     counts[bin] += (long long)cnt * wt;
                 }

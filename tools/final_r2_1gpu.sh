@@ -30,3 +30,4 @@ print("roofline", d["roofline"]); print("e2e", d["e2e"]); print("cpu", d["cpu_ba
 print(open("gpurun_out/r02_bench_1gpu_reference_arm.json").read()[:600])
 print(open("gpurun_out/r02_variants_1gpu.json").read())
 PY
+bash tools/r2_np2.sh

@@ -140,18 +140,14 @@ T21_HD ModeBins classify(const t21_binspec& B, int ix, int iy, int iz, bool has_
 // short.  The mirror mode nx - f must agree (shells and |mu| bins are even in kx; signed mu is refused by the caller):
 // a pencil where it does not, or with more than `stride` ranges, reports stride + 1 and the table is not used.
 constexpr unsigned kSegSentinel = 0xFFFF0000u;
-// modes of an x pencil (even nx, H = nx / 2) with a <= |kx index| < b, 0 <= a < b <= H + 1, in the kx >= 0 half
-// (indices 0 .. H-1: LO), the kx < 0 half (|kx| = 1 .. H, the Nyquist sample counted there: HI), or both
-T21_HD unsigned segment_modes(bool lo, bool hi, unsigned a, unsigned b, unsigned H) {
-    if (lo && hi) return 2u * (b - a) - (a == 0u ? 1u : 0u) - (b == H + 1u ? 1u : 0u);
-    if (lo) return (b < H ? b : H) - (a < H ? a : H);
-    return b - (a > 1u ? a : 1u);
+// modes of an x pencil of nx samples (H = nx / 2) with a <= |kx index| < b, 0 <= a < b <= H + 1, in the kx >= 0 half
+// (LO), the kx < 0 half (HI), or both.  Even nx: the Nyquist sample |kx| = H is single and counted with the kx < 0 half.
+T21_HD unsigned segment_modes(bool lo, bool hi, unsigned a, unsigned b, unsigned H, bool even = true) {
+    const unsigned lo_end = even ? H : H + 1u;                      // kx >= 0 half: |kx| in [0, lo_end)
+    const unsigned nlo = (b < lo_end ? b : lo_end) - (a < lo_end ? a : lo_end);
+    const unsigned nhi = b - (a > 1u ? a : 1u);                      // kx < 0 half: |kx| in [1, H]
+    return (lo ? nlo : 0u) + (hi ? nhi : 0u);
 }
-// which: 0  bins even in kx (shells, |mu|): the stored mode's bin, checked against its mirror nx - f;
-//        1 / 2  signed mu, the stored mode's own bin for kx = +f / kx = -f;
-//        3 / 4  signed mu, the bin of its Hermitian twin (-1 where the twin is itself stored) for kx = +f / -f;
-//        5  shells for the multipole moments: as 0, minus the k_perp = 0 line of B.los_axis when B.exclude_zero is set
-//           (power_legendre.py:51, power_spectrum.py:563-575).
 // bin_of(ix) -> flat bin or -1, for ix = f (and ix = nx - f when `mirror_of` is asked to agree)
 template <class BinOf>
 T21_HD int emit_pencil_segments(int nx, bool check_mirror, bool negative_half, BinOf&& bin_of, unsigned* __restrict__ out, int stride) {
@@ -197,6 +193,36 @@ T21_HD int build_pencil_segments_cyl(int n0, int n1, int n2, int nu_axis, const 
         return (pe < 0 || pa < 0) ? -1 : pe * npar + pa;
     }, out, stride);
 }
+
+#ifdef __CUDACC__
+// One warp (or a team of `tw` warps, this one being number `sub`) walks the ranges of a pencil whose powers sit in shared
+// memory, pp[0 .. nx-1] in FFT order: lanes and team warps interleave over |kx|, every warp books its partial sum of a
+// range and warp 0 of the team the range's closed-form mode count.  LO / HI: the kx >= 0 / kx < 0 half.
+template <typename T, bool LO, bool HI, class Hist>
+__device__ __forceinline__ void walk_pencil_ranges(const T* __restrict__ pp, unsigned nx, unsigned ent, int lane, int sub, int tw,
+                                                   unsigned wt, Hist& hist) {
+    const unsigned pos = ent >> 16, binp1 = ent & 0xFFFFu;
+    const unsigned S = (unsigned)__popc(__ballot_sync(0xffffffffu, pos != 0xFFFFu));
+    const unsigned H = nx / 2u;
+    const bool even = (nx & 1u) == 0u;
+    const unsigned lo_end = even ? H : H + 1u;
+    for (unsigned j = 0; j < S; ++j) {                              // warp-uniform
+        const int bin = (int)__shfl_sync(0xffffffffu, binp1, j) - 1;
+        const unsigned a = __shfl_sync(0xffffffffu, pos, j);
+        const unsigned b = j + 1u < S ? __shfl_sync(0xffffffffu, pos, (j + 1u) & 31u) : H + 1u;
+        if (bin < 0) continue;
+        T sum = (T)0;
+        for (unsigned f = a + (unsigned)lane + 32u * (unsigned)sub; f < b; f += 32u * (unsigned)tw) {
+            if (LO && f < lo_end) sum += pp[f];
+            if (HI && f >= 1u) sum += pp[nx - f];
+        }
+        double t = (double)sum;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) hist.add(bin, t * (double)wt, sub == 0 ? segment_modes(LO, HI, a, b, H, even) * wt : 0u);
+    }
+}
+#endif
 
 // ---- accumulators ---------------------------------------------------------------------
 // RunAcc: per-thread run-length accumulator.  Used where one thread walks modes whose bin

@@ -282,6 +282,56 @@ gen_xpass_kernel(const cx<T>* __restrict__ w0, const cx<T>* __restrict__ w1, int
             res0 = r0;
             if (NF == 2) res1 = mixed_fft<T>(tile1, r0 == tile0 ? scratch : tile0, nx, WZ, f, roots);
         }
+        if (HK != 2 && f.nf > 0 && B.seg_tab != nullptr) {
+            // Bins as index ranges (pencil segment table): powers go pencil-major into the buffer the transforms left
+            // free, then every warp walks pencils range by range -- no per-mode classification, no per-mode atomics.
+            cx<T>* freeb = (res0 != tile0 && (NF == 1 || res1 != tile0)) ? tile0
+                         : ((NF == 2 && res0 != tile1 && res1 != tile1) ? tile1 : scratch);
+            T* pw = reinterpret_cast<T*>(freeb);
+            const int PPg = nx + 4;
+            for (int e = threadIdx.x; e < nx * WZ; e += kGenThreads) {
+                const int ix = e / WZ, zl = e % WZ, iz = chunk * WZ + zl;
+                if (iz >= nzh) continue;
+                const T ar = res0[e].x, ai = res0[e].y;
+                const T br = NF == 2 ? res1[e].x : ar, bi = NF == 2 ? res1[e].y : ai;
+                T pv = ar * br + ai * bi;
+                if ((ix | iy | iz) == 0) {
+                    const double c0 = off0 ? (double)ldg(off0) : 0.0;
+                    const double c1 = (NF == 2 && off1) ? (double)ldg(off1) : c0;
+                    const double dc = ((double)ar + c0 * ntot) * ((double)br + c1 * ntot) + (double)ai * (double)bi;
+                    const int b0 = (int)(ldg(B.seg_tab) & 0xFFFFu) - 1;        // range 0 of pencil (0, 0)
+                    if (b0 >= 0) { if (HK == 0) sh.add(b0, dc, 0u); else gh.add(b0, dc, 0u); }
+                    pv = (T)0;                                                 // counted with its range, power added above
+                }
+                pw[zl * PPg + ix] = pv;
+            }
+            __syncthreads();
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            const size_t tstep = (size_t)ny * nzh * B.seg_stride;
+            for (int pz = warp; pz < WZ; pz += kGenThreads / 32) {
+                const int iz = chunk * WZ + pz;
+                if (iz >= nzh) continue;
+                const bool has_twin = (iz != 0) && (iz != nz - iz);
+                const unsigned* e0 = B.seg_tab + ((size_t)iy * nzh + iz) * B.seg_stride + lane;
+                const bool on = lane < B.seg_stride;
+                const T* pp = pw + pz * PPg;
+#define T21_GEN_WALK(LO, HI, ENT, WT)                                                                              \
+                { if (HK == 0) walk_pencil_ranges<T, LO, HI>(pp, (unsigned)nx, ENT, lane, 0, 1, WT, sh);           \
+                  else walk_pencil_ranges<T, LO, HI>(pp, (unsigned)nx, ENT, lane, 0, 1, WT, gh); }
+                if (!signed_mu) {
+                    T21_GEN_WALK(true, true, on ? ldg(e0) : kSegSentinel, has_twin ? 2u : 1u)
+                } else {
+                    T21_GEN_WALK(true, false, on ? ldg(e0) : kSegSentinel, 1u)
+                    T21_GEN_WALK(false, true, on ? ldg(e0 + tstep) : kSegSentinel, 1u)
+                    if (has_twin) {
+                        T21_GEN_WALK(true, false, on ? ldg(e0 + 2 * tstep) : kSegSentinel, 1u)
+                        T21_GEN_WALK(false, true, on ? ldg(e0 + 3 * tstep) : kSegSentinel, 1u)
+                    }
+                }
+#undef T21_GEN_WALK
+            }
+            continue;
+        }
         for (int e = threadIdx.x; e < nx * WZ; e += kGenThreads) {
             const int ix = e / WZ, zl = e % WZ, iz = chunk * WZ + zl;
             if (iz >= nzh) continue;
@@ -429,7 +479,11 @@ static int gen_x(XArgs& a, cudaStream_t st) {
     if (g < 1) g = 1;
     t21_binspec dummy;
     memset(&dummy, 0, sizeof(dummy));
-    const t21_binspec& B = is_bin ? *a.bins : dummy;
+    t21_binspec B = is_bin ? *a.bins : dummy;
+    {   // the segment table is used only when it matches the mode (four tables for signed mu, one otherwise)
+        const bool is_signed = B.nmu > 0 && !B.absolute_mus;
+        if (!x_use_segments() || B.seg_ntab != (is_signed ? 4 : 1)) B.seg_tab = nullptr;
+    }
 #define T21_GEN_X(HKV)                                                                                          \
     {                                                                                                           \
         auto kern = gen_xpass_kernel<T, NF, HKV>;                                                               \

@@ -576,24 +576,7 @@ struct XPass {
     template <bool LO, bool HI, class Hist>
     static __device__ __forceinline__ void walk_tile_pencil(const T* __restrict__ pp, unsigned ent, int lane, int sub, int tw,
                                                             unsigned wt, Hist& hist) {
-        const unsigned pos = ent >> 16, binp1 = ent & 0xFFFFu;
-        const unsigned S = (unsigned)__popc(__ballot_sync(0xffffffffu, pos != 0xFFFFu));
-        constexpr unsigned H = NX / 2;
-        for (unsigned j = 0; j < S; ++j) {                          // warp-uniform
-            const int bin = (int)__shfl_sync(0xffffffffu, binp1, j) - 1;
-            const unsigned a = __shfl_sync(0xffffffffu, pos, j);
-            const unsigned b = j + 1u < S ? __shfl_sync(0xffffffffu, pos, (j + 1u) & 31u) : H + 1u;
-            if (bin < 0) continue;
-            T sum = (T)0;
-            for (unsigned f = a + (unsigned)lane + 32u * (unsigned)sub; f < b; f += 32u * (unsigned)tw) {
-                if (LO && f < H) sum += pp[f];
-                if (HI && f >= 1u) sum += pp[NX - f];
-            }
-            double t = (double)sum;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            if (lane == 0) hist.add(bin, t * (double)wt, sub == 0 ? segment_modes(LO, HI, a, b, H) * wt : 0u);
-        }
+        walk_pencil_ranges<T, LO, HI>(pp, (unsigned)NX, ent, lane, sub, tw, wt, hist);
     }
 
     template <class Hist>

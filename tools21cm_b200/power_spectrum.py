@@ -140,8 +140,8 @@ class _Device:
         """The pencil segment table of the warp-per-pencil X pass (``t21_build_pencil_segments``): along an x pencil the
         bins are index ranges, found once per (shape, bin spec) on the device with the per-mode classification of the
         other kernels and kept with the cached spec -- plan data like the twiddle tables, 8-32 entries per pencil.
-        Power-of-two nx from 64 to 4096 (the Stockham X passes) and at most 128 bins get one; four for signed mu bins,
-        which are not even in kx."""
+        nx from 32 to 4096 and at most 128 bins get one (every X pass reads it: warp-per-pencil, CTA-per-tile, mixed
+        radix); four for signed mu bins, which are not even in kx."""
         spec, cspec, owners = hit
         if getattr(spec, "_segments_tried", False):
             return
@@ -149,7 +149,7 @@ class _Device:
         if os.environ.get("T21_X32_SEGMENTS", "1") == "0":
             return
         nx = int(spec.shape[0])
-        if nx < 64 or nx > 4096 or (nx & (nx - 1)) or spec.nbins > 128 or int(spec.zero_idx[0]) != 0 or len(spec.shape) != 3:
+        if nx < 32 or nx > 4096 or spec.nbins > 128 or int(spec.zero_idx[0]) != 0 or len(spec.shape) != 3:
             return
         ntab = 4 if (spec.nmu and not spec.absolute_mus) else 1      # signed mu: own / twin bins for kx >= 0 and kx < 0
         lib = _lib.load()

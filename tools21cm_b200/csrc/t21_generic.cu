@@ -49,6 +49,26 @@ __device__ __forceinline__ void small_dft(cx<T>* v, const cx<T>* __restrict__ ro
         const cx<T> a = cadd(v[0], v[2]), b = csub(v[0], v[2]), c = cadd(v[1], v[3]), d = csub(v[1], v[3]);
         const cx<T> dmi = cmake<T>(d.y, -d.x);                 // -i d
         v[0] = cadd(a, c); v[2] = csub(a, c); v[1] = cadd(b, dmi); v[3] = csub(b, dmi);
+    } else if constexpr (R == 3) {
+        // X1 = v0 - (v1 + v2)/2 - i s (v1 - v2), X2 = conj-symmetric partner, s = sin(pi/3)
+        const T s3 = (T)0.86602540378443864676;
+        const cx<T> t1 = cadd(v[1], v[2]), d = csub(v[1], v[2]);
+        const cx<T> t2 = cmake<T>(v[0].x - (T)0.5 * t1.x, v[0].y - (T)0.5 * t1.y);
+        const cx<T> q = cmake<T>(s3 * d.y, -s3 * d.x);                 // -i s d
+        v[0] = cadd(v[0], t1); v[1] = cadd(t2, q); v[2] = csub(t2, q);
+    } else if constexpr (R == 5) {
+        const T c1 = (T)0.30901699437494742410, c2 = (T)-0.80901699437494742410;      // cos(2 pi/5), cos(4 pi/5)
+        const T s1 = (T)0.95105651629515357212, s2 = (T)0.58778525229247312917;       // sin(2 pi/5), sin(4 pi/5)
+        const cx<T> a1 = cadd(v[1], v[4]), a2 = cadd(v[2], v[3]), b1 = csub(v[1], v[4]), b2 = csub(v[2], v[3]);
+        const cx<T> r1 = cmake<T>(v[0].x + c1 * a1.x + c2 * a2.x, v[0].y + c1 * a1.y + c2 * a2.y);
+        const cx<T> r2 = cmake<T>(v[0].x + c2 * a1.x + c1 * a2.x, v[0].y + c2 * a1.y + c1 * a2.y);
+        const cx<T> q1 = cmake<T>(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
+        const cx<T> q2 = cmake<T>(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
+        v[0] = cmake<T>(v[0].x + a1.x + a2.x, v[0].y + a1.y + a2.y);
+        v[1] = cmake<T>(r1.x + q1.y, r1.y - q1.x);                     // r1 - i q1
+        v[4] = cmake<T>(r1.x - q1.y, r1.y + q1.x);                     // r1 + i q1
+        v[2] = cmake<T>(r2.x + q2.y, r2.y - q2.x);
+        v[3] = cmake<T>(r2.x - q2.y, r2.y + q2.x);
     } else {
         cx<T> in[R];
 #pragma unroll
@@ -69,49 +89,49 @@ __device__ __forceinline__ void small_dft(cx<T>* v, const cx<T>* __restrict__ ro
     }
 }
 
-template <int R, typename T>
-__device__ __forceinline__ void mixed_stage(const cx<T>* __restrict__ a, cx<T>* __restrict__ b, int n, int ncol, int ns,
+template <int R, int NCOL, typename T>
+__device__ __forceinline__ void mixed_stage(const cx<T>* __restrict__ a, cx<T>* __restrict__ b, int n, int ns,
                                             const cx<T>* __restrict__ roots, int tid, int nthreads) {
-    const int nb = n / R;                       // butterflies per pencil
-    const int tstep = n / (ns * R);             // root index of w_(ns R)^1
-    for (int w = tid; w < nb * ncol; w += nthreads) {
-        const int jj = w / ncol, col = w - jj * ncol;
-        const int m = jj % ns;
+    const unsigned nb = (unsigned)n / R;                   // butterflies per pencil
+    const unsigned tstep = (unsigned)n / ((unsigned)ns * R);   // root index of w_(ns R)^1
+    for (unsigned w = tid; w < nb * NCOL; w += nthreads) {
+        const unsigned jj = w / NCOL, col = w % NCOL;      // NCOL is a power of two
+        const unsigned m = jj % (unsigned)ns;
         cx<T> v[R];
-        int idx = 0;
+        unsigned idx = 0;
 #pragma unroll
         for (int k = 0; k < R; ++k) {
-            cx<T> x = a[(jj + k * nb) * ncol + col];
+            cx<T> x = a[(jj + k * nb) * NCOL + col];
             if (k > 0 && m > 0) {
                 idx += m * tstep;               // k m n / (ns R) < n: a single conditional subtraction keeps it in range
-                if (idx >= n) idx -= n;
+                if (idx >= (unsigned)n) idx -= (unsigned)n;
                 x = cmul(x, ldg(roots + idx));
             }
             v[k] = x;
         }
         small_dft<R, T>(v, roots, n);
-        const int base = (jj - m) * R + m;
+        const unsigned base = (jj - m) * R + m;
 #pragma unroll
-        for (int k = 0; k < R; ++k) b[(base + k * ns) * ncol + col] = v[k];
+        for (int k = 0; k < R; ++k) b[(base + k * ns) * NCOL + col] = v[k];
     }
 }
 
-// transforms the ncol pencils of tile a[n][ncol] (forward, exp(-i ...)); b is scratch of the same size.  All threads of
+// transforms the NCOL pencils of tile a[n][NCOL] (forward, exp(-i ...)); b is scratch of the same size.  All threads of
 // the CTA take part (CTA barriers inside).  Returns the buffer that holds the result (a or b), natural order.
-template <typename T>
-__device__ __forceinline__ cx<T>* mixed_fft(cx<T>* a, cx<T>* b, int n, int ncol, const Factors& f, const cx<T>* __restrict__ roots) {
+template <int NCOL, typename T>
+__device__ __forceinline__ cx<T>* mixed_fft(cx<T>* a, cx<T>* b, int n, const Factors& f, const cx<T>* __restrict__ roots) {
     int ns = 1;
     for (int s = 0; s < f.nf; ++s) {
         const int R = f.radix[s];
         const int tid = threadIdx.x, nt = blockDim.x;
         switch (R) {
-            case 2: mixed_stage<2, T>(a, b, n, ncol, ns, roots, tid, nt); break;
-            case 3: mixed_stage<3, T>(a, b, n, ncol, ns, roots, tid, nt); break;
-            case 4: mixed_stage<4, T>(a, b, n, ncol, ns, roots, tid, nt); break;
-            case 5: mixed_stage<5, T>(a, b, n, ncol, ns, roots, tid, nt); break;
-            case 7: mixed_stage<7, T>(a, b, n, ncol, ns, roots, tid, nt); break;
-            case 11: mixed_stage<11, T>(a, b, n, ncol, ns, roots, tid, nt); break;
-            default: mixed_stage<13, T>(a, b, n, ncol, ns, roots, tid, nt); break;
+            case 2: mixed_stage<2, NCOL, T>(a, b, n, ns, roots, tid, nt); break;
+            case 3: mixed_stage<3, NCOL, T>(a, b, n, ns, roots, tid, nt); break;
+            case 4: mixed_stage<4, NCOL, T>(a, b, n, ns, roots, tid, nt); break;
+            case 5: mixed_stage<5, NCOL, T>(a, b, n, ns, roots, tid, nt); break;
+            case 7: mixed_stage<7, NCOL, T>(a, b, n, ns, roots, tid, nt); break;
+            case 11: mixed_stage<11, NCOL, T>(a, b, n, ns, roots, tid, nt); break;
+            default: mixed_stage<13, NCOL, T>(a, b, n, ns, roots, tid, nt); break;
         }
         __syncthreads();
         cx<T>* t = a; a = b; b = t;
@@ -153,9 +173,10 @@ gen_zpass_kernel(const T* __restrict__ in, cx<T>* __restrict__ out, long long nr
     }
 }
 
-// smooth nz: RZ rows at a time as the columns of a [nz][RZ] complex tile (imaginary parts zero), mixed-radix FFT, the
-// first nz/2+1 outputs of every row stored.  (The half-length packing trick of ZPass would halve the work; the real
-// rows of a 250^3 cube are 1 % of a millisecond either way.)
+// smooth nz: 2 * RZ real rows at a time, packed in pairs as the real and imaginary parts of the RZ columns of a
+// [nz][RZ] complex tile: one mixed-radix FFT transforms both rows of a pair, Z[k] = X1[k] + i X2[k], and they come apart
+// as X1[k] = (Z[k] + conj Z[nz-k]) / 2, X2[k] = (Z[k] - conj Z[nz-k]) / 2i.  The load writes shared memory
+// contiguously (element e of the tile, as floats, is sample z = e / (2 RZ) of row e % (2 RZ)).
 constexpr int kGenRZ = 8;
 template <typename T>
 __global__ void __launch_bounds__(kGenThreads)
@@ -166,24 +187,36 @@ gen_zpass_fft_kernel(const T* __restrict__ in, cx<T>* __restrict__ out, long lon
     cx<T>* tb = ta + (size_t)nz * kGenRZ;
     const T off = offset ? ldg(offset) : (T)0;
     constexpr int LW = WLay<T>::LW;
+    constexpr int NR = 2 * kGenRZ;                                        // real rows per tile
     const long long cstride = nxa * ny * LW;
-    const long long ngroups = (nrows + kGenRZ - 1) / kGenRZ;
+    const long long ngroups = (nrows + NR - 1) / NR;
     for (long long g = blockIdx.x; g < ngroups; g += gridDim.x) {
-        const long long r0 = g * kGenRZ;
+        const long long r0 = g * NR;
         __syncthreads();
-        for (int e = threadIdx.x; e < nz * kGenRZ; e += kGenThreads) {
-            const int rr = e / nz, z = e - rr * nz;                   // consecutive threads read consecutive z of one row
+        T* taf = reinterpret_cast<T*>(ta);
+        // a warp takes 4 consecutive z of 8 rows: 16-byte runs of global memory (the rest of each sector is an L1 hit on
+        // the next trip), a 2-way bank conflict on the store instead of the 16-way one of a z-major deal
+        for (int e = threadIdx.x; e < ((nz + 3) / 4) * 4 * NR; e += kGenThreads) {
+            const int rr = (e & 7) | (((e >> 5) & 1) << 3), z = ((e >> 6) << 2) | ((e >> 3) & 3);
             const long long r = r0 + rr;
-            ta[z * kGenRZ + rr] = cmake<T>(r < nrows ? in[r * nz + z] - off : (T)0, (T)0);
+            if (z < nz) taf[z * NR + rr] = r < nrows ? in[r * nz + z] - off : (T)0;
         }
         __syncthreads();
-        const cx<T>* res = mixed_fft<T>(ta, tb, nz, kGenRZ, f, roots);
-        for (int e = threadIdx.x; e < nzh * kGenRZ; e += kGenThreads) {
-            const int k = e / kGenRZ, rr = e - k * kGenRZ;
-            const long long r = r0 + rr;
-            if (r >= nrows) continue;
-            const long long x = r / ny, y = r - x * ny;
-            out[(long long)(k / LW) * cstride + (x * ny + y) * LW + (k % LW)] = res[k * kGenRZ + rr];
+        const cx<T>* res = mixed_fft<kGenRZ, T>(ta, tb, nz, f, roots);
+        // lanes along the LW columns of a 64-byte piece, then along the row pairs: a store instruction writes whole pieces
+        const int nkc = (nzh + LW - 1) / LW;
+        for (int e = threadIdx.x; e < nkc * kGenRZ * LW; e += kGenThreads) {
+            const int kl = e % LW, c = (e / LW) % kGenRZ, kc = e / (LW * kGenRZ);
+            const int k = kc * LW + kl;
+            if (k >= nzh) continue;
+            const cx<T> zk = res[k * kGenRZ + c], zm = res[(k ? nz - k : 0) * kGenRZ + c];
+            const cx<T> x1 = cmake<T>((T)0.5 * (zk.x + zm.x), (T)0.5 * (zk.y - zm.y));
+            const cx<T> x2 = cmake<T>((T)0.5 * (zk.y + zm.y), (T)0.5 * (zm.x - zk.x));
+            const long long ra = r0 + 2 * c;
+            const long long kofs = (long long)kc * cstride + kl;
+            // (row (x, y) sits at x * ny + y = its row number)
+            if (ra < nrows) out[kofs + ra * LW] = x1;
+            if (ra + 1 < nrows) out[kofs + (ra + 1) * LW] = x2;
         }
     }
 }
@@ -212,7 +245,7 @@ gen_ypass_kernel(cx<T>* __restrict__ w, long long nouter, int ny, int nzh, int p
         }
         __syncthreads();
         if (f.nf > 0) {
-            const cx<T>* res = mixed_fft<T>(tile, tile + (size_t)ny * WZ, ny, WZ, f, roots);
+            const cx<T>* res = mixed_fft<WZ, T>(tile, tile + (size_t)ny * WZ, ny, f, roots);
             for (int e = threadIdx.x; e < ny * WZ; e += kGenThreads) {
                 const int zl = e % WZ;
                 if (chunk * WZ + zl < nzh) base[(e / WZ) * stride + zl] = res[e];
@@ -278,9 +311,9 @@ gen_xpass_kernel(const cx<T>* __restrict__ w0, const cx<T>* __restrict__ w1, int
         const cx<T>* res1 = tile1;
         if (f.nf > 0) {
             // the transformed field ends in its own tile or in the scratch buffer; whichever is free serves the next field
-            cx<T>* r0 = mixed_fft<T>(tile0, scratch, nx, WZ, f, roots);
+            cx<T>* r0 = mixed_fft<WZ, T>(tile0, scratch, nx, f, roots);
             res0 = r0;
-            if (NF == 2) res1 = mixed_fft<T>(tile1, r0 == tile0 ? scratch : tile0, nx, WZ, f, roots);
+            if (NF == 2) res1 = mixed_fft<WZ, T>(tile1, r0 == tile0 ? scratch : tile0, nx, f, roots);
         }
         if (HK != 2 && f.nf > 0 && B.seg_tab != nullptr) {
             // Bins as index ranges (pencil segment table): powers go pencil-major into the buffer the transforms left
@@ -415,7 +448,7 @@ static int gen_z(const ZArgs& a, cudaStream_t st) {
     if (f.nf > 0 && smem_fft <= 200 * 1024 && !a.window) {
         auto kern = gen_zpass_fft_kernel<T>;
         if (int rc = ensure_smem(kern, smem_fft)) return rc;
-        const long long ngroups = (a.nrows + kGenRZ - 1) / kGenRZ;
+        const long long ngroups = (a.nrows + 2 * kGenRZ - 1) / (2 * kGenRZ);
         long long g = ngroups < (long long)device_sm_count() * 8 ? ngroups : (long long)device_sm_count() * 8;
         if (g < 1) return 0;
         kern<<<(unsigned)g, kGenThreads, smem_fft, st>>>((const T*)a.in, (cx<T>*)a.out, a.nrows, a.nz, nzh, a.ny, a.nxa,

@@ -89,6 +89,8 @@ typedef struct t21_binspec {
     const uint32_t* seg_tab;
     int32_t seg_stride;   /* entries per pencil: 8, 16 or 32 */
     int32_t seg_ntab;     /* 1 (shells, |mu|) or 4 (signed mu: own bin for kx >= 0, own for kx < 0, twin's bin for each) */
+    int32_t seg_overflow; /* pencils marked 0xFFFE0000 in entry 0 (more ranges than seg_stride): only the warp-per-pencil
+                           * X pass takes such a table, and classifies those pencils mode by mode */
 } t21_binspec;
 
 /* Bins are index ranges along an x pencil: for fixed (ky, kz), k only grows with |kx| and so does |mu| when the line of
@@ -98,8 +100,9 @@ typedef struct t21_binspec {
  * look-up cannot decide) -- so that the X pass adds whole ranges instead of classifying 10^9 modes per cube.
  * `spec` must be in FFT index order.  out: T * ny * (nz/2+1) * stride uint32 (device), T = 1 table for shells and |mu|
  * bins (even in kx), T = 4 consecutive tables for signed mu (the stored mode's own bin for kx = +f and for kx = -f, then
- * the bin of its Hermitian twin for each; seg_ntab).  max_segments_dev (device int): largest number of ranges any pencil needs; a value above `stride` means
- * the table is unusable (rebuild with a larger stride, 32 at most; above 32 the X pass classifies per mode). */
+ * the bin of its Hermitian twin for each; seg_ntab).  max_segments_dev (two device ints): [0] the largest number of ranges
+ * any pencil needs, stride + 1 if some pencil needs more than `stride`; [1] how many pencils do -- entry 0 of those is the
+ * overflow mark 0xFFFE0000 (put the count in seg_overflow). */
 T21_API int t21_build_pencil_segments(const t21_binspec* spec, uint32_t* out, int stride, int* max_segments_dev, void* stream);
 
 /* The same table for the (k_perp, k_par) bins of power_spectrum_2d (power_spectrum.py:177-254), from the separable tables of

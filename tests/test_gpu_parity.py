@@ -185,6 +185,27 @@ def test_multipoles_against_oracle(t2c, shape, los):
 
 
 @pytest.mark.parametrize("shape", [(1024, 16, 32), (1024, 32, 16)])
+def test_warp_per_pencil_x_pass_overflow_pencils(t2c, shape, monkeypatch):
+    """Fine binnings (the reference's default is kbins = 100): pencils next to the kx axis cross more than 32 ranges, are
+    marked in the segment table and classified mode by mode by the same kernel.  In these thin slabs most pencils are
+    such pencils, so the share a table may carry is lifted for the test."""
+    from oracle import ps_oracle
+    monkeypatch.setenv("T21_SEG_MAX_OVERFLOW", "1.0")
+    x = (np.random.default_rng(5).standard_normal(shape) + 2.0).astype(np.float32)
+    box = [300.0, 40.0, 60.0]
+    ps, ks, nm = t2c.power_spectrum_1d(x, kbins=100, box_dims=box, return_n_modes=True)
+    ps_o, ks_o, nm_o = ps_oracle.power_spectrum_1d(x, kbins=100, box_dims=box, return_n_modes=True)
+    assert np.array_equal(nm, nm_o) and np.array_equal(ks, ks_o)
+    np.testing.assert_allclose(ps, ps_o, rtol=1e-5, equal_nan=True)
+    for absmu in (True, False):
+        kw = dict(los_axis=0, mubins=3, kbins=40, box_dims=box, return_n_modes=True, absolute_mus=absmu)
+        pm, _, _, nmu = t2c.power_spectrum_mu(x, **kw)
+        pm_o, _, _, nmu_o = ps_oracle.power_spectrum_mu(x, **kw)
+        assert np.array_equal(nmu, nmu_o)
+        np.testing.assert_allclose(pm, pm_o, rtol=1e-5, equal_nan=True)
+
+
+@pytest.mark.parametrize("shape", [(1024, 16, 32), (1024, 32, 16)])
 @pytest.mark.parametrize("los", [0, 1, 2])
 def test_fused_multipoles_on_the_warp_per_pencil_pass(t2c, shape, los):
     """fp32 cubes with nx = 1024 take the fused route (t21_ps_multipoles: the five sums per k bin are added by the X pass

@@ -48,6 +48,7 @@ class BinSpecC(C.Structure):
         ("seg_tab", C.c_void_p),
         ("seg_stride", C.c_int32),
         ("seg_ntab", C.c_int32),
+        ("seg_overflow", C.c_int32),
     ]
 
 

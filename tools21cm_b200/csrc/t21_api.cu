@@ -438,7 +438,7 @@ int t21_build_pencil_segments(const t21_binspec* spec, uint32_t* out, int stride
     if (spec->zero_idx[0] != 0 || spec->n[0] < 2 || spec->n[0] >= 65535) { set_error("segment tables need a spec in FFT index order"); return T21_EINVAL; }
     if (spec->nk * (spec->nmu > 0 ? spec->nmu : 1) >= 65535) { set_error("too many bins for a segment table"); return T21_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
-    T21_CUDA_OK(cudaMemsetAsync(max_segments_dev, 0, sizeof(int), st));
+    T21_CUDA_OK(cudaMemsetAsync(max_segments_dev, 0, 2 * sizeof(int), st));
     const bool is_signed = spec->nmu > 0 && !spec->absolute_mus;
     if (!is_signed) return launch_pencil_segments(*spec, (spec->nmu == 0 && spec->exclude_zero) ? 5 : 0, out, stride, max_segments_dev, st);
     const size_t per_table = (size_t)spec->n[1] * (spec->n[2] / 2 + 1) * stride;
@@ -455,7 +455,7 @@ int t21_build_pencil_segments_cyl(int n0, int n1, int n2, int nu_axis, const int
         set_error("bad argument to t21_build_pencil_segments_cyl"); return T21_EINVAL;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    T21_CUDA_OK(cudaMemsetAsync(max_segments_dev, 0, sizeof(int), st));
+    T21_CUDA_OK(cudaMemsetAsync(max_segments_dev, 0, 2 * sizeof(int), st));
     return launch_pencil_segments_cyl(n0, n1, n2, nu_axis, perp_tab, par_tab, npar, out, stride, max_segments_dev, st);
 }
 

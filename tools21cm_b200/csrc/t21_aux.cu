@@ -592,8 +592,9 @@ pencil_segments_kernel(const __grid_constant__ t21_binspec B, int which, unsigne
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int s = 0;
     if (i < np) s = build_pencil_segments(B, (int)(i / nzh), (int)(i % nzh), which, out + i * stride, stride);
+    const unsigned novf = __popc(__ballot_sync(0xffffffffu, s > stride));
     for (int o = 16; o > 0; o >>= 1) { const int t = __shfl_xor_sync(0xffffffffu, s, o); s = t > s ? t : s; }
-    if ((threadIdx.x & 31) == 0 && s > 0) atomicMax(max_seg, s);
+    if ((threadIdx.x & 31) == 0 && s > 0) { atomicMax(max_seg, s); if (novf) atomicAdd(max_seg + 1, (int)novf); }
 }
 
 __global__ void __launch_bounds__(128)
@@ -604,8 +605,9 @@ pencil_segments_cyl_kernel(int n0, int n1, int n2, int nu_axis, const int* __res
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int s = 0;
     if (i < np) s = build_pencil_segments_cyl(n0, n1, n2, nu_axis, perp_tab, par_tab, npar, (int)(i / nzh), (int)(i % nzh), out + i * stride, stride);
+    const unsigned novf = __popc(__ballot_sync(0xffffffffu, s > stride));
     for (int o = 16; o > 0; o >>= 1) { const int t = __shfl_xor_sync(0xffffffffu, s, o); s = t > s ? t : s; }
-    if ((threadIdx.x & 31) == 0 && s > 0) atomicMax(max_seg, s);
+    if ((threadIdx.x & 31) == 0 && s > 0) { atomicMax(max_seg, s); if (novf) atomicAdd(max_seg + 1, (int)novf); }
 }
 
 int launch_pencil_segments_cyl(int n0, int n1, int n2, int nu_axis, const int* perp_tab, const int* par_tab, int npar,

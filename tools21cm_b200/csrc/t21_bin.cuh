@@ -148,7 +148,10 @@ T21_HD unsigned segment_modes(bool lo, bool hi, unsigned a, unsigned b, unsigned
     const unsigned nhi = b - (a > 1u ? a : 1u);                      // kx < 0 half: |kx| in [1, H]
     return (lo ? nlo : 0u) + (hi ? nhi : 0u);
 }
-// bin_of(ix) -> flat bin or -1, for ix = f (and ix = nx - f when `mirror_of` is asked to agree)
+// bin_of(ix) -> flat bin or -1, for ix = f (and ix = nx - f when the mirror is asked to agree).  A pencil that needs more
+// than `stride` ranges, or whose mirror disagrees, gets the overflow mark in entry 0 and reports stride + 1: the
+// warp-per-pencil X pass classifies such a pencil mode by mode; the other kernels only take tables without any.
+constexpr unsigned kSegOverflow = 0xFFFE0000u;
 template <class BinOf>
 T21_HD int emit_pencil_segments(int nx, bool check_mirror, bool negative_half, BinOf&& bin_of, unsigned* __restrict__ out, int stride) {
     int s = 0, prev = -2;
@@ -163,7 +166,12 @@ T21_HD int emit_pencil_segments(int nx, bool check_mirror, bool negative_half, B
         }
     }
     for (int j = s; j < stride; ++j) out[j] = kSegSentinel;
-    return (bad || s > stride) ? stride + 1 : s;
+    if (bad || s > stride) {
+        out[0] = kSegOverflow;
+        for (int j = 1; j < stride; ++j) out[j] = kSegSentinel;
+        return stride + 1;
+    }
+    return s;
 }
 
 T21_HD int build_pencil_segments(const t21_binspec& B, int iy, int iz, int which, unsigned* __restrict__ out, int stride) {

@@ -515,7 +515,7 @@ static int gen_x(XArgs& a, cudaStream_t st) {
     t21_binspec B = is_bin ? *a.bins : dummy;
     {   // the segment table is used only when it matches the mode (four tables for signed mu, one otherwise)
         const bool is_signed = B.nmu > 0 && !B.absolute_mus;
-        if (!x_use_segments() || B.seg_ntab != (is_signed ? 4 : 1)) B.seg_tab = nullptr;
+        if (!x_use_segments() || B.seg_ntab != (is_signed ? 4 : 1) || B.seg_overflow != 0) B.seg_tab = nullptr;
     }
 #define T21_GEN_X(HKV)                                                                                          \
     {                                                                                                           \

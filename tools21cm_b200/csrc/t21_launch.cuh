@@ -158,7 +158,7 @@ inline int launch_x(XArgs& a, cudaStream_t st) {
     if constexpr (K::kMode == MODE_BIN) {
         // bins as index ranges from the spec's pencil segment table, when it carries one this kernel can use
         const bool is_signed = a.bins && a.bins->nmu > 0 && !a.bins->absolute_mus;
-        if (K::kSegOk && a.bins && a.bins->seg_tab && a.bins->seg_ntab == (is_signed ? 4 : 1) && x_use_segments()) {
+        if (K::kSegOk && a.bins && a.bins->seg_tab && a.bins->seg_overflow == 0 && a.bins->seg_ntab == (is_signed ? 4 : 1) && x_use_segments()) {
             p.seg = a.bins->seg_tab;
             p.seg_stride = a.bins->seg_stride;
             p.seg_ntab = a.bins->seg_ntab;

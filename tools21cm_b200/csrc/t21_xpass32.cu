@@ -51,6 +51,7 @@ struct Params {
     int seg_stride;
     long long seg_pencils; // pencils per table: ny_global * nzh
     int mp_los;            // multipoles: line-of-sight axis
+    int seg_overflow;      // pencils of the table marked kSegOverflow (classified mode by mode)
 };
 
 #if T21_DEVICE_CODE
@@ -293,9 +294,47 @@ __device__ __forceinline__ void walk_segments(const cx<float>* v, int lane, unsi
 }
 
 // NT = 1: bins even in kx, one table; NT = 4: signed mu, tables {own kx>=0, own kx<0, twin kx>=0, twin kx<0}
+// A pencil with more ranges than the table holds (a fine binning -- the reference's default is 100 bins -- on a pencil
+// next to the kx axis): classify its modes one by one, as the CTA-per-tile kernel does, through the two-entry warp cache.
+template <int NT, class Hist>
+__device__ __noinline__ void epilogue_classify(const Params& p, float v0x, float v0y, int lane, int iy, int iz, float* __restrict__ strip,
+                                               Hist& hist) {
+    // (the caller has parked the 32 powers of every lane in the strip: the values stay in registers on its side)
+    const bool has_twin = (iz != 0) && (iz != p.nz - iz);
+    if (iy == 0 && iz == 0 && lane == 0) {
+        const double c0 = p.offset ? (double)ldg(p.offset) : 0.0;
+        const double ra = (double)v0x + c0 * p.ntot;
+        const double dc = ra * ra + (double)v0y * (double)v0y;
+        strip[0] = 0.f;                                    // counted in the flow, its power added here
+        const int b0 = classify(p.bins, 0, 0, 0, false).own;
+        if (b0 >= 0) hist.add(b0, dc, 0u);
+    }
+    WarpBinCache c;
+    wbc_init(c);
+#pragma unroll 1
+    for (int q = 0; q < 32; ++q) {
+        const ModeBins mb = classify(p.bins, lane + 32 * q, iy, iz, has_twin);
+        const double pw = (double)strip[q * 32 + lane];
+        wbc_add(c, hist, mb.own, pw * (double)mb.own_w, (unsigned)mb.own_w);
+        if (NT == 4) wbc_add(c, hist, mb.twin, pw, 1u);
+    }
+    wbc_flush(c, hist);
+}
+
 template <int NT, class Hist>
 __device__ __forceinline__ void epilogue_segments(const Params& p, cx<float>* v, int lane, int iy, int iz, const unsigned* ent,
                                                   float* __restrict__ strip, Hist& hist) {
+    if (p.seg_overflow) {                                  // (warp-uniform: entry 0 of table 0, or of any table for signed mu)
+        bool ovf = false;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) ovf = ovf || ent[t] == kSegOverflow;
+        if (__any_sync(0xffffffffu, ovf)) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) strip[q * 32 + lane] = v[q].x * v[q].x + v[q].y * v[q].y;
+            epilogue_classify<NT>(p, v[0].x, v[0].y, lane, iy, iz, strip, hist);
+            return;
+        }
+    }
     if (iy == 0 && iz == 0) {
         // DC of (x - c) plus c*N: the only sample the mean offset changes.  It stays in the flow with power 0 (so
         // that it is counted like any other mode); its true power goes to the histogram here, with count 0.
@@ -613,6 +652,7 @@ static int launch(XArgs& a, cudaStream_t st, int moments_los = -1) {
     p.seg = a.bins->seg_tab;
     p.seg_stride = a.bins->seg_stride;
     p.seg_pencils = (long long)a.bins->n[1] * a.nzh;
+    p.seg_overflow = a.bins->seg_overflow;
     const int nt = (p.seg != nullptr && use_segments()) ? a.bins->seg_ntab : 0;
     if (nt != 0 && nt != 1 && nt != 4) { set_error("bad segment table count %d", nt); return T21_EINVAL; }
     p.mp_los = moments_los;
@@ -667,7 +707,7 @@ bool xpass32_applicable(int dtype, const XArgs& a) {
         return false;
     if (a.bins->seg_tab != nullptr && x32::use_segments()) {     // bins as table-driven index ranges
         const bool is_signed = a.bins->nmu > 0 && !a.bins->absolute_mus;
-        return a.nbins <= 128 && a.bins->seg_ntab == (is_signed ? 4 : 1);
+        return a.nbins <= 128 && a.bins->seg_ntab == (is_signed ? 4 : 1) && (a.bins->seg_overflow == 0 || a.bins->thr != nullptr);
     }
     return a.bins->nmu == 0 && a.bins->nk <= 31;
 }
@@ -679,7 +719,8 @@ int launch_xpass32_bin(XArgs& a, cudaStream_t st) {
 // multipole moments fused into the X pass: fp32, nx = 1024, one field, a shell spec that carries its segment table
 bool xpass32_moments_applicable(int dtype, const XArgs& a) {
     return dtype == T21_F32 && a.nx == x32::NX && a.nf == 1 && a.bins != nullptr && a.tw32 != nullptr && a.pitch % x32::WZ == 0 &&
-           a.bins->seg_tab != nullptr && a.bins->seg_ntab == 1 && a.bins->nmu == 0 && a.bins->nk <= 64 && x32::use_segments();
+           a.bins->seg_tab != nullptr && a.bins->seg_ntab == 1 && a.bins->seg_overflow == 0 && a.bins->nmu == 0 && a.bins->nk <= 64 &&
+           x32::use_segments();
 }
 int launch_xpass32_moments(XArgs& a, int los_axis, cudaStream_t st) {
     return x32::launch(a, st, los_axis);

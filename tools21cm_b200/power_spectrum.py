@@ -116,25 +116,28 @@ class _Device:
             self._attach_segments(hit)
         return hit
 
-    def _segment_table(self, entries_per_stride, build):
+    def _segment_table(self, entries_per_stride, build, max_overflow=0.0):
         """Run a segment-table builder with 32 entries per pencil, then again with 8 or 16 if that is all any pencil
-        needs.  Returns (int32 tensor, stride) or (None, 0) when some pencil needs more than 32 ranges."""
+        needs.  Returns (int32 tensor, stride, overflow pencils) or (None, 0, 0) when more than ``max_overflow`` of the
+        pencils need over 32 ranges (the few that do are marked in the table and classified mode by mode)."""
         torch = _torch()
         dev = "cuda:%d" % self.index
-        maxseg = torch.zeros(1, dtype=torch.int32, device=dev)
+        stats = torch.zeros(2, dtype=torch.int32, device=dev)
         stream = _stream_ptr(torch, self.index)
         stride = 32
         for _ in range(2):
             table = torch.empty(entries_per_stride * stride, dtype=torch.int32, device=dev)
-            build(table.data_ptr(), stride, maxseg.data_ptr(), stream)
-            m = int(maxseg.item())
+            build(table.data_ptr(), stride, stats.data_ptr(), stream)
+            m, novf = (int(v) for v in stats.tolist())
             if m > stride:
-                return None, 0
+                if stride == 32 and novf <= max_overflow * entries_per_stride:
+                    return table, stride, novf
+                return None, 0, 0
             want = 8 if m <= 8 else (16 if m <= 16 else 32)
             if want == stride:
                 break
             stride = want
-        return table, stride
+        return table, stride, 0
 
     def _attach_segments(self, hit):
         """The pencil segment table of the warp-per-pencil X pass (``t21_build_pencil_segments``): along an x pencil the
@@ -154,10 +157,14 @@ class _Device:
         ntab = 4 if (spec.nmu and not spec.absolute_mus) else 1      # signed mu: own / twin bins for kx >= 0 and kx < 0
         lib = _lib.load()
         npencils = int(spec.shape[1]) * (int(spec.shape[2]) // 2 + 1)
-        table, stride = self._segment_table(ntab * npencils, lambda ptr, st, mx, stream: _lib.check(
-            lib.t21_build_pencil_segments(C.byref(cspec), ptr, st, mx, stream), "t21_build_pencil_segments"))
+        # (pencils next to the kx axis cross every bin: with a fine binning a few need more than 32 ranges; the
+        # warp-per-pencil kernel classifies those mode by mode, the other X passes only take tables without any)
+        table, stride, novf = self._segment_table(ntab * npencils, lambda ptr, st, mx, stream: _lib.check(
+            lib.t21_build_pencil_segments(C.byref(cspec), ptr, st, mx, stream), "t21_build_pencil_segments"),
+            max_overflow=float(os.environ.get("T21_SEG_MAX_OVERFLOW", "0.02")) if nx == 1024 else 0.0)
         if table is None:
-            return                          # some pencil needs more ranges than a table holds: classify per mode
+            return                          # too many pencils need more ranges than a table holds: classify per mode
+        cspec.seg_overflow = novf
         owners.append(table)
         cspec.seg_tab = table.data_ptr()
         cspec.seg_stride = stride
@@ -173,7 +180,7 @@ class _Device:
                 return None
             lib = _lib.load()
             n0, n1, n2 = (int(v) for v in key[0])
-            table, stride = self._segment_table(n1 * (n2 // 2 + 1), lambda ptr, st, mx, stream: _lib.check(
+            table, stride, _novf = self._segment_table(n1 * (n2 // 2 + 1), lambda ptr, st, mx, stream: _lib.check(
                 lib.t21_build_pencil_segments_cyl(n0, n1, n2, nu_axis, perp.data_ptr(), par.data_ptr(), cyl.nperp, cyl.npar,
                                                   ptr, st, mx, stream), "t21_build_pencil_segments_cyl"))
             if table is None:

@@ -133,6 +133,15 @@ T21_API int t21_ps_binned(const t21_plan* plan, const void* x1, const void* x2_o
                   const t21_binspec* spec, double* sums_out, long long* counts_out,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* t21_ps_binned fed from HOST memory (one field; power-of-two axes): the cube is copied in groups of x planes on an
+ * internal copy stream -- through the pinned ring of t21_h2d_staged for pageable memory (host_is_pinned == 0), straight
+ * for pinned memory -- while `stream` runs the Z and Y passes on the groups that have landed; only the X pass is left
+ * after the copy.  x_dev: device buffer of the cube's size (scratch for the caller afterwards).  This is what
+ * power_spectrum_1d(numpy_array) (power_spectrum.py:137-174 with its float64 copy at :45) costs end to end. */
+T21_API int t21_ps_binned_host(const t21_plan* plan, const void* x_host, int host_is_pinned, int subtract_mean,
+                               const t21_binspec* spec, double* sums_out, long long* counts_out, void* x_dev,
+                               void* workspace, size_t workspace_bytes, int threads, void* stream);
+
 /* The batch behind integrated_bispectrum / power_spectrum_response (position_dependent_power_spectrum.py:45-88): the
  * binned auto power spectrum of `nwindows` cubically masked copies of one cube, `cube * W_L` (:65-77,90-103), with the
  * mask fused into the first pass's load -- no masked cube is written, only the window's samples are read, and one

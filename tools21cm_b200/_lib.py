@@ -141,6 +141,8 @@ def load():
     lib.t21_workspace_bytes.restype = sz
     lib.t21_ps_binned.argtypes = [vp, vp, vp, i32, C.POINTER(BinSpecC), vp, vp, vp, sz, vp]
     lib.t21_ps_binned.restype = i32
+    lib.t21_ps_binned_host.argtypes = [vp, vp, i32, i32, C.POINTER(BinSpecC), vp, vp, vp, vp, sz, i32, vp]
+    lib.t21_ps_binned_host.restype = i32
     lib.t21_ps_binned_windows.argtypes = [vp, vp, C.POINTER(C.c_int), i32, C.POINTER(BinSpecC), vp, vp, vp, sz, vp]
     lib.t21_ps_binned_windows.restype = i32
     lib.t21_ps_nd.argtypes = [vp, vp, vp, i32, dbl, vp, i32, vp, sz, vp]

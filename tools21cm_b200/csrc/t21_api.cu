@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "t21_internal.h"
@@ -328,6 +330,112 @@ int t21_ps_multipoles(const t21_plan* p, const void* x1, int subtract_mean, cons
     prof_mark(st, SLOT_X);
     const int rc = launch_reduce_moments(a.part_sum, a.part_cnt, a.grid_used, nk, sums_out, counts_out, st);
     prof_mark(st, SLOT_REDUCE);
+    return rc;
+}
+
+// ---- the estimator fed from HOST memory, copy overlapped with the first two passes ----------------------------------------
+// A numpy cube (the reference's calling convention) costs one PCIe copy of 4 N^3 bytes, ~78 ms at 1024^3 against 4 ms of
+// kernels.  The Z and Y passes work plane by plane along x, so they can run on the x planes that have already landed
+// while the rest of the cube is still on the link: the cube is copied in groups of planes on an internal copy stream
+// (through the pinned ring for pageable memory, straight for pinned memory), the caller's stream waits for each group's
+// event and runs Z and Y on it; only the last group's passes and the X pass are left after the copy.
+namespace t21 {
+struct HostFeed {
+    cudaStream_t copy = nullptr;
+    std::vector<cudaEvent_t> ev;
+    cudaEvent_t start = nullptr;
+};
+static HostFeed g_feed[64];
+static std::mutex g_feed_mu;
+}  // namespace t21
+
+int t21_ps_binned_host(const t21_plan* p, const void* x_host, int host_is_pinned, int subtract_mean, const t21_binspec* spec,
+                       double* sums_out, long long* counts_out, void* x_dev, void* workspace, size_t workspace_bytes,
+                       int threads, void* stream) {
+    if (!spec || !sums_out || !counts_out || !x_host || !x_dev) { set_error("null argument"); return T21_EINVAL; }
+    const int nbins = spec->nk * (spec->nmu > 0 ? spec->nmu : 1);
+    if (nbins < 1) { set_error("no bins"); return T21_EINVAL; }
+    if (p && (spec->n[0] != p->n[0] || spec->n[1] != p->n[1] || spec->n[2] != p->n[2])) {
+        set_error("bin spec shape does not match the plan"); return T21_EINVAL;
+    }
+    const WsLayout L = p ? ws_layout(p, 1, nbins) : WsLayout();
+    if (int rc = check_common(p, x_dev, workspace, L.total, workspace_bytes)) return rc;
+    if (!(p->fast[0] && p->fast[1] && p->fast[2]) || p->device < 0 || p->device >= 64) {
+        set_error("the host-fed estimator needs power-of-two axes"); return T21_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* ws = (unsigned char*)workspace;
+    const size_t rsz = p->dtype == T21_F32 ? 4 : 8, esz = 2 * rsz, lw = 64 / esz;
+    const size_t plane = (size_t)p->n[1] * p->n[2] * rsz;
+    int gp = (int)std::max<size_t>(1, (size_t)(128u << 20) / plane);          // x planes per group, ~128 MB
+    if (gp > p->n[0]) gp = p->n[0];
+    const int ngroups = (p->n[0] + gp - 1) / gp;
+
+    std::lock_guard<std::mutex> lock(g_feed_mu);
+    HostFeed& F = g_feed[p->device];
+    if (!F.copy) {
+        T21_CUDA_OK(cudaStreamCreateWithFlags(&F.copy, cudaStreamNonBlocking));
+        T21_CUDA_OK(cudaEventCreateWithFlags(&F.start, cudaEventDisableTiming));
+    }
+    while ((int)F.ev.size() < ngroups) {
+        cudaEvent_t e;
+        T21_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        F.ev.push_back(e);
+    }
+    // the copy may only start once the caller's earlier work on `stream` (which may still use x_dev) is done
+    T21_CUDA_OK(cudaEventRecord(F.start, st));
+    T21_CUDA_OK(cudaStreamWaitEvent(F.copy, F.start, 0));
+    prof_begin(st);
+    const void* off = nullptr;
+    for (int g = 0; g < ngroups; ++g) {
+        const int x0 = g * gp, np = std::min(gp, p->n[0] - x0);
+        unsigned char* dst = (unsigned char*)x_dev + (size_t)x0 * plane;
+        const unsigned char* src = (const unsigned char*)x_host + (size_t)x0 * plane;
+        if (host_is_pinned) T21_CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)np * plane, cudaMemcpyHostToDevice, F.copy));
+        else if (int rc = t21_h2d_staged(dst, src, (size_t)np * plane, threads, F.copy)) return rc;
+        T21_CUDA_OK(cudaEventRecord(F.ev[g], F.copy));
+        T21_CUDA_OK(cudaStreamWaitEvent(st, F.ev[g], 0));
+        if (g == 0 && subtract_mean) {
+            // c only has to be close to the mean (the DC sample is repaired exactly): the first group's sample will do
+            void* o = ws + L.offs;
+            if (int rc = launch_mean_estimate(p->dtype, dst, (long long)np * p->n[1] * p->n[2], o, st)) return rc;
+            off = o;
+        }
+        unsigned char* wg = ws + L.w[0] + (size_t)x0 * p->n[1] * lw * esz;
+        ZArgs z{dst, wg, (long long)np * p->n[1], p->n[2], p->pitch, p->n[1], (long long)p->n[0], off, p->tw[2], p->twr, nullptr};
+        if (int rc = launch_zpass(p->dtype, z, st)) return rc;
+        YArgs y{wg, (long long)np, p->n[1], p->nzh, p->pitch, p->tw[1], nullptr, 0, nullptr, 0, 0, 0, (long long)p->n[0]};
+        if (int rc = launch_ypass(p->dtype, y, st)) return rc;
+    }
+    prof_mark(st, SLOT_Z);
+    XArgs a;
+    memset(&a, 0, sizeof(a));
+    a.w[0] = ws + L.w[0];
+    a.nf = 1;
+    a.nx = p->n[0]; a.ny = p->n[1]; a.nz = p->n[2]; a.nzh = p->nzh; a.pitch = p->pitch; a.xs_log2 = -1;
+    a.tw = p->tw[0]; a.tw32 = p->tw32[0];
+    a.offset[0] = off;
+    a.ntot = (double)p->n[0] * p->n[1] * p->n[2];
+    a.bins = spec;
+    a.nbins = nbins;
+    a.hist_global = L.nbins_cap == 0;
+    a.part_sum = (double*)(ws + L.part_sum);
+    a.part_cnt = (unsigned*)(ws + L.part_cnt);
+    a.gsum = sums_out;
+    a.gcnt = (unsigned long long*)counts_out;
+    a.max_grid = p->max_grid;
+    if (!spec->thr && !xpass32_applicable(p->dtype, a)) {
+        set_error("a table-only bin spec (no thresholds) can only run on the warp-per-pencil X pass"); return T21_EINVAL;
+    }
+    if (a.hist_global)
+        if (int rc = launch_zero_hist(sums_out, counts_out, nbins, st)) return rc;
+    int rc = launch_xpass_bin(p->dtype, a, st);
+    if (rc) return rc;
+    prof_mark(st, SLOT_X);
+    if (!a.hist_global) {
+        rc = launch_reduce_partials(a.part_sum, a.part_cnt, a.grid_used, nbins, sums_out, counts_out, st);
+        prof_mark(st, SLOT_REDUCE);
+    }
     return rc;
 }
 

@@ -63,6 +63,9 @@ static void stream_copy(unsigned char* dst, const unsigned char* src, size_t n) 
 
 static int ring_init() {
     if (g_ring.ok) return 0;
+    // several ranks on one host (torchrun sets LOCAL_WORLD_SIZE): their rings together no longer fit the last-level
+    // cache, so each goes back to 32 MB chunks written with streaming stores (8 ranks: 43 cubes/s against 16)
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) { if (atoi(e) > 1) { g_nt_stores = true; kChunk = 32u << 20; } }
     if (const char* e = getenv("T21_H2D_NT")) g_nt_stores = e[0] != '0';
     if (const char* e = getenv("T21_H2D_CHUNK_MB")) { const long mb = atol(e); if (mb >= 1 && mb <= 1024) kChunk = (size_t)mb << 20; }
     for (int i = 0; i < kRing; ++i) {

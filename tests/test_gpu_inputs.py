@@ -93,3 +93,24 @@ def test_staged_host_to_device_copy_is_exact(t2c):
     ps_o, ks_o, nm_o = ps_oracle.power_spectrum_1d(cube, kbins=8, box_dims=100.0, return_n_modes=True)
     assert np.array_equal(nm, nm_o)
     np.testing.assert_allclose(ps, ps_o, rtol=1e-5, equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_host_fed_estimator_equals_the_resident_one(t2c, monkeypatch):
+    """A numpy cube (or a pinned CPU tensor) handed to power_spectrum_1d / power_spectrum_mu is copied in groups of x planes
+    while the Z and Y passes run on the groups that have landed (t21_ps_binned_host).  Same mode counts, and powers equal
+    to the device-resident call up to the rounding of a different mean offset (it is estimated on the first group)."""
+    import torch
+    from tools21cm_b200 import synthetic
+    monkeypatch.setenv("T21_HOST_FEED_GROUP_MB", "8")          # (read once per process: eight groups for this cube)
+    a = synthetic.toy_dt_cube((256, 256, 256), 3, np.dtype("float32"))
+    dev = torch.from_numpy(a).cuda()
+    ref = t2c.power_spectrum_1d(dev, kbins=12, box_dims=300.0, return_n_modes=True)
+    for host in (a, torch.from_numpy(a).pin_memory()):
+        got = t2c.power_spectrum_1d(host, kbins=12, box_dims=300.0, return_n_modes=True)
+        assert np.array_equal(got[2], ref[2]) and np.array_equal(got[1], ref[1])
+        np.testing.assert_allclose(got[0], ref[0], rtol=2e-6)
+    refm = t2c.power_spectrum_mu(dev, los_axis=1, mubins=4, kbins=6, box_dims=300.0, return_n_modes=True, absolute_mus=False)
+    gotm = t2c.power_spectrum_mu(a, los_axis=1, mubins=4, kbins=6, box_dims=300.0, return_n_modes=True, absolute_mus=False)
+    assert np.array_equal(gotm[3], refm[3])
+    np.testing.assert_allclose(gotm[0], refm[0], rtol=2e-6, equal_nan=True)

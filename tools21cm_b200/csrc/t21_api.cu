@@ -367,7 +367,12 @@ int t21_ps_binned_host(const t21_plan* p, const void* x_host, int host_is_pinned
     unsigned char* ws = (unsigned char*)workspace;
     const size_t rsz = p->dtype == T21_F32 ? 4 : 8, esz = 2 * rsz, lw = 64 / esz;
     const size_t plane = (size_t)p->n[1] * p->n[2] * rsz;
-    int gp = (int)std::max<size_t>(1, (size_t)(128u << 20) / plane);          // x planes per group, ~128 MB
+    static const size_t group_bytes = [] {                                    // ~128 MB per group; T21_HOST_FEED_GROUP_MB for tests
+        const char* e = getenv("T21_HOST_FEED_GROUP_MB");
+        const long mb = e ? atol(e) : 0;
+        return (size_t)(mb >= 1 && mb <= 4096 ? mb : 128) << 20;
+    }();
+    int gp = (int)std::max<size_t>(1, group_bytes / plane);                    // x planes per group
     if (gp > p->n[0]) gp = p->n[0];
     const int ngroups = (p->n[0] + gp - 1) / gp;
 

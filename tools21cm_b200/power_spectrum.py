@@ -234,8 +234,29 @@ def _require_cuda():
     return torch
 
 
-def _stage(arr):
-    """-> (contiguous CUDA tensor of float32/float64, was_numpy).  Never copies back."""
+class _HostCube:
+    """A cube still in host memory, handed to the fused estimator as it is: ``t21_ps_binned_host`` copies it in groups of
+    x planes while the Z and Y passes already run on the groups that have landed.  Carries what the estimators read from
+    a staged tensor (shape, dtype, device)."""
+    is_host = True
+
+    def __init__(self, owner, ptr, shape, dtype, pinned, device):
+        self.owner, self.ptr, self.shape, self.dtype, self.pinned, self.device = owner, ptr, tuple(shape), dtype, pinned, device
+
+    def dim(self):
+        return len(self.shape)
+
+
+def _host_feed_ok(shape, nbytes):
+    """Cubes worth overlapping: 3-D, power-of-two axes the Stockham passes take, at least 64 MB."""
+    if os.environ.get("T21_HOST_FEED", "1") == "0" or len(shape) != 3 or nbytes < (64 << 20):
+        return False
+    return all(8 <= n <= 4096 and (n & (n - 1)) == 0 for n in shape)
+
+
+def _stage(arr, lazy=False):
+    """-> (contiguous CUDA tensor of float32/float64, was_numpy).  Never copies back.  ``lazy``: a large host cube is
+    returned as a ``_HostCube`` for the estimators that overlap its copy with their first passes."""
     torch = _require_cuda()
     was_numpy = not isinstance(arr, torch.Tensor)
     if was_numpy:
@@ -245,6 +266,9 @@ def _stage(arr):
         else:
             want = np.dtype(np.float32) if a.dtype == np.float32 else np.dtype(np.float64)
         a = np.ascontiguousarray(a, dtype=want)
+        if lazy and _host_feed_ok(a.shape, a.nbytes) and a.ctypes.data % 16 == 0:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            return _HostCube(a, a.ctypes.data, a.shape, torch.float32 if want == np.float32 else torch.float64, False, dev), True
         t = _h2d(a)
     else:
         t = arr
@@ -252,6 +276,10 @@ def _stage(arr):
             want = torch.float32 if _PRECISION == "float32" else torch.float64
         else:
             want = torch.float32 if t.dtype == torch.float32 else torch.float64
+        if (lazy and not t.is_cuda and t.dtype == want and t.is_contiguous() and t.is_pinned() and t.data_ptr() % 16 == 0
+                and _host_feed_ok(tuple(t.shape), t.numel() * t.element_size())):
+            dev = torch.device("cuda", torch.cuda.current_device())
+            return _HostCube(t, t.data_ptr(), t.shape, want, True, dev), False
         if not t.is_cuda:
             t = t.to("cuda", non_blocking=True)
         if t.dtype != want:
@@ -315,11 +343,19 @@ def _fused_binned(fields, spec_key, spec_builder):
         ws = dev.workspace(need)
         sums = torch.empty(nb, dtype=torch.float64, device=x.device)
         counts = torch.empty(nb, dtype=torch.int64, device=x.device)
-        x2 = fields[1].data_ptr() if len(fields) == 2 else None
-        rc = lib.t21_ps_binned(plan, x.data_ptr(), x2, 1 if code == T21_F32 else 0, C.byref(cspec),
-                               sums.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(),
-                               _stream_ptr(torch, x.device.index))
-        _lib.check(rc, "t21_ps_binned")
+        if getattr(x, "is_host", False):
+            # the cube is still on the host: copy it in groups of x planes while Z and Y run on the ones that have landed
+            xdev = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+            rc = lib.t21_ps_binned_host(plan, x.ptr, int(x.pinned), 1 if code == T21_F32 else 0, C.byref(cspec),
+                                        sums.data_ptr(), counts.data_ptr(), xdev.data_ptr(), ws.data_ptr(), ws.numel(),
+                                        _copy_threads(), _stream_ptr(torch, x.device.index))
+            _lib.check(rc, "t21_ps_binned_host")
+        else:
+            x2 = fields[1].data_ptr() if len(fields) == 2 else None
+            rc = lib.t21_ps_binned(plan, x.data_ptr(), x2, 1 if code == T21_F32 else 0, C.byref(cspec),
+                                   sums.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(),
+                                   _stream_ptr(torch, x.device.index))
+            _lib.check(rc, "t21_ps_binned")
         out = torch.empty(2 * nb, dtype=torch.float64, device=x.device)
         out[:nb] = sums
         out[nb:] = counts.to(torch.float64)
@@ -627,7 +663,7 @@ def power_spectrum_1d(input_array_nd, kbins=100, box_dims=None, return_n_modes=F
     if kwargs.get("boxsize") is not None:
         box_dims = kwargs.get("boxsize")
     box_dims = _get_dims(box_dims, input_array_nd.shape)
-    x, _ = _stage(input_array_nd)
+    x, _ = _stage(input_array_nd, lazy=True)
     ps, bins, n_modes = _shell_estimate([x], kbins, box_dims, binning, breakpoint)
     if return_n_modes:
         return ps, bins, n_modes
@@ -660,7 +696,7 @@ def power_spectrum_mu(input_array, los_axis=0, mubins=20, kbins=10, box_dims=Non
         box_dims = kwargs.get("boxsize")
     box_dims = _get_dims(box_dims, input_array.shape)
     _reject_weights(weights)
-    x, _ = _stage(input_array)
+    x, _ = _stage(input_array, lazy=True)
     ps, mu_bins, k_bins, n_modes = _mu_estimate([x], los_axis, mubins, kbins, box_dims, weights,
                                                 exclude_zero_modes, absolute_mus)
     if return_n_modes:

@@ -540,7 +540,8 @@ static int ps_nd_impl(const t21_plan* p, const void* x1, const void* x2, int sub
     a.nd_out = out; a.nd_f64 = out_dtype == T21_F64; a.scale = scale; a.nd_half = half ? t21_half_pitch(p) : 0;
     a.max_grid = p->max_grid;
     const int rc = !p->fast[0] ? launch_xpass_generic(p->dtype, a, st)
-                               : (p->dtype == T21_F32 ? launch_xpass_f32_nd(a, st) : launch_xpass_f64_nd(a, st));
+                               : (xpass32_store_applicable(p->dtype, a) ? launch_xpass32_store(a, st)
+                               : (p->dtype == T21_F32 ? launch_xpass_f32_nd(a, st) : launch_xpass_f64_nd(a, st)));
     prof_mark(st, SLOT_X);
     return rc;
 }
@@ -764,7 +765,8 @@ int t21_slab_stage2_nd(const t21_plan* p, const void* w1, const void* w2, int n_
     a.ntot = (double)p->n[0] * ny_global * p->n[2];
     a.nd_out = out_half; a.nd_f64 = out_dtype == T21_F64; a.nd_half = t21_half_pitch(p); a.scale = scale;
     a.max_grid = p->max_grid;
-    const int rc = p->dtype == T21_F32 ? launch_xpass_f32_nd(a, st) : launch_xpass_f64_nd(a, st);
+    const int rc = xpass32_store_applicable(p->dtype, a) ? launch_xpass32_store(a, st)
+                 : (p->dtype == T21_F32 ? launch_xpass_f32_nd(a, st) : launch_xpass_f64_nd(a, st));
     prof_mark(st, SLOT_X);
     return rc;
 }

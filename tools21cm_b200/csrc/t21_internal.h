@@ -45,6 +45,8 @@ int launch_xpass_f64_nd(XArgs& a, cudaStream_t st);
 // t21_xpass32.cu: warp-per-pencil X pass (fp32, nx = 1024, one field), TMA-staged
 bool xpass32_applicable(int dtype, const XArgs& a);
 int launch_xpass32_bin(XArgs& a, cudaStream_t st);
+bool xpass32_store_applicable(int dtype, const XArgs& a);
+int launch_xpass32_store(XArgs& a, cudaStream_t st);
 bool xpass32_moments_applicable(int dtype, const XArgs& a);
 int launch_xpass32_moments(XArgs& a, int los_axis, cudaStream_t st);   // part_sum [grid][nk][5], part_cnt [grid][nk]
 

@@ -52,6 +52,9 @@ struct Params {
     long long seg_pencils; // pencils per table: ny_global * nzh
     int mp_los;            // multipoles: line-of-sight axis
     int seg_overflow;      // pencils of the table marked kSegOverflow (classified mode by mode)
+    void* nd_out;          // NT = 6: out_half[NX][ny][nd_pitch], the scaled power of the computed half spectrum, FFT order
+    int nd_f64, nd_pitch;
+    double scale;
 };
 
 #if T21_DEVICE_CODE
@@ -513,12 +516,12 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& 
         cx<float> v[32];
         const int iz = (int)chunk * WZ + warp;
         // this pencil's ranges: asked for now, needed after the two butterfly stages
-        constexpr int NTAB = NT == 4 ? 4 : 1;             // NT: 0 in-kernel shells, 1 one table, 4 signed mu, 5 multipoles
+        constexpr int NTAB = NT == 4 ? 4 : 1;             // NT: 0 in-kernel shells, 1 one table, 4 signed mu, 5 multipoles, 6 n-D store
         unsigned ent[NTAB];
 #pragma unroll
         for (int t = 0; t < NTAB; ++t) {
             ent[t] = kSegSentinel;
-            if (NT > 0 && lane < p.seg_stride && iz < p.nzh)
+            if (NT > 0 && NT != 6 && lane < p.seg_stride && iz < p.nzh)
                 ent[t] = ldg(p.seg + ((size_t)t * p.seg_pencils + (size_t)iy * p.nzh + iz) * p.seg_stride + lane);
         }
         mbar_wait(bar, parity);
@@ -552,7 +555,50 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& 
 #pragma unroll
         for (int k = 1; k < 32; ++k) v[k] = cmul(v[k], ldg(p.tw + (k - 1) * 32 + lane));
         DFT<32, float>::run(v);                            // v[k] = X[lane + 32 k]
-        if (iz < p.nzh) {
+        if constexpr (NT == 6) {
+            // n-D outputs: powers go to a [kx][8 + 1] tile in shared memory (pitch 9: a warp's 32 kx fall on 32 banks),
+            // then every thread writes whole 32-byte runs -- the 8 columns of this piece at one kx -- of the output
+            float* st = reinterpret_cast<float*>(smem_raw + STAGE_OFF);
+            double* dc_slot = reinterpret_cast<double*>(smem_raw + BAR_OFF + 64);
+            if (iz < p.nzh) {
+                if (iy == 0 && iz == 0 && lane == 0) {
+                    const double c0 = p.offset ? (double)ldg(p.offset) : 0.0;
+                    const double ra = (double)v[0].x + c0 * p.ntot;
+                    *dc_slot = ra * ra + (double)v[0].y * (double)v[0].y;
+                }
+#pragma unroll
+                for (int k = 0; k < 32; ++k) st[(lane + 32 * k) * 9 + warp] = v[k].x * v[k].x + v[k].y * v[k].y;
+            }
+            __syncthreads();
+            const int ncols = p.nzh - (int)chunk * WZ < WZ ? p.nzh - (int)chunk * WZ : WZ;
+            const int iy_loc = iy - p.iy0;
+#pragma unroll 1
+            for (int kx = tid; kx < NX; kx += THREADS) {
+                const float* row = st + kx * 9;
+                const size_t o = ((size_t)kx * p.ny + iy_loc) * p.nd_pitch + (size_t)chunk * WZ;
+                double val[WZ];
+#pragma unroll
+                for (int c = 0; c < WZ; ++c) val[c] = (double)row[c] * p.scale;
+                if (kx == 0 && iy == 0 && chunk == 0) val[0] = *dc_slot * p.scale;
+                if (p.nd_f64) {
+                    double* d = (double*)p.nd_out + o;
+                    if (ncols == WZ) {
+#pragma unroll
+                        for (int c = 0; c < WZ; c += 2) *reinterpret_cast<double2*>(d + c) = make_double2(val[c], val[c + 1]);
+                    } else {
+                        for (int c = 0; c < ncols; ++c) d[c] = val[c];
+                    }
+                } else {
+                    float* d = (float*)p.nd_out + o;
+                    if (ncols == WZ) {
+                        *reinterpret_cast<float4*>(d) = make_float4((float)val[0], (float)val[1], (float)val[2], (float)val[3]);
+                        *reinterpret_cast<float4*>(d + 4) = make_float4((float)val[4], (float)val[5], (float)val[6], (float)val[7]);
+                    } else {
+                        for (int c = 0; c < ncols; ++c) d[c] = (float)val[c];
+                    }
+                }
+            }
+        } else if (iz < p.nzh) {
             float* stage = reinterpret_cast<float*>(smem_raw + STAGE_OFF) + warp * 1024;
             if constexpr (NT == 5) epilogue_multipoles(p, v, lane, iy, iz, ent[0], stage, hist);
             else if constexpr (NT > 0) epilogue_segments<NT>(p, v, lane, iy, iz, ent, stage, hist);
@@ -627,6 +673,25 @@ xpass32_moments_kernel(const __grid_constant__ CUtensorMap map, const __grid_con
         for (int w = 0; w < NW; ++w) c += hc[(size_t)w * nk + b];
         part_cnt[(size_t)blockIdx.x * nk + b] = c;
     }
+#endif
+}
+
+// n-D outputs: no histogram, the power of the computed half spectrum is stored
+struct NoHist32 {
+    __device__ void add(int, double, unsigned) {}
+};
+constexpr int kStoreSmem = STAGE_OFF + NX * 9 * 4;
+__global__ void __launch_bounds__(THREADS, 2)
+xpass32_store_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ Params p) {
+#if T21_DEVICE_CODE
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    if (threadIdx.x == 0) {
+        mbar_init(smem_raw + BAR_OFF, 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
+    NoHist32 hist;
+    run_tiles<6>(&map, p, smem_raw, hist, 0);
 #endif
 }
 
@@ -714,6 +779,42 @@ bool xpass32_applicable(int dtype, const XArgs& a) {
 
 int launch_xpass32_bin(XArgs& a, cudaStream_t st) {
     return x32::launch(a, st);
+}
+
+// the scaled power of the computed half spectrum (t21_ps_half, t21_slab_stage2_nd): fp32 transform, nx = 1024, one field
+bool xpass32_store_applicable(int dtype, const XArgs& a) {
+    static const bool on = [] { const char* e = getenv("T21_PENCIL32_ND"); return !(e && e[0] == '0'); }();
+    return on && dtype == T21_F32 && a.nx == x32::NX && a.nf == 1 && a.nd_out != nullptr && a.nd_half > 0 && a.nd_half % x32::WZ == 0 &&
+           a.tw32 != nullptr && a.pitch % x32::WZ == 0;
+}
+int launch_xpass32_store(XArgs& a, cudaStream_t st) {
+    using namespace x32;
+    Params p;
+    memset(&p, 0, sizeof(p));
+    p.ny = a.ny; p.nz = a.nz; p.nzh = a.nzh; p.iy0 = a.iy0;
+    p.nchunks = (a.nzh + WZ - 1) / WZ;
+    p.ntiles = (long long)a.ny * p.nchunks;
+    p.xs_log2 = a.xs_log2 >= 0 ? a.xs_log2 : 10;
+    const int nxs = 1 << p.xs_log2;
+    p.box_rows = nxs < 256 ? nxs : 256;
+    p.tw = (const cx<float>*)a.tw32;
+    p.offset = (const float*)a.offset[0];
+    p.ntot = a.ntot;
+    p.nd_out = a.nd_out; p.nd_f64 = a.nd_f64; p.nd_pitch = a.nd_half; p.scale = a.scale;
+    CUtensorMap map;
+    if (int rc = make_wmap_f32(&map, a.w[0], nxs, a.ny, a.pitch / WZ, NX / nxs, p.box_rows)) return rc;
+    auto kern = xpass32_store_kernel;
+    if (int rc = ensure_smem(kern, (size_t)kStoreSmem)) return rc;
+    int occ = 0;
+    T21_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, (size_t)kStoreSmem));
+    if (occ < 1) { set_error("x pass (n-D store) does not fit on an SM"); return T21_EINVAL; }
+    long long g = (long long)occ * device_sm_count();
+    if (g > p.ntiles) g = p.ntiles;
+    kern<<<(int)g, THREADS, kStoreSmem, st>>>(map, p);
+    count_launch();
+    T21_CUDA_OK(cudaGetLastError());
+    a.grid_used = (int)g;
+    return 0;
 }
 
 // multipole moments fused into the X pass: fp32, nx = 1024, one field, a shell spec that carries its segment table

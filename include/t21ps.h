@@ -249,6 +249,12 @@ T21_API size_t t21_bin_cyl_workspace_bytes(int nperp, int npar);
  * (power_legendre.py:4-90) never materialise the fftshifted float64 cube the reference builds (:45-46). */
 T21_API int t21_ps_half(const t21_plan* plan, const void* x1, const void* x2_or_null, int subtract_mean, double scale,
                         void* out_half, int out_dtype, void* workspace, size_t workspace_bytes, void* stream);
+/* The same PENCIL-MAJOR, out_t[ny][nz/2+1][nx] -- the layout the warp-per-pencil X pass writes with full 128-byte runs (fp32
+ * transform, nx = 1024, one field; T21_EINVAL otherwise) -- and the pass that turns it into the complete fftshifted cube
+ * of power_spectrum_nd (power_spectrum.py:45-54), transposing 32 x 32 tiles through shared memory. */
+T21_API int t21_ps_half_t(const t21_plan* plan, const void* x1, int subtract_mean, double scale, void* out_t, int out_dtype,
+                          void* workspace, size_t workspace_bytes, void* stream);
+T21_API int t21_nd_assemble_t(const void* half_t, int dtype, int nx, int ny, int nz, void* out, void* stream);
 /* t21_bin_cyl on that half spectrum (rows of `row_pitch` elements): perp_tab / par_tab in FFT index order and over
  * the full axes; a mode whose Hermitian twin is not stored stands for both (weight 2).  sums_out only: the mode
  * counts of separable bins are a product of two table histograms and are formed on the host. */

@@ -187,6 +187,10 @@ def load():
     lib.t21_bin_cyl_workspace_bytes.restype = sz
     lib.t21_ps_half.argtypes = [vp, vp, vp, i32, dbl, vp, i32, vp, sz, vp]
     lib.t21_ps_half.restype = i32
+    lib.t21_ps_half_t.argtypes = [vp, vp, i32, dbl, vp, i32, vp, sz, vp]
+    lib.t21_ps_half_t.restype = i32
+    lib.t21_nd_assemble_t.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+    lib.t21_nd_assemble_t.restype = i32
     lib.t21_half_pitch.argtypes = [vp]
     lib.t21_half_pitch.restype = i32
     lib.t21_bin_cyl_half.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp, sz, vp]

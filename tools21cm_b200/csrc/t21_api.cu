@@ -514,6 +514,14 @@ int t21_ps_half(const t21_plan* p, const void* x1, const void* x2, int subtract_
     return ps_nd_impl(p, x1, x2, subtract_mean, scale, out_half, out_dtype, 1, workspace, workspace_bytes, stream);
 }
 
+// The scaled power of the computed half spectrum PENCIL-MAJOR, out_t[ny][nz/2+1][nx]: what the warp-per-pencil X pass can
+// write with full 128-byte runs (fp32 transform, nx = 1024, one field; T21_EINVAL otherwise).  t21_nd_assemble_t turns
+// it into the fftshifted cube of power_spectrum_nd (power_spectrum.py:45-54).
+int t21_ps_half_t(const t21_plan* p, const void* x1, int subtract_mean, double scale, void* out_t, int out_dtype,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+    return ps_nd_impl(p, x1, nullptr, subtract_mean, scale, out_t, out_dtype, -1, workspace, workspace_bytes, stream);
+}
+
 static int ps_nd_impl(const t21_plan* p, const void* x1, const void* x2, int subtract_mean, double scale, void* out,
                       int out_dtype, int half, void* workspace, size_t workspace_bytes, void* stream) {
     if (!out) { set_error("null output"); return T21_EINVAL; }
@@ -537,8 +545,11 @@ static int ps_nd_impl(const t21_plan* p, const void* x1, const void* x2, int sub
     a.tw = p->tw[0]; a.tw32 = p->tw32[0];
     a.offset[0] = offs[0]; a.offset[1] = offs[1];
     a.ntot = (double)p->n[0] * p->n[1] * p->n[2];
-    a.nd_out = out; a.nd_f64 = out_dtype == T21_F64; a.scale = scale; a.nd_half = half ? t21_half_pitch(p) : 0;
+    a.nd_out = out; a.nd_f64 = out_dtype == T21_F64; a.scale = scale; a.nd_half = half > 0 ? t21_half_pitch(p) : (half < 0 ? -1 : 0);
     a.max_grid = p->max_grid;
+    if (half < 0 && !(p->fast[0] && xpass32_store_applicable(p->dtype, a))) {
+        set_error("the pencil-major half spectrum needs the warp-per-pencil X pass (fp32, nx = 1024, one field)"); return T21_EINVAL;
+    }
     const int rc = !p->fast[0] ? launch_xpass_generic(p->dtype, a, st)
                                : (xpass32_store_applicable(p->dtype, a) ? launch_xpass32_store(a, st)
                                : (p->dtype == T21_F32 ? launch_xpass_f32_nd(a, st) : launch_xpass_f64_nd(a, st)));

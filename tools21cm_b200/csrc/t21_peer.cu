@@ -82,11 +82,70 @@ nd_assemble_kernel(const T* __restrict__ half, int nx, int nyl, int nz, int pitc
     }
 }
 
+// The same assembly from a PENCIL-MAJOR half spectrum, half_t[ny][nz/2+1][nx] (what the warp-per-pencil X pass writes
+// with full 128-byte runs): 32 x 32 (kz, kx) tiles go through shared memory, so both the reads (along kx) and the writes
+// (along kz, for the mode and, mirrored, for its Hermitian twin) are 128-byte runs.  One rank, all three axes shifted.
+template <typename T, int TZ, int TX>
+__global__ void __launch_bounds__(256)
+nd_assemble_t_kernel(const T* __restrict__ half_t, int nx, int ny, int nz, T* __restrict__ out) {
+    // tile[kz][kx]: TZ x TX modes of one ky.  Reads: TX consecutive kx per kz (runs of TX elements); writes: TZ
+    // consecutive kz per kx (runs of TZ elements, twice -- the mode and its twin).  TZ > TX: the writes are 2/3 of the traffic.
+    __shared__ T tile[TZ][TX + 1];
+    const int nzh = nz / 2 + 1, hx = nx / 2, hz = nz / 2;
+    const int ix0 = blockIdx.x * TX, iz0 = blockIdx.y * TZ, iy = blockIdx.z;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // (row bases once per warp and row, wrap-arounds by conditional subtraction: a run-time modulo per element made the
+    // first version of this kernel instruction bound)
+    for (int izl = warp; izl < TZ; izl += 8) {
+        const int iz = iz0 + izl;
+        if (iz >= nzh) break;
+        const T* src = half_t + ((size_t)iy * nzh + iz) * nx + ix0;
+        for (int ixl = lane; ixl < TX; ixl += 32)
+            if (ix0 + ixl < nx) tile[izl][ixl] = src[ixl];
+    }
+    __syncthreads();
+    int sy = iy + ny / 2; if (sy >= ny) sy -= ny;
+    int uy = (iy ? ny - iy : 0) + ny / 2; if (uy >= ny) uy -= ny;
+    for (int ixl = warp; ixl < TX; ixl += 8) {
+        const int ix = ix0 + ixl;
+        if (ix >= nx) break;
+        int sx = ix + hx; if (sx >= nx) sx -= nx;
+        int ux = (ix ? nx - ix : 0) + hx; if (ux >= nx) ux -= nx;
+        T* lo = out + ((size_t)sx * ny + sy) * nz;
+        T* mi = out + ((size_t)ux * ny + uy) * nz;
+        for (int izl = lane; izl < TZ; izl += 32) {
+            const int iz = iz0 + izl;
+            if (iz >= nzh) break;
+            const T val = tile[izl][ixl];
+            int sz = iz + hz; if (sz >= nz) sz -= nz;
+            lo[sz] = val;
+            if (iz != 0 && 2 * iz != nz) mi[hz - iz] = val;       // the twin (-kx, -ky, -kz): kz index nz - iz, shifted
+        }
+    }
+}
+
 }  // namespace t21
 
 using namespace t21;
 
 extern "C" {
+
+int t21_nd_assemble_t(const void* half_t, int dtype, int nx, int ny, int nz, void* out, void* stream) {
+    if (!half_t || !out || nx < 1 || ny < 1 || nz < 1 || ny > 65535 || (dtype != T21_F32 && dtype != T21_F64)) {
+        set_error("bad argument to t21_nd_assemble_t"); return T21_EINVAL;
+    }
+    const int nzh = nz / 2 + 1;
+    if (dtype == T21_F32) {
+        const dim3 grid((nx + 63) / 64, (nzh + 127) / 128, ny);
+        nd_assemble_t_kernel<float, 128, 64><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)half_t, nx, ny, nz, (float*)out);
+    } else {
+        const dim3 grid((nx + 63) / 64, (nzh + 63) / 64, ny);
+        nd_assemble_t_kernel<double, 64, 64><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)half_t, nx, ny, nz, (double*)out);
+    }
+    count_launch();
+    T21_CUDA_OK(cudaGetLastError());
+    return T21_OK;
+}
 
 size_t t21_peer_comm_bytes(int nranks, int slot_bytes) {
     if (nranks < 1 || slot_bytes < 4) return 0;

@@ -521,7 +521,7 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& 
 #pragma unroll
         for (int t = 0; t < NTAB; ++t) {
             ent[t] = kSegSentinel;
-            if (NT > 0 && NT != 6 && lane < p.seg_stride && iz < p.nzh)
+            if (NT > 0 && NT < 6 && lane < p.seg_stride && iz < p.nzh)
                 ent[t] = ldg(p.seg + ((size_t)t * p.seg_pencils + (size_t)iy * p.nzh + iz) * p.seg_stride + lane);
         }
         mbar_wait(bar, parity);
@@ -555,7 +555,28 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& 
 #pragma unroll
         for (int k = 1; k < 32; ++k) v[k] = cmul(v[k], ldg(p.tw + (k - 1) * 32 + lane));
         DFT<32, float>::run(v);                            // v[k] = X[lane + 32 k]
-        if constexpr (NT == 6) {
+        if constexpr (NT == 7) {
+            // n-D outputs, pencil-major: out_t[ky][kz][kx] -- a warp writes its pencil as 32 runs of 128 bytes; the pass
+            // that assembles the fftshifted cube transposes tiles of it through shared memory (t21_nd_assemble_t).
+            // (Storing [kx][ky][kz] from here writes 32-byte pieces 2 MB apart: 2.97 ms per 1024^3 cube against 1.1.)
+            if (iz < p.nzh) {
+                const size_t base = ((size_t)(iy - p.iy0) * p.nzh + iz) * NX + lane;
+                double dc = 0.0;
+                const bool is_dc = iy == 0 && iz == 0 && lane == 0;
+                if (is_dc) {
+                    const double c0 = p.offset ? (double)ldg(p.offset) : 0.0;
+                    const double ra = (double)v[0].x + c0 * p.ntot;
+                    dc = ra * ra + (double)v[0].y * (double)v[0].y;
+                }
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    double val = (double)(v[k].x * v[k].x + v[k].y * v[k].y) * p.scale;
+                    if (k == 0 && is_dc) val = dc * p.scale;
+                    if (p.nd_f64) ((double*)p.nd_out)[base + 32 * k] = val;
+                    else ((float*)p.nd_out)[base + 32 * k] = (float)val;
+                }
+            }
+        } else if constexpr (NT == 6) {
             // n-D outputs: powers go to a [kx][8 + 1] tile in shared memory (pitch 9: a warp's 32 kx fall on 32 banks),
             // then every thread writes whole 32-byte runs -- the 8 columns of this piece at one kx -- of the output
             float* st = reinterpret_cast<float*>(smem_raw + STAGE_OFF);
@@ -681,6 +702,7 @@ struct NoHist32 {
     __device__ void add(int, double, unsigned) {}
 };
 constexpr int kStoreSmem = STAGE_OFF + NX * 9 * 4;
+template <int NT>
 __global__ void __launch_bounds__(THREADS, 2)
 xpass32_store_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ Params p) {
 #if T21_DEVICE_CODE
@@ -691,7 +713,7 @@ xpass32_store_kernel(const __grid_constant__ CUtensorMap map, const __grid_const
     }
     __syncthreads();
     NoHist32 hist;
-    run_tiles<6>(&map, p, smem_raw, hist, 0);
+    run_tiles<NT>(&map, p, smem_raw, hist, 0);
 #endif
 }
 
@@ -784,9 +806,13 @@ int launch_xpass32_bin(XArgs& a, cudaStream_t st) {
 // the scaled power of the computed half spectrum (t21_ps_half, t21_slab_stage2_nd): fp32 transform, nx = 1024, one field
 bool xpass32_store_applicable(int dtype, const XArgs& a) {
     static const bool on = [] { const char* e = getenv("T21_PENCIL32_ND"); return !(e && e[0] == '0'); }();
-    return on && dtype == T21_F32 && a.nx == x32::NX && a.nf == 1 && a.nd_out != nullptr && a.nd_half > 0 && a.nd_half % x32::WZ == 0 &&
-           a.tw32 != nullptr && a.pitch % x32::WZ == 0;
+    // (the [kx][ky][kz] form writes 32-byte pieces 2 MB apart whoever does it: 2.97 ms here, 2.93 ms on the CTA-per-tile
+    // kernel, which therefore keeps it unless T21_PENCIL32_HALF=1; the pencil-major form is this kernel's own)
+    static const bool half_too = [] { const char* e = getenv("T21_PENCIL32_HALF"); return e && e[0] == '1'; }();
+    return on && dtype == T21_F32 && a.nx == x32::NX && a.nf == 1 && a.nd_out != nullptr && a.tw32 != nullptr && a.pitch % x32::WZ == 0 &&
+           (a.nd_half == -1 || (half_too && a.nd_half > 0 && a.nd_half % x32::WZ == 0));
 }
+// nd_half > 0: out_half[kx][ky][nd_half]; nd_half == -1: pencil-major out_t[ky][nz/2+1][kx]
 int launch_xpass32_store(XArgs& a, cudaStream_t st) {
     using namespace x32;
     Params p;
@@ -803,7 +829,7 @@ int launch_xpass32_store(XArgs& a, cudaStream_t st) {
     p.nd_out = a.nd_out; p.nd_f64 = a.nd_f64; p.nd_pitch = a.nd_half; p.scale = a.scale;
     CUtensorMap map;
     if (int rc = make_wmap_f32(&map, a.w[0], nxs, a.ny, a.pitch / WZ, NX / nxs, p.box_rows)) return rc;
-    auto kern = xpass32_store_kernel;
+    auto kern = a.nd_half == -1 ? xpass32_store_kernel<7> : xpass32_store_kernel<6>;
     if (int rc = ensure_smem(kern, (size_t)kStoreSmem)) return rc;
     int occ = 0;
     T21_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, (size_t)kStoreSmem));

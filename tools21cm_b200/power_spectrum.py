@@ -382,6 +382,18 @@ def _fused_nd(fields, scale, out_dtype):
         out = torch.empty(tuple(x.shape), dtype=out_dtype, device=x.device)
         x2 = fields[1].data_ptr() if len(fields) == 2 else None
         ocode = T21_F32 if out_dtype == torch.float32 else T21_F64
+        if code == T21_F32 and len(fields) == 1 and x.shape[0] == 1024 and os.environ.get("T21_PENCIL32_ND", "1") != "0" and \
+                all(8 <= n <= 4096 and (n & (n - 1)) == 0 for n in x.shape[1:]):
+            # warp-per-pencil X pass: the half spectrum is written pencil-major (128-byte runs), the assembly pass
+            # transposes 32 x 32 tiles of it into the fftshifted cube (both sides 128-byte runs)
+            half = torch.empty((x.shape[1], x.shape[2] // 2 + 1, x.shape[0]), dtype=out_dtype, device=x.device)
+            rc = lib.t21_ps_half_t(plan, x.data_ptr(), 1, float(scale), half.data_ptr(), ocode, ws.data_ptr(), ws.numel(),
+                                   _stream_ptr(torch, x.device.index))
+            _lib.check(rc, "t21_ps_half_t")
+            rc = lib.t21_nd_assemble_t(half.data_ptr(), ocode, x.shape[0], x.shape[1], x.shape[2], out.data_ptr(),
+                                       _stream_ptr(torch, x.device.index))
+            _lib.check(rc, "t21_nd_assemble_t")
+            return out
         if x.shape[2] >= 64:
             # The X pass stores the computed half spectrum (sector-aligned 32-byte runs), then one pass writes the
             # fftshifted array with 128-byte runs both for the kz >= 0 half and for the mirrored kz < 0 half (the

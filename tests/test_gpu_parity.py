@@ -184,6 +184,38 @@ def test_multipoles_against_oracle(t2c, shape, los):
         np.testing.assert_allclose(got["P4"], want["P4"], rtol=1e-6, atol=atol, equal_nan=True)
 
 
+@pytest.mark.parametrize("shape", [(512, 16, 32), (512, 32, 16), (512, 8, 64)])
+def test_warp_per_pencil_x_pass_nx512(t2c, shape):
+    """nx = 512 fp32 takes its own warp-per-pencil X pass (t21_xpass16.cu: radix 16 x 2 x 16, no CTA barrier), for one field
+    and for two (cross spectra keep the first field's results in registers): shells, |mu| bins for every line of sight, the
+    excluded k_perp = 0 line, explicit edges with a zero edge and an empty bin, against the oracle."""
+    from oracle import ps_oracle
+    rng = np.random.default_rng(sum(shape))
+    x = (rng.standard_normal(shape) + 3.0).astype(np.float32)
+    y = (0.5 * x + rng.standard_normal(shape)).astype(np.float32)
+    box = [300.0, 40.0, 60.0]
+    for kb in (9, 31, np.array([0.0, 0.05, 0.3, 0.31, 0.31, 2.0, 9.0])):
+        ps, ks, nm = t2c.power_spectrum_1d(x, kbins=kb, box_dims=box, return_n_modes=True)
+        ps_o, ks_o, nm_o = ps_oracle.power_spectrum_1d(x, kbins=kb, box_dims=box, return_n_modes=True)
+        assert np.array_equal(nm, nm_o) and np.array_equal(ks, ks_o)
+        np.testing.assert_allclose(ps, ps_o, rtol=1e-5, equal_nan=True)
+        xs, _, xn = t2c.cross_power_spectrum_1d(x, y, kbins=kb, box_dims=box, return_n_modes=True)
+        xs_o, _, xn_o = ps_oracle.cross_power_spectrum_1d(x, y, kbins=kb, box_dims=box, return_n_modes=True)
+        assert np.array_equal(xn, xn_o)
+        np.testing.assert_allclose(xs, xs_o, rtol=1e-5, atol=1e-5 * np.nanmax(np.abs(ps_o)), equal_nan=True)
+    for los in (0, 1, 2):
+        for excl in (True, False):
+            kw = dict(los_axis=los, mubins=5, kbins=6, box_dims=box, return_n_modes=True, exclude_zero_modes=excl)
+            pm, _, _, nmu = t2c.power_spectrum_mu(x, **kw)
+            pm_o, _, _, nmu_o = ps_oracle.power_spectrum_mu(x, **kw)
+            assert np.array_equal(nmu, nmu_o)
+            np.testing.assert_allclose(pm, pm_o, rtol=1e-5, equal_nan=True)
+        cm, _, _, cn = t2c.cross_power_spectrum_mu(x, y, los_axis=los, mubins=4, kbins=5, box_dims=box, return_n_modes=True)
+        cm_o, _, _, cn_o = ps_oracle.cross_power_spectrum_mu(x, y, los_axis=los, mubins=4, kbins=5, box_dims=box, return_n_modes=True)
+        assert np.array_equal(cn, cn_o)
+        np.testing.assert_allclose(cm, cm_o, rtol=1e-5, atol=1e-5 * np.nanmax(np.abs(pm_o)), equal_nan=True)
+
+
 @pytest.mark.parametrize("shape", [(1024, 16, 32), (1024, 32, 16)])
 def test_warp_per_pencil_x_pass_overflow_pencils(t2c, shape, monkeypatch):
     """Fine binnings (the reference's default is kbins = 100): pencils next to the kx axis cross more than 32 ranges, are

@@ -1,6 +1,7 @@
 // C ABI of libt21ps.so (declared in include/t21ps.h): plans, workspace layout, and the
 // three entry points that chain the passes on the caller's stream.
 #include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -140,6 +141,16 @@ static int build_tables(t21_plan* p) {
         for (int d = 0; d < 2; ++d)
             if (p->n[d] == 1024)
                 if (int rc = upload<T>(build_stage_twiddles<T>(1024, 32), &p->tw32[d])) return rc;
+    if (sizeof(T) == 4 && use_pencil32() && p->n[0] == 512) {
+        // the nx = 512 warp-per-pencil kernel: w512^(r q), r = 0..15 (rows), q = 0..31
+        std::vector<cx<T>> tw(16 * 32);
+        for (int r = 0; r < 16; ++r)
+            for (int q = 0; q < 32; ++q) {
+                const double ang = -2.0 * 3.14159265358979323846264338327950288 * (double)(r * q) / 512.0;
+                tw[r * 32 + q] = cx<T>{(T)cos(ang), (T)sin(ang)};
+            }
+        if (int rc = upload<T>(tw, &p->tw32[0])) return rc;
+    }
     if (p->fast[2]) {
         if (int rc = upload<T>(build_roots<T>(p->n[2], p->n[2] / 2 + 1), &p->twr)) return rc;
     } else {

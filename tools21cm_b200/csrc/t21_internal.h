@@ -50,8 +50,13 @@ int launch_xpass32_store(XArgs& a, cudaStream_t st);
 bool xpass32_moments_applicable(int dtype, const XArgs& a);
 int launch_xpass32_moments(XArgs& a, int los_axis, cudaStream_t st);   // part_sum [grid][nk][5], part_cnt [grid][nk]
 
+// t21_xpass16.cu: warp-per-pencil X pass for nx = 512 (fp32, one or two fields, a spec with one segment table)
+bool xpass16_applicable(int dtype, const XArgs& a);
+int launch_xpass16_bin(XArgs& a, cudaStream_t st);
+
 inline int launch_xpass_bin(int dtype, XArgs& a, cudaStream_t st) {
     if (xpass32_applicable(dtype, a)) return launch_xpass32_bin(a, st);
+    if (xpass16_applicable(dtype, a)) return launch_xpass16_bin(a, st);
     const int mu = (a.bins && a.bins->nmu > 0) ? (a.bins->absolute_mus ? 1 : 2) : 0;
     if (dtype == T21_F32)
         return mu == 0 ? launch_xpass_f32_bin_mu0(a, st) : (mu == 1 ? launch_xpass_f32_bin_mu1(a, st) : launch_xpass_f32_bin_mu2(a, st));

@@ -65,6 +65,7 @@ __device__ __forceinline__ void named_arrive(int id, int nthreads) { asm volatil
 // Tensor map of a chunk-major half spectrum, complex64: element (slab s, piece c, x_lo, y, l) of
 // [nslab][nch][nxs][nya][8 complex] as a 5-D fp32 tensor (16 floats, nya, nxs, nch, nslab); the box is
 // `box_rows` x planes of one (y, piece): box_rows * 64 bytes.  Returns 0 or a T21_E* code (t21_api.cu).
-int make_wmap_f32(CUtensorMap* out, const void* w, int nxs, int nya, int nch, int nslab, int box_rows);
+// box_floats: 16 (the whole 64-byte piece) or 4 (one pair of columns: the nx = 512 kernel lands a tile as four column pairs).
+int make_wmap_f32(CUtensorMap* out, const void* w, int nxs, int nya, int nch, int nslab, int box_rows, int box_floats = 16);
 
 }  // namespace t21

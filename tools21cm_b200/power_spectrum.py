@@ -341,8 +341,9 @@ def _fused_binned(fields, spec_key, spec_builder):
         nb = spec.nbins
         need = lib.t21_workspace_bytes(plan, len(fields), nb)
         ws = dev.workspace(need)
-        sums = torch.empty(nb, dtype=torch.float64, device=x.device)
-        counts = torch.empty(nb, dtype=torch.int64, device=x.device)
+        # sums (float64) and counts (int64) share one buffer: one device->host read per call, no glue kernels
+        both = torch.empty(2 * nb, dtype=torch.float64, device=x.device)
+        sums, counts = both[:nb], both[nb:].view(torch.int64)
         if getattr(x, "is_host", False):
             # the cube is still on the host: copy it in groups of x planes while Z and Y run on the ones that have landed
             xdev = torch.empty(x.shape, dtype=x.dtype, device=x.device)
@@ -356,11 +357,8 @@ def _fused_binned(fields, spec_key, spec_builder):
                                    sums.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(),
                                    _stream_ptr(torch, x.device.index))
             _lib.check(rc, "t21_ps_binned")
-        out = torch.empty(2 * nb, dtype=torch.float64, device=x.device)
-        out[:nb] = sums
-        out[nb:] = counts.to(torch.float64)
-        host = out.cpu().numpy()
-    return spec, host[:nb].copy(), host[nb:].copy()
+        host = both.cpu().numpy()
+    return spec, host[:nb].copy(), host[nb:].view(np.int64).astype(np.float64)
 
 
 def _fused_nd(fields, scale, out_dtype):

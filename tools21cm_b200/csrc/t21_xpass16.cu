@@ -43,6 +43,11 @@ struct Params {
     int seg_stride;
 };
 
+// tile buffers: one field keeps TWO tiles in shared memory (the next one is requested as soon as every warp has read the
+// one before the current -- a whole tile's work ahead of its use); two fields have room for one (128 KB would leave a
+// single CTA per SM), requested when every warp has read the current one.
+template <int NF> struct Bufs { static constexpr int N = NF == 1 ? 2 : 1; };
+
 #if T21_DEVICE_CODE
 
 // close-range walk on 16 powers per lane: steps k = 0..7 hold |kx| = 32k + lane (pw[k]) and 32k + 32 - lane (pw[15 - k])
@@ -145,52 +150,59 @@ __device__ __forceinline__ void pencil_fft(cx<float>* a, int lane, cx<float>* __
 template <int NF, class Hist>
 __device__ __forceinline__ void run_tiles(const CUtensorMap* map0, const CUtensorMap* map1, const Params& p, unsigned char* smem_raw,
                                           Hist& hist) {
-    constexpr int BAR_OFF = NF * TILE_BYTES;
+    constexpr int NB = Bufs<NF>::N;
+    constexpr int BAR_OFF = NB * NF * TILE_BYTES;
     constexpr int XCH_OFF = BAR_OFF + 128;
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + BAR_OFF);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + BAR_OFF);     // bar[b]: tile buffer b is full
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     cx<float>* xb = reinterpret_cast<cx<float>*>(smem_raw + XCH_OFF + warp * XCH_BYTES);
 
-    auto issue = [&](long long tile) {
+    auto issue = [&](long long tile, int b) {
         const unsigned chunk = (unsigned)tile / (unsigned)p.ny;
         const int iy_loc = (int)((unsigned)tile - chunk * (unsigned)p.ny);
-        mbar_expect_tx(bar, NF * TILE_BYTES);
+        mbar_expect_tx(bar + b, NF * TILE_BYTES);
 #pragma unroll
         for (int f = 0; f < NF; ++f)
             for (int pr = 0; pr < 4; ++pr)
                 for (int x = 0; x < NX; x += p.box_rows)
-                    tma_load_5d(smem_raw + f * TILE_BYTES + pr * SUB_BYTES + (size_t)x * 16, f == 0 ? map0 : map1, bar, 4 * pr, iy_loc,
-                                x & ((1 << p.xs_log2) - 1), (int)chunk, x >> p.xs_log2);
+                    tma_load_5d(smem_raw + (b * NF + f) * TILE_BYTES + pr * SUB_BYTES + (size_t)x * 16, f == 0 ? map0 : map1, bar + b,
+                                4 * pr, iy_loc, x & ((1 << p.xs_log2) - 1), (int)chunk, x >> p.xs_log2);
     };
     constexpr int kBatch = 8;
     auto tile_at = [&](long long i) { return ((i / kBatch) * gridDim.x + blockIdx.x) * kBatch + (i % kBatch); };
     long long it = 0;
     long long tile = tile_at(0);
-    if (tid == 0 && tile < p.ntiles) issue(tile);
-    unsigned parity = 0;
+    if (tid == 0) {
+        if (tile < p.ntiles) issue(tile, 0);
+        if (NB == 2 && tile_at(1) < p.ntiles) issue(tile_at(1), 1);
+    }
+    unsigned parity = 0;                                   // bit b: phase of bar[b] to wait for
     for (; tile < p.ntiles; tile = tile_at(++it)) {
+        const int b = NB == 2 ? (int)(it & 1) : 0;
         const unsigned chunk = (unsigned)tile / (unsigned)p.ny;
         const int iy = (int)((unsigned)tile - chunk * (unsigned)p.ny) + p.iy0;
         const int iz = (int)chunk * WZ + warp;
         unsigned ent = kSegSentinel;
         if (lane < p.seg_stride && iz < p.nzh) ent = ldg(p.seg + ((size_t)iy * p.nzh + iz) * p.seg_stride + lane);
         cx<float> a[NF][NV];
-        mbar_wait(bar, parity);
-        parity ^= 1u;
+        mbar_wait(bar + b, (parity >> b) & 1u);
+        parity ^= 1u << b;
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
-            const cx<float>* sub = reinterpret_cast<const cx<float>*>(smem_raw + f * TILE_BYTES + (warp >> 1) * SUB_BYTES) + (warp & 1);
+            const cx<float>* sub = reinterpret_cast<const cx<float>*>(smem_raw + (b * NF + f) * TILE_BYTES + (warp >> 1) * SUB_BYTES) + (warp & 1);
 #pragma unroll
             for (int k = 0; k < NV; ++k) a[f][k] = sub[(lane + 32 * k) * 2];
         }
-        // the tile may be overwritten once every warp has its rows: the issuing warp waits for that, the others go on
+        // buffer b may be overwritten once every warp has its rows: the issuing warp waits for that, the others go on
+        // (with two buffers a warp can be one tile ahead of the slowest one -- the tile after that is only requested once
+        // everybody has read this one -- so consecutive tiles use different named barriers)
         fence_proxy_async();
         if (warp == 0) {
-            named_sync(1, THREADS);
-            const long long next = tile_at(it + 1);
-            if (lane == 0 && next < p.ntiles) issue(next);
+            named_sync(1 + b, THREADS);
+            const long long next = tile_at(it + NB);
+            if (lane == 0 && next < p.ntiles) issue(next, b);
         } else {
-            named_arrive(1, THREADS);
+            named_arrive(1 + b, THREADS);
         }
         if (iz >= p.nzh) continue;
         float pw[NV];
@@ -228,11 +240,12 @@ xpass16_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
                double* __restrict__ part_sum, unsigned* __restrict__ part_cnt) {
 #if T21_DEVICE_CODE
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    constexpr int BAR_OFF = NF * TILE_BYTES;
+    constexpr int NB = Bufs<NF>::N;
+    constexpr int BAR_OFF = NB * NF * TILE_BYTES;
     constexpr int HIST_OFF = BAR_OFF + 128 + (THREADS / 32) * XCH_BYTES;
     const int tid = threadIdx.x;
     if (tid == 0) {
-        mbar_init(smem_raw + BAR_OFF, 1);
+        for (int b = 0; b < NB; ++b) mbar_init(smem_raw + BAR_OFF + 8 * b, 1);
         mbar_init_fence();
     }
     constexpr int NW = THREADS / 32;
@@ -272,7 +285,7 @@ static int launch(XArgs& a, cudaStream_t st) {
     CUtensorMap map0, map1;
     if (int rc = make_wmap_f32(&map0, a.w[0], nxs, a.ny, a.pitch / WZ, NX / nxs, p.box_rows, 4)) return rc;
     if (int rc = make_wmap_f32(&map1, NF == 2 ? a.w[1] : a.w[0], nxs, a.ny, a.pitch / WZ, NX / nxs, p.box_rows, 4)) return rc;
-    const size_t smem = (size_t)NF * TILE_BYTES + 128 + (size_t)(THREADS / 32) * XCH_BYTES + (size_t)(THREADS / 32) * a.nbins * 12;
+    const size_t smem = (size_t)Bufs<NF>::N * NF * TILE_BYTES + 128 + (size_t)(THREADS / 32) * XCH_BYTES + (size_t)(THREADS / 32) * a.nbins * 12;
     auto kern = xpass16_kernel<NF>;
     if (int rc = ensure_smem(kern, smem)) return rc;
     int occ = 0;

@@ -3,8 +3,8 @@
 set -u
 N=${1:-8}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_distributed.py -m gpu -q -rA > gpurun_out/r02_pytest_gpu_${N}gpu_distributed.log 2>&1; echo "pytest rc=$?"; tail -18 gpurun_out/r02_pytest_gpu_${N}gpu_distributed.log
-timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r02_bench_${N}gpu.json 2> gpurun_out/r02_bench_${N}gpu.err; echo "bench rc=$?"; tail -12 gpurun_out/r02_bench_${N}gpu.err; ls -la /tmp/t21_nccl* 2>/dev/null | head -3
+timeout 300 python -m pytest tests/test_gpu_distributed.py -m gpu -q -rA > gpurun_out/r02_pytest_gpu_${N}gpu_distributed.log 2>&1; echo "pytest rc=$?"; tail -18 gpurun_out/r02_pytest_gpu_${N}gpu_distributed.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r02_bench_${N}gpu.json 2> gpurun_out/r02_bench_${N}gpu.err; echo "bench rc=$?"; tail -12 gpurun_out/r02_bench_${N}gpu.err; ls -la /tmp/t21_nccl* 2>/dev/null | head -3
 python - <<PY
 import json
 try:

@@ -3,7 +3,7 @@
 # list of the bench command and one full capture of each pass.  Everything lands in gpurun_out/ (copied to profiles/).
 set -u
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -rs --durations=6 > gpurun_out/r02_pytest_gpu_1gpu.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/r02_pytest_gpu_1gpu.log
+timeout 600 python -m pytest tests -m gpu -q -rs --durations=6 > gpurun_out/r02_pytest_gpu_1gpu.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/r02_pytest_gpu_1gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
 timeout 900 python bench.py > gpurun_out/r02_bench_1gpu.json 2> gpurun_out/r02_bench_1gpu.err; echo "bench rc=$?"
 timeout 900 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/r02_bench_1gpu_reference_arm.json 2> gpurun_out/r02_bench_ref.err; echo "ref rc=$?"
@@ -31,3 +31,4 @@ print(open("gpurun_out/r02_bench_1gpu_reference_arm.json").read()[:600])
 print(open("gpurun_out/r02_variants_1gpu.json").read())
 PY
 bash tools/r2_np2.sh
+bash tools/r2_512.sh

@@ -324,10 +324,10 @@ __device__ __noinline__ void epilogue_classify(const Params& p, float v0x, float
     wbc_flush(c, hist);
 }
 
-template <int NT, class Hist>
+template <int NT, bool OVF, class Hist>
 __device__ __forceinline__ void epilogue_segments(const Params& p, cx<float>* v, int lane, int iy, int iz, const unsigned* ent,
                                                   float* __restrict__ strip, Hist& hist) {
-    if (p.seg_overflow) {                                  // (warp-uniform: entry 0 of table 0, or of any table for signed mu)
+    if constexpr (OVF) {                                  // (warp-uniform: entry 0 of table 0, or of any table for signed mu)
         bool ovf = false;
 #pragma unroll
         for (int t = 0; t < NT; ++t) ovf = ovf || ent[t] == kSegOverflow;
@@ -482,7 +482,7 @@ __device__ __forceinline__ void epilogue_multipoles(const Params& p, cx<float>* 
     close((unsigned)(NX / 2 + 1));
 }
 
-template <int NT, class Hist>
+template <int NT, bool OVF, class Hist>
 __device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& p, unsigned char* smem_raw, Hist& hist, int nbins) {
     cx<float>* buf = reinterpret_cast<cx<float>*>(smem_raw);
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + BAR_OFF);
@@ -622,7 +622,7 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& 
         } else if (iz < p.nzh) {
             float* stage = reinterpret_cast<float*>(smem_raw + STAGE_OFF) + warp * 1024;
             if constexpr (NT == 5) epilogue_multipoles(p, v, lane, iy, iz, ent[0], stage, hist);
-            else if constexpr (NT > 0) epilogue_segments<NT>(p, v, lane, iy, iz, ent, stage, hist);
+            else if constexpr (NT > 0) epilogue_segments<NT, OVF>(p, v, lane, iy, iz, ent, stage, hist);
             else epilogue_shells(p, v, lane, iy, iz, stage, wbc, hist);
         }
     }
@@ -634,7 +634,8 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& 
 // The histogram (at most 31 bins) lives in shared memory, one copy per warp: only lane 0 of the owning warp writes
 // it, in program order; warps are summed in order here and CTAs in order by reduce_partials_kernel, so the result
 // is bit-reproducible run to run.
-template <int NT>
+// OVF: the table carries overflow marks (pencils classified mode by mode); the common kernels are compiled without that path
+template <int NT, bool OVF>
 __global__ void __launch_bounds__(THREADS, 2)
 xpass32_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ Params p, int nbins,
                double* __restrict__ part_sum, unsigned* __restrict__ part_cnt) {
@@ -651,7 +652,7 @@ xpass32_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ 
     for (int b = tid; b < NW * nbins; b += THREADS) { hs[b] = 0.0; hc[b] = 0u; }
     __syncthreads();
     WarpPrivHist hist{hs + (size_t)(tid >> 5) * nbins, hc + (size_t)(tid >> 5) * nbins};
-    run_tiles<NT>(&map, p, smem_raw, hist, nbins);
+    run_tiles<NT, OVF>(&map, p, smem_raw, hist, nbins);
     __syncthreads();
     for (int b = tid; b < nbins; b += THREADS) {
         double s = 0.0;
@@ -682,7 +683,7 @@ xpass32_moments_kernel(const __grid_constant__ CUtensorMap map, const __grid_con
     for (int b = tid; b < NW * nk; b += THREADS) hc[b] = 0u;
     __syncthreads();
     MomentHist hist{hs + (size_t)(tid >> 5) * ns, hc + (size_t)(tid >> 5) * nk};
-    run_tiles<5>(&map, p, smem_raw, hist, ns);
+    run_tiles<5, false>(&map, p, smem_raw, hist, ns);
     __syncthreads();
     for (int b = tid; b < ns; b += THREADS) {
         double s = 0.0;
@@ -713,7 +714,7 @@ xpass32_store_kernel(const __grid_constant__ CUtensorMap map, const __grid_const
     }
     __syncthreads();
     NoHist32 hist;
-    run_tiles<NT>(&map, p, smem_raw, hist, 0);
+    run_tiles<NT, false>(&map, p, smem_raw, hist, 0);
 #endif
 }
 
@@ -767,7 +768,10 @@ static int launch(XArgs& a, cudaStream_t st, int moments_los = -1) {
     if (int rc = make_wmap_f32(&map, a.w[0], nxs, a.ny, a.pitch / WZ, NX / nxs, p.box_rows)) return rc;
 
     const size_t smem = HIST_OFF + (size_t)(THREADS / 32) * a.nbins * 12;
-    auto kern = nt == 0 ? xpass32_kernel<0> : (nt == 1 ? xpass32_kernel<1> : xpass32_kernel<4>);
+    const bool ovf = nt != 0 && p.seg_overflow != 0;
+    auto kern = nt == 0 ? xpass32_kernel<0, false>
+              : (nt == 1 ? (ovf ? xpass32_kernel<1, true> : xpass32_kernel<1, false>)
+                         : (ovf ? xpass32_kernel<4, true> : xpass32_kernel<4, false>));
     if (int rc = ensure_smem(kern, smem)) return rc;
     int occ = 0;
     T21_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));

@@ -216,7 +216,7 @@ def test_warp_per_pencil_x_pass_nx512(t2c, shape):
         np.testing.assert_allclose(cm, cm_o, rtol=1e-5, atol=1e-5 * np.nanmax(np.abs(pm_o)), equal_nan=True)
 
 
-@pytest.mark.parametrize("shape", [(1024, 16, 32), (1024, 32, 16)])
+@pytest.mark.parametrize("shape", [(1024, 16, 32), (1024, 32, 16), (512, 16, 32)])
 def test_warp_per_pencil_x_pass_overflow_pencils(t2c, shape, monkeypatch):
     """Fine binnings (the reference's default is kbins = 100): pencils next to the kx axis cross more than 32 ranges, are
     marked in the segment table and classified mode by mode by the same kernel.  In these thin slabs most pencils are
@@ -229,6 +229,10 @@ def test_warp_per_pencil_x_pass_overflow_pencils(t2c, shape, monkeypatch):
     ps_o, ks_o, nm_o = ps_oracle.power_spectrum_1d(x, kbins=100, box_dims=box, return_n_modes=True)
     assert np.array_equal(nm, nm_o) and np.array_equal(ks, ks_o)
     np.testing.assert_allclose(ps, ps_o, rtol=1e-5, equal_nan=True)
+    xs, _, xn = t2c.cross_power_spectrum_1d(x, x[::-1].copy(), kbins=100, box_dims=box, return_n_modes=True)
+    xs_o, _, xn_o = ps_oracle.cross_power_spectrum_1d(x, x[::-1].copy(), kbins=100, box_dims=box, return_n_modes=True)
+    assert np.array_equal(xn, xn_o)
+    np.testing.assert_allclose(xs, xs_o, rtol=1e-5, atol=1e-5 * np.nanmax(np.abs(ps_o)), equal_nan=True)
     for absmu in (True, False):
         kw = dict(los_axis=0, mubins=3, kbins=40, box_dims=box, return_n_modes=True, absolute_mus=absmu)
         pm, _, _, nmu = t2c.power_spectrum_mu(x, **kw)

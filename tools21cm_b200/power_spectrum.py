@@ -56,6 +56,7 @@ class _Device:
         self.specs = OrderedDict()
         self.cyls = OrderedDict()
         self.cylsegs = OrderedDict()
+        self._seg_lru = []
         self.ws = {}
         self._scratch = {}
 
@@ -169,6 +170,14 @@ class _Device:
         cspec.seg_tab = table.data_ptr()
         cspec.seg_stride = stride
         cspec.seg_ntab = ntab
+        # tables are tens of MB (hundreds at 2048^3): only the most recently built few stay attached; an older spec that
+        # comes back rebuilds its table
+        self._seg_lru.append(hit)
+        while len(self._seg_lru) > 8:
+            o_spec, o_cspec, o_owners = self._seg_lru.pop(0)
+            o_cspec.seg_tab, o_cspec.seg_stride, o_cspec.seg_ntab, o_cspec.seg_overflow = None, 0, 0, 0
+            del o_owners[1:]
+            o_spec._segments_tried = False
 
 
     def cyl_segments(self, key, cyl, perp, par, nu_axis):

@@ -21,6 +21,10 @@
 #include "t21_launch.cuh"
 #include "t21_tma.cuh"
 
+#ifndef T21_X32_BATCH
+#define T21_X32_BATCH 8      // tiles per deal; measured at 1024^3: X 1.074 / 1.072 / 1.090 ms for 4 / 8 / 16
+#endif
+
 namespace t21 {
 
 namespace x32 {
@@ -504,7 +508,7 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap* map, const Params& 
     // warp then cross nearly the same bins, so the warp's cached bins survive from one pencil to the next, while the
     // expensive tiles (pencils near the kx axis cross many bin edges) are spread over all CTAs.  (One contiguous
     // range per CTA left the SMs idle 41 % of the time: profiles/r02_x32_imbalance.txt.)
-    constexpr int kBatch = 8;
+    constexpr int kBatch = T21_X32_BATCH;
     auto tile_at = [&](long long i) { return ((i / kBatch) * gridDim.x + blockIdx.x) * kBatch + (i % kBatch); };
     long long it = 0;
     long long tile = tile_at(0);

@@ -71,7 +71,9 @@ struct ZPass {
     static constexpr int ROWPITCH = (M + (M >> 4) + 2 * kRun) / (2 * kRun) * (2 * kRun) + kRun;
     static constexpr int SMEM_ELEMS = ROWS * ROWPITCH;
     static constexpr int SMEM_BYTES = SMEM_ELEMS * (int)sizeof(cx<T>);
-    static constexpr int MIN_CTAS = (THREADS <= 256 && sizeof(T) == 4) ? 4 : 1;   // 64 registers: what it needs anyway
+    // fp32: 64 registers is what it needs anyway.  fp64: uncapped it takes 146 registers -- ONE 256-thread CTA per SM;
+    // capped at 128 two fit (1024^3 fp64 Z pass: see DESIGN.md section 4)
+    static constexpr int MIN_CTAS = THREADS <= 256 ? (sizeof(T) == 4 ? 4 : 2) : 1;
     // When the last stage is a radix-2 one, it is fused with the untangle phase: outputs k, M-k, M/2-k, M/2+k
     // need exactly the four stage inputs a[k], a[k+M/2], a[M/2-k], a[M-k], so one thread reads those four values
     // and writes four outputs -- one shared-memory exchange (16 stores, 16 loads, two barriers) less.

@@ -355,9 +355,9 @@ struct HostFeed {
     cudaStream_t copy = nullptr;
     std::vector<cudaEvent_t> ev;
     cudaEvent_t start = nullptr;
+    std::mutex mu;            // one feed at a time per device (the copy stream and its events are shared)
 };
 static HostFeed g_feed[64];
-static std::mutex g_feed_mu;
 }  // namespace t21
 
 int t21_ps_binned_host(const t21_plan* p, const void* x_host, int host_is_pinned, int subtract_mean, const t21_binspec* spec,
@@ -387,8 +387,8 @@ int t21_ps_binned_host(const t21_plan* p, const void* x_host, int host_is_pinned
     if (gp > p->n[0]) gp = p->n[0];
     const int ngroups = (p->n[0] + gp - 1) / gp;
 
-    std::lock_guard<std::mutex> lock(g_feed_mu);
     HostFeed& F = g_feed[p->device];
+    std::lock_guard<std::mutex> lock(F.mu);
     if (!F.copy) {
         T21_CUDA_OK(cudaStreamCreateWithFlags(&F.copy, cudaStreamNonBlocking));
         T21_CUDA_OK(cudaEventCreateWithFlags(&F.start, cudaEventDisableTiming));
@@ -572,6 +572,9 @@ int t21_build_pencil_segments(const t21_binspec* spec, uint32_t* out, int stride
     if (!spec || !out || !max_segments_dev) { set_error("null argument to t21_build_pencil_segments"); return T21_EINVAL; }
     if (stride != 8 && stride != 16 && stride != 32) { set_error("segment stride must be 8, 16 or 32"); return T21_EINVAL; }
     if (spec->zero_idx[0] != 0 || spec->n[0] < 2 || spec->n[0] >= 65535) { set_error("segment tables need a spec in FFT index order"); return T21_EINVAL; }
+    if (!spec->thr || !spec->k_lut || !spec->tab_s[0] || !spec->tab_s[1] || !spec->tab_s[2] || !spec->tab_sf[0] || !spec->tab_sf[1] || !spec->tab_sf[2]) {
+        set_error("segment tables are built from a complete bin spec (thresholds, look-up and k tables)"); return T21_EINVAL;
+    }
     if (spec->nk * (spec->nmu > 0 ? spec->nmu : 1) >= 65535) { set_error("too many bins for a segment table"); return T21_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
     T21_CUDA_OK(cudaMemsetAsync(max_segments_dev, 0, 2 * sizeof(int), st));

@@ -214,6 +214,17 @@ def test_warp_per_pencil_x_pass_nx512(t2c, shape):
         cm_o, _, _, cn_o = ps_oracle.cross_power_spectrum_mu(x, y, los_axis=los, mubins=4, kbins=5, box_dims=box, return_n_modes=True)
         assert np.array_equal(cn, cn_o)
         np.testing.assert_allclose(cm, cm_o, rtol=1e-5, atol=1e-5 * np.nanmax(np.abs(pm_o)), equal_nan=True)
+        for excl in (True, False):                       # signed mu: four tables (own / twin bins for kx >= 0 and kx < 0)
+            kw = dict(los_axis=los, mubins=6, kbins=5, box_dims=box, return_n_modes=True, exclude_zero_modes=excl, absolute_mus=False)
+            pm, _, _, nmu = t2c.power_spectrum_mu(x, **kw)
+            pm_o, _, _, nmu_o = ps_oracle.power_spectrum_mu(x, **kw)
+            assert np.array_equal(nmu, nmu_o)
+            np.testing.assert_allclose(pm, pm_o, rtol=1e-5, equal_nan=True)
+        cm, _, _, cn = t2c.cross_power_spectrum_mu(x, y, los_axis=los, mubins=4, kbins=5, box_dims=box, return_n_modes=True, absolute_mus=False)
+        cm_o, _, _, cn_o = ps_oracle.cross_power_spectrum_mu(x, y, los_axis=los, mubins=4, kbins=5, box_dims=box, return_n_modes=True,
+                                                             absolute_mus=False)
+        assert np.array_equal(cn, cn_o)
+        np.testing.assert_allclose(cm, cm_o, rtol=1e-5, atol=1e-5 * np.nanmax(np.abs(pm_o)), equal_nan=True)
 
 
 @pytest.mark.parametrize("shape", [(1024, 16, 32), (1024, 32, 16), (512, 16, 32)])

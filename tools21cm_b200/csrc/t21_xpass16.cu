@@ -12,8 +12,8 @@
 //     v[k'] = X[q + 32 k'] -- the layout the range walk of the nx = 1024 kernel works on, with 8 steps instead of 16;
 //   * cross spectra keep the first field's 16 results in registers (32 of them) while the second field is transformed:
 //     Re(F1 conj F2) per mode, then the same walk.  (At nx = 1024 the two fields' 64 values per lane do not fit.)
-// Bins come from the pencil segment table (t21_build_pencil_segments); specs without one, pencils with overflow marks and
-// signed mu take the CTA-per-tile kernel.  BASELINE configs 2 / 3 (512^3 cross spectra) run here.
+// Bins come from the pencil segment table(s) (t21_build_pencil_segments; four for signed mu); specs without one and tables
+// with overflow marks take the CTA-per-tile kernel.  BASELINE configs 2 / 3 (512^3 cross spectra) run here.
 #include <string.h>
 #include "t21_launch.cuh"
 #include "t21_tma.cuh"
@@ -41,6 +41,8 @@ struct Params {
     double ntot;
     const unsigned* seg;
     int seg_stride;
+    int seg_ntab;             // 1, or 4 for signed mu (own / twin bins for kx >= 0 and kx < 0)
+    long long seg_pencils;
 };
 
 // tile buffers: one field keeps TWO tiles in shared memory (the next one is requested as soon as every warp has read the
@@ -50,8 +52,9 @@ template <int NF> struct Bufs { static constexpr int N = NF == 1 ? 2 : 1; };
 
 #if T21_DEVICE_CODE
 
-// close-range walk on 16 powers per lane: steps k = 0..7 hold |kx| = 32k + lane (pw[k]) and 32k + 32 - lane (pw[15 - k])
-template <class Hist>
+// close-range walk on 16 powers per lane: steps k = 0..7 hold |kx| = 32k + lane (pw[k]) and 32k + 32 - lane (pw[15 - k]).
+// LO / HI: take the kx >= 0 / the kx < 0 half (signed mu walks them separately, with the own and the twin tables).
+template <bool LO, bool HI, class Hist>
 __device__ __forceinline__ void walk16(const float* pw, int lane, unsigned ent, float wf, unsigned wt, float* __restrict__ strip, Hist& hist) {
     const unsigned pos = ent >> 16, binp1 = ent & 0xFFFFu;
     const unsigned S = (unsigned)__popc(__ballot_sync(0xffffffffu, pos != 0xFFFFu));
@@ -66,7 +69,7 @@ __device__ __forceinline__ void walk16(const float* pw, int lane, unsigned ent, 
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
         const unsigned a = __shfl_sync(0xffffffffu, pos, j);
         const int bin = (int)__shfl_sync(0xffffffffu, binp1, j) - 1;
-        if (lane == 0 && bin >= 0) hist.add(bin, (double)(t * wf), segment_modes(true, true, a, b, (unsigned)(NX / 2)) * wt);
+        if (lane == 0 && bin >= 0) hist.add(bin, (double)(t * wf), segment_modes(LO, HI, a, b, (unsigned)(NX / 2)) * wt);
     };
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -77,12 +80,12 @@ __device__ __forceinline__ void walk16(const float* pw, int lane, unsigned ent, 
             const int k = half * 4 + kk;
             if ((mixed >> k) & 1u) {
                 float* d = strip + slot * 96u + lane;
-                d[0] = run; d[32] = pw[k]; d[64] = pw[15 - k];
+                d[0] = run; d[32] = LO ? pw[k] : 0.f; d[64] = HI ? pw[15 - k] : 0.f;
                 run = 0.f;
                 ks |= (unsigned)k << (4u * slot);
                 ++slot;
             } else {
-                run += pw[k] + pw[15 - k];
+                run += (LO ? pw[k] : 0.f) + (HI ? pw[15 - k] : 0.f);
             }
         }
 #pragma unroll 1
@@ -182,8 +185,13 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap* map0, const CUtenso
         const unsigned chunk = (unsigned)tile / (unsigned)p.ny;
         const int iy = (int)((unsigned)tile - chunk * (unsigned)p.ny) + p.iy0;
         const int iz = (int)chunk * WZ + warp;
-        unsigned ent = kSegSentinel;
-        if (lane < p.seg_stride && iz < p.nzh) ent = ldg(p.seg + ((size_t)iy * p.nzh + iz) * p.seg_stride + lane);
+        unsigned ent = kSegSentinel, ent1 = kSegSentinel, ent2 = kSegSentinel, ent3 = kSegSentinel;
+        if (lane < p.seg_stride && iz < p.nzh) {
+            const unsigned* e = p.seg + ((size_t)iy * p.nzh + iz) * p.seg_stride + lane;
+            const size_t ts = (size_t)p.seg_pencils * p.seg_stride;
+            ent = ldg(e);
+            if (p.seg_ntab == 4) { ent1 = ldg(e + ts); ent2 = ldg(e + 2 * ts); ent3 = ldg(e + 3 * ts); }
+        }
         cx<float> a[NF][NV];
         mbar_wait(bar + b, (parity >> b) & 1u);
         parity ^= 1u << b;
@@ -228,7 +236,15 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap* map0, const CUtenso
         const bool has_twin = (iz != 0) && (iz != p.nz - iz);
         const unsigned wt = has_twin ? 2u : 1u;
         __syncwarp();
-        walk16(pw, lane, ent, (float)wt, wt, reinterpret_cast<float*>(xb), hist);
+        float* strip = reinterpret_cast<float*>(xb);
+        if (p.seg_ntab == 1) {
+            walk16<true, true>(pw, lane, ent, (float)wt, wt, strip, hist);
+        } else {
+            walk16<true, false>(pw, lane, ent, 1.f, 1u, strip, hist);
+            walk16<false, true>(pw, lane, ent1, 1.f, 1u, strip, hist);
+            walk16<true, false>(pw, lane, ent2, 1.f, 1u, strip, hist);
+            walk16<false, true>(pw, lane, ent3, 1.f, 1u, strip, hist);
+        }
     }
 }
 
@@ -282,6 +298,8 @@ static int launch(XArgs& a, cudaStream_t st) {
     p.ntot = a.ntot;
     p.seg = a.bins->seg_tab;
     p.seg_stride = a.bins->seg_stride;
+    p.seg_ntab = a.bins->seg_ntab;
+    p.seg_pencils = (long long)a.bins->n[1] * a.nzh;
     CUtensorMap map0, map1;
     if (int rc = make_wmap_f32(&map0, a.w[0], nxs, a.ny, a.pitch / WZ, NX / nxs, p.box_rows, 4)) return rc;
     if (int rc = make_wmap_f32(&map1, NF == 2 ? a.w[1] : a.w[0], nxs, a.ny, a.pitch / WZ, NX / nxs, p.box_rows, 4)) return rc;
@@ -310,7 +328,7 @@ bool xpass16_applicable(int dtype, const XArgs& a) {
         return false;
     const t21_binspec& B = *a.bins;
     const bool is_signed = B.nmu > 0 && !B.absolute_mus;
-    return B.seg_tab != nullptr && B.seg_ntab == 1 && B.seg_overflow == 0 && !is_signed && a.nbins <= 128;
+    return B.seg_tab != nullptr && B.seg_ntab == (is_signed ? 4 : 1) && B.seg_overflow == 0 && a.nbins <= 128;
 }
 
 int launch_xpass16_bin(XArgs& a, cudaStream_t st) {
